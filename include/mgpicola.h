@@ -1,0 +1,183 @@
+/*
+ * mgpicola.h -- C ABI of the B200-native COLA particle-mesh force path.
+ *
+ * This is the drop-in boundary for MG-PICOLA's C driver.  The reference has no plugin
+ * mechanism: its "operator API" is a set of argument-less C functions that talk through the
+ * globals of src/vars.h.  Every entry point below names the reference function (file:line
+ * under the reference's src/) whose work it takes over; adapter/auxPM_cuda.c keeps the
+ * reference names and fills these calls from the reference globals.
+ *
+ * Conventions
+ *  - plain C types only; every function returns 0 on success or a negative mgp_status, and
+ *    mgp_last_error() gives the text (the driver maps non-zero to FatalError, auxPM.c:668).
+ *  - the library owns all device memory (particles, grids, cuFFT plans, NCCL communicator).
+ *    Host pointers passed in are read during the call only.
+ *  - every call is synchronous with respect to its host-visible outputs.
+ *  - there is no CPU fallback: without a CUDA device mgp_create fails.
+ *  - one context per process per GPU; with nranks > 1 the x-slab decomposition of
+ *    2LPT.c:47-113 is used (rank r owns mesh planes [r*N/P, (r+1)*N/P)).
+ */
+#ifndef MGPICOLA_H
+#define MGPICOLA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mgp_ctx mgp_ctx;
+
+enum mgp_status {
+  MGP_OK = 0,
+  MGP_ERR_INVALID = -1,      /* bad argument / configuration */
+  MGP_ERR_CUDA = -2,         /* CUDA, cuFFT or NCCL failure */
+  MGP_ERR_BUFFER = -3,       /* particle buffer overflow: "increase Buffer" (auxPM.c:178-199, 250-254) */
+  MGP_ERR_STATE = -4         /* call order violated (e.g. Kick before GetDisplacements) */
+};
+
+/* modified-gravity model == the reference's compile-time -D choice (Makefile:61-106) */
+enum mgp_model {
+  MGP_MODEL_NONE = 0,        /* modified_gravity_active = 0 */
+  MGP_MODEL_FOFR = 1,        /* FOFRGRAVITY / MBETAMODEL: potential screening, mg.h:147-189 */
+  MGP_MODEL_DGP = 2,         /* DGPGRAVITY: density screening + smoothing filter, mg.h:197-260 */
+  MGP_MODEL_GEFF = 3         /* BRANSDICKE-like: delta_k *= Geff(a), mg.h:127-137 */
+};
+
+enum mgp_deposit_mode {
+  MGP_DEPOSIT_ATOMIC = 0,    /* cell-sorted particles, warp-aggregated global reductions */
+  MGP_DEPOSIT_TILE = 1,      /* cell-sorted particles, shared-memory tile accumulation */
+  MGP_DEPOSIT_DETERMINISTIC = 2  /* cell-sorted, per-cell ordered gather: bitwise reproducible */
+};
+
+enum mgp_grid_id {
+  MGP_GRID_DENSITY = 0,      /* density / P3D          (vars.h:98-114) */
+  MGP_GRID_FORCE_X = 1,      /* N11 / FN11 */
+  MGP_GRID_FORCE_Y = 2,      /* N12 / FN12 */
+  MGP_GRID_FORCE_Z = 3,      /* N13 / FN13 */
+  MGP_GRID_MG_ONE = 4,       /* mgarray_one (vars.h:181-186) */
+  MGP_GRID_MG_TWO = 5        /* mgarray_two */
+};
+
+typedef struct mgp_config {
+  int nmesh;                 /* Nmesh */
+  int nsample;               /* Nsample */
+  double box;                /* Box (Mpc/h) */
+  double buffer;             /* Buffer: particle capacity = ceil(NumPart0 * buffer) (main.c:228) */
+  double omega;              /* Omega */
+  int use_cola;              /* UseCOLA */
+  int model;                 /* enum mgp_model */
+  int include_screening;     /* include_screening */
+  int grid_bytes;            /* 8 = double grids (reference default), 4 = -DSINGLE_PRECISION */
+  int deposit_mode;          /* enum mgp_deposit_mode */
+  int sort_particles;        /* 1: re-sort particles by mesh cell every step (recommended) */
+  int rank, nranks;          /* slab decomposition: ThisTask / NTask */
+  int device;                /* CUDA device ordinal */
+  const void *nccl_unique_id;/* 128-byte ncclUniqueId shared by all ranks (NULL if nranks == 1) */
+} mgp_config;
+
+/* P(k) binning == the pofk_* parameters (user_defined_functions.h:303-337) */
+typedef struct mgp_pofk_config {
+  int nbins;
+  int bintype;               /* 0 linear, 1 log */
+  int subtract_shotnoise;
+  double kmin, kmax;         /* h/Mpc */
+} mgp_pofk_config;
+
+/* Per-step scalars the reference evaluates per cell / per mode on the host
+ * (SURVEY.md section 8(b)); the adapter computes them once per step with the reference's own
+ * functions and passes numbers. */
+typedef struct mgp_step_scalars {
+  double a;                  /* aexp_global */
+  /* MGP_MODEL_FOFR (mg.h:21-116, user_defined_functions.h:725-750) */
+  double phi_crit;           /* screening_factor_potential's phicrit(a) */
+  double coupling;           /* coupling_function(a) */
+  double massterm2;          /* a^2 m^2(a) / (2 pi INVERSE_H0_MPCH / Box)^2 (mg.h:80) */
+  /* MGP_MODEL_DGP (mg.h:197-309, user_defined_functions.h:757-773) */
+  double dgp_fac0;           /* 8/9 Omega (rcH0/beta_DGP(a))^2 */
+  double rsmooth;            /* Rsmooth_global (Mpc/h) */
+  /* MGP_MODEL_GEFF */
+  double geff;               /* GeffoverG(a, 0) */
+  int compute_pofk;          /* pofk_compute_every_step: bin P(k) of the CDM density this step */
+} mgp_step_scalars;
+
+const char *mgp_last_error(void);
+int mgp_version(void);
+/* fills 128 bytes with a fresh ncclUniqueId (rank 0 calls this and broadcasts it) */
+int mgp_nccl_unique_id(void *out128);
+
+/* replaces initialize_ffts + initialize_parts (2LPT.c:47-176) and the per-step malloc/plan churn
+ * of MEMORY_MODE (auxPM.c:46-51, 61-71, 80-102): everything is allocated and planned once. */
+int mgp_create(const mgp_config *cfg, mgp_ctx **out);
+int mgp_destroy(mgp_ctx *ctx);
+
+/* slab layout as the reference globals: Local_nx, Local_x_start, Local_np, Local_p_start, NumPart */
+int mgp_get_layout(mgp_ctx *ctx, int *local_nx, int *local_x_start, int *local_np,
+                   int *local_p_start, uint64_t *numpart);
+
+/* ---- particle store (struct part_data, vars.h:293-321; GPU-resident SoA) ---- */
+/* load n particles of this rank from host arrays laid out [n][3] (D2, id may be NULL) */
+int mgp_upload_particles(mgp_ctx *ctx, uint64_t n, const float *pos, const float *vel,
+                         const float *D, const float *D2, const uint64_t *id);
+/* copy back for Output (main.c:792-1061); any pointer may be NULL; arrays sized NumPart */
+int mgp_download_particles(mgp_ctx *ctx, float *pos, float *vel, float *D, float *D2, uint64_t *id);
+/* Disp[3][NumPart] of MtoParticles (auxPM.c:605-630), as [n][3] */
+int mgp_download_disp(mgp_ctx *ctx, float *disp);
+
+/* ---- the per-step force path ---- */
+/* MoveParticles (auxPM.c:108-275): slab ownership + migration; also (re)sorts by cell */
+int mgp_move_particles(mgp_ctx *ctx);
+/* PtoMesh (auxPM.c:280-432): CIC deposit, halo add, MG copy, r2c; optional P(k) */
+int mgp_ptomesh(mgp_ctx *ctx, const mgp_step_scalars *s);
+/* ComputeFifthForce (user_defined_functions.h:687-719 -> mg.h) */
+int mgp_compute_fifth_force(mgp_ctx *ctx, const mgp_step_scalars *s);
+/* Forces (auxPM.c:437-555): Green's function + gradient, 3 c2r, force halo */
+int mgp_forces(mgp_ctx *ctx);
+/* MtoParticles (auxPM.c:560-644): trilinear gather; returns sumDxyz (already / TotNumPart) */
+int mgp_mtoparticles(mgp_ctx *ctx, double sumDxyz[3]);
+/* GetDisplacements (auxPM.c:37-103) = the five calls above */
+int mgp_get_displacements(mgp_ctx *ctx, const mgp_step_scalars *s, double sumDxyz[3]);
+
+/* Kick particle loop (main.c:707-739).  dda = Sphi(...), ddDddy/ddD2ddy = growth_ddDddy(A),
+ * growth_ddD2ddy(A) stay on the host.  sumDxyz in (0 on the second kick of an output step,
+ * main.c:566-569); sumxyz out (mean velocity, / TotNumPart). */
+int mgp_kick(mgp_ctx *ctx, double A, double dda, double ddDddy, double ddD2ddy,
+             const double sumDxyz[3], double sumxyz[3]);
+/* Drift particle loop (main.c:762-783).  dyyy = Sq(...), deltaD = growth_D(AFF)-Di, ... */
+int mgp_drift(mgp_ctx *ctx, double dyyy, double deltaD, double deltaD2, const double sumxyz[3]);
+
+/* ---- P(k) (compute_pofk.c:71-271) ---- */
+int mgp_set_pofk_config(mgp_ctx *ctx, const mgp_pofk_config *pc);
+/* bins the k-space density currently in MGP_GRID_DENSITY; arrays sized mgp_pofk_nbins() */
+int mgp_pofk_nbins(mgp_ctx *ctx);
+int mgp_compute_power_spectrum(mgp_ctx *ctx, double *pofk, double *kmean, double *nmodes);
+/* result of the in-step binning requested through mgp_step_scalars.compute_pofk */
+int mgp_get_step_power_spectrum(mgp_ctx *ctx, double *pofk, double *kmean, double *nmodes);
+
+/* ---- grid access (tests, write_grid_to_file auxPM.c:757-813) ---- */
+/* local slab incl. ghost plane: (Local_nx+1) * Nmesh * 2*(Nmesh/2+1) values of grid_bytes */
+size_t mgp_grid_local_values(mgp_ctx *ctx);
+int mgp_download_grid(mgp_ctx *ctx, int grid_id, void *host);
+int mgp_upload_grid(mgp_ctx *ctx, int grid_id, const void *host);
+/* in-place transforms of one grid (my_fftw_execute on r2c / c2r plans, wrappers.c:42-46) */
+int mgp_fft_r2c(mgp_ctx *ctx, int grid_id);
+int mgp_fft_c2r(mgp_ctx *ctx, int grid_id);
+
+/* ---- instrumentation ---- */
+/* number of kernels this library has launched on ctx since creation / last reset */
+uint64_t mgp_launch_count(mgp_ctx *ctx, int reset);
+/* CUDA-event time (ms) accumulated per phase since last reset; names mirror timer.h
+ * (MoveParticles, PtoMesh, FFT, ComputeFifthForce, Forces, MtoParticles, Kick, Drift, Pofk) */
+int mgp_phase_count(void);
+const char *mgp_phase_name(int i);
+int mgp_phase_times_ms(mgp_ctx *ctx, double *ms, uint64_t *calls, int reset);
+/* enable/disable per-phase event timing (adds synchronisation; off by default) */
+int mgp_set_phase_timing(mgp_ctx *ctx, int on);
+/* the stream all work is issued on (cudaStream_t), for external event timing */
+void *mgp_stream(mgp_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,292 @@
+"""mgpicola_b200 -- Python host side of the B200-native COLA particle-mesh library.
+
+The product is the C-ABI shared library built from csrc/ (include/mgpicola.h).  This module is the
+ctypes binding used by the tests and bench.py; its `PM` class mirrors the reference's operator
+interface for the path (the argument-less C functions of src/proto.h:45-48, 211-215 that talk
+through globals) with the same names and argument meaning:
+
+    MoveParticles / PtoMesh / ComputeFifthForce / Forces / MtoParticles / GetDisplacements
+    Kick / Drift / compute_power_spectrum
+
+There is no CPU fallback: importing works anywhere (so that CPU-only tests can check the exported
+symbols), but constructing a `PM` without the built library or without a CUDA device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmgpicola_cuda.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mgpicola.h")
+
+MODEL_NONE, MODEL_FOFR, MODEL_DGP, MODEL_GEFF = 0, 1, 2, 3
+DEPOSIT_ATOMIC, DEPOSIT_TILE, DEPOSIT_DETERMINISTIC = 0, 1, 2
+GRID_DENSITY, GRID_FORCE_X, GRID_FORCE_Y, GRID_FORCE_Z, GRID_MG_ONE, GRID_MG_TWO = range(6)
+
+
+class MgpError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("mgpicola error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [("nmesh", C.c_int), ("nsample", C.c_int), ("box", C.c_double), ("buffer", C.c_double),
+                ("omega", C.c_double), ("use_cola", C.c_int), ("model", C.c_int), ("include_screening", C.c_int),
+                ("grid_bytes", C.c_int), ("deposit_mode", C.c_int), ("sort_particles", C.c_int),
+                ("rank", C.c_int), ("nranks", C.c_int), ("device", C.c_int), ("nccl_unique_id", C.c_void_p)]
+
+
+class PofkConfig(C.Structure):
+    _fields_ = [("nbins", C.c_int), ("bintype", C.c_int), ("subtract_shotnoise", C.c_int),
+                ("kmin", C.c_double), ("kmax", C.c_double)]
+
+
+class StepScalars(C.Structure):
+    _fields_ = [("a", C.c_double), ("phi_crit", C.c_double), ("coupling", C.c_double), ("massterm2", C.c_double),
+                ("dgp_fac0", C.c_double), ("rsmooth", C.c_double), ("geff", C.c_double), ("compute_pofk", C.c_int)]
+
+
+_lib = None
+
+
+def load_library(path=None):
+    """dlopen the C-ABI library.  Raises (never falls back) when it is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise ImportError("libmgpicola_cuda.so not built at %s -- run `python -c 'import __graft_entry__ as g; g.build()'`" % p)
+    L = C.CDLL(p)
+    L.mgp_last_error.restype = C.c_char_p
+    L.mgp_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+    L.mgp_destroy.argtypes = [C.c_void_p]
+    L.mgp_nccl_unique_id.argtypes = [C.c_void_p]
+    L.mgp_get_layout.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4 + [C.POINTER(C.c_uint64)]
+    fp, dp, up = C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_uint64)
+    L.mgp_upload_particles.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mgp_download_particles.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mgp_download_disp.argtypes = [C.c_void_p, C.c_void_p]
+    L.mgp_move_particles.argtypes = [C.c_void_p]
+    L.mgp_ptomesh.argtypes = [C.c_void_p, C.POINTER(StepScalars)]
+    L.mgp_compute_fifth_force.argtypes = [C.c_void_p, C.POINTER(StepScalars)]
+    L.mgp_forces.argtypes = [C.c_void_p]
+    L.mgp_mtoparticles.argtypes = [C.c_void_p, dp]
+    L.mgp_get_displacements.argtypes = [C.c_void_p, C.POINTER(StepScalars), dp]
+    L.mgp_kick.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, dp, dp]
+    L.mgp_drift.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, dp]
+    L.mgp_set_pofk_config.argtypes = [C.c_void_p, C.POINTER(PofkConfig)]
+    L.mgp_pofk_nbins.argtypes = [C.c_void_p]
+    L.mgp_compute_power_spectrum.argtypes = [C.c_void_p, dp, dp, dp]
+    L.mgp_get_step_power_spectrum.argtypes = [C.c_void_p, dp, dp, dp]
+    L.mgp_grid_local_values.argtypes = [C.c_void_p]
+    L.mgp_grid_local_values.restype = C.c_size_t
+    L.mgp_download_grid.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.mgp_upload_grid.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.mgp_fft_r2c.argtypes = [C.c_void_p, C.c_int]
+    L.mgp_fft_c2r.argtypes = [C.c_void_p, C.c_int]
+    L.mgp_launch_count.argtypes = [C.c_void_p, C.c_int]
+    L.mgp_launch_count.restype = C.c_uint64
+    L.mgp_phase_name.argtypes = [C.c_int]
+    L.mgp_phase_name.restype = C.c_char_p
+    L.mgp_phase_times_ms.argtypes = [C.c_void_p, dp, up, C.c_int]
+    L.mgp_set_phase_timing.argtypes = [C.c_void_p, C.c_int]
+    L.mgp_stream.argtypes = [C.c_void_p]
+    L.mgp_stream.restype = C.c_void_p
+    if path is None:
+        _lib = L
+    return L
+
+
+def declared_symbols(header=HEADER_PATH):
+    """Names of all functions include/mgpicola.h declares (used by the CPU-side symbol test)."""
+    import re
+    txt = open(header).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(mgp_[a-z0-9_]+)\s*\(", txt)))
+
+
+def nccl_unique_id():
+    L = load_library()
+    buf = C.create_string_buffer(128)
+    rc = L.mgp_nccl_unique_id(buf)
+    if rc:
+        raise MgpError(rc, L.mgp_last_error().decode())
+    return buf.raw
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+class PM:
+    """One GPU-resident particle-mesh context (one per process per GPU)."""
+
+    def __init__(self, nmesh, nsample, box, omega=0.267, use_cola=1, model=MODEL_NONE, include_screening=0,
+                 grid_bytes=8, deposit_mode=DEPOSIT_DETERMINISTIC, sort_particles=1, buffer=1.5, rank=0, nranks=1,
+                 device=0, nccl_id=None):
+        self.L = load_library()
+        self._idbuf = C.create_string_buffer(nccl_id, 128) if nccl_id is not None else None
+        self.cfg = Config(nmesh, nsample, box, buffer, omega, use_cola, model, include_screening, grid_bytes,
+                          deposit_mode, sort_particles, rank, nranks, device,
+                          C.cast(self._idbuf, C.c_void_p) if self._idbuf is not None else None)
+        self.ctx = C.c_void_p()
+        self._ck(self.L.mgp_create(C.byref(self.cfg), C.byref(self.ctx)))
+        self.N, self.Ns, self.box = nmesh, nsample, box
+        self.gdtype = np.float32 if grid_bytes == 4 else np.float64
+        self.cdtype = np.complex64 if grid_bytes == 4 else np.complex128
+        lay = [C.c_int() for _ in range(4)]
+        npart = C.c_uint64()
+        self._ck(self.L.mgp_get_layout(self.ctx, *[C.byref(x) for x in lay], C.byref(npart)))
+        self.local_nx, self.local_x_start, self.local_np, self.local_p_start = [x.value for x in lay]
+        self.sumDxyz = np.zeros(3)
+        self.sumxyz = np.zeros(3)
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise MgpError(rc, self.L.mgp_last_error().decode())
+
+    def close(self):
+        if getattr(self, "ctx", None) is not None and self.ctx:
+            self.L.mgp_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def numpart(self):
+        n = C.c_uint64()
+        self._ck(self.L.mgp_get_layout(self.ctx, None, None, None, None, C.byref(n)))
+        return n.value
+
+    # ---- particles ----
+    def upload_particles(self, pos, vel=None, D=None, D2=None, ids=None):
+        pos, vel, D, D2 = _f32(pos), _f32(vel), _f32(D), _f32(D2)
+        ids = None if ids is None else np.ascontiguousarray(ids, dtype=np.uint64)
+        self._ck(self.L.mgp_upload_particles(self.ctx, pos.shape[0], _ptr(pos), _ptr(vel), _ptr(D), _ptr(D2), _ptr(ids)))
+
+    def download_particles(self, want=("pos", "vel", "D", "D2", "id")):
+        n = self.numpart
+        out = {}
+        for k in ("pos", "vel", "D", "D2"):
+            out[k] = np.empty((n, 3), np.float32) if k in want else None
+        out["id"] = np.empty(n, np.uint64) if "id" in want else None
+        self._ck(self.L.mgp_download_particles(self.ctx, _ptr(out["pos"]), _ptr(out["vel"]), _ptr(out["D"]),
+                                               _ptr(out["D2"]), _ptr(out["id"])))
+        return {k: v for k, v in out.items() if v is not None}
+
+    def download_disp(self):
+        d = np.empty((self.numpart, 3), np.float32)
+        self._ck(self.L.mgp_download_disp(self.ctx, _ptr(d)))
+        return d
+
+    # ---- the reference's per-step functions ----
+    @staticmethod
+    def scalars(a=1.0, phi_crit=0.0, coupling=0.0, massterm2=0.0, dgp_fac0=0.0, rsmooth=0.0, geff=1.0, compute_pofk=0):
+        return StepScalars(a, phi_crit, coupling, massterm2, dgp_fac0, rsmooth, geff, compute_pofk)
+
+    def MoveParticles(self):
+        self._ck(self.L.mgp_move_particles(self.ctx))
+
+    def PtoMesh(self, s=None):
+        self._ck(self.L.mgp_ptomesh(self.ctx, C.byref(s) if s is not None else None))
+
+    def ComputeFifthForce(self, s):
+        self._ck(self.L.mgp_compute_fifth_force(self.ctx, C.byref(s)))
+
+    def Forces(self):
+        self._ck(self.L.mgp_forces(self.ctx))
+
+    def MtoParticles(self):
+        out = (C.c_double * 3)()
+        self._ck(self.L.mgp_mtoparticles(self.ctx, out))
+        self.sumDxyz = np.array(out[:])
+        return self.sumDxyz
+
+    def GetDisplacements(self, s=None):
+        out = (C.c_double * 3)()
+        self._ck(self.L.mgp_get_displacements(self.ctx, C.byref(s) if s is not None else None, out))
+        self.sumDxyz = np.array(out[:])
+        return self.sumDxyz
+
+    def Kick(self, A, dda, ddDddy, ddD2ddy, sumDxyz=None):
+        sd = (C.c_double * 3)(*(self.sumDxyz if sumDxyz is None else sumDxyz))
+        out = (C.c_double * 3)()
+        self._ck(self.L.mgp_kick(self.ctx, A, dda, ddDddy, ddD2ddy, sd, out))
+        self.sumxyz = np.array(out[:])
+        return self.sumxyz
+
+    def Drift(self, dyyy, deltaD, deltaD2, sumxyz=None):
+        sv = (C.c_double * 3)(*(self.sumxyz if sumxyz is None else sumxyz))
+        self._ck(self.L.mgp_drift(self.ctx, dyyy, deltaD, deltaD2, sv))
+
+    # ---- P(k) ----
+    def set_pofk(self, nbins, bintype, subtract_shotnoise, kmin, kmax):
+        pc = PofkConfig(nbins, bintype, subtract_shotnoise, kmin, kmax)
+        self._ck(self.L.mgp_set_pofk_config(self.ctx, C.byref(pc)))
+
+    def _pofk_out(self, fn):
+        nb = self.L.mgp_pofk_nbins(self.ctx)
+        if nb < 0:
+            raise MgpError(nb, "P(k) binning not configured")
+        p, k, n = np.zeros(nb), np.zeros(nb), np.zeros(nb)
+        dp = C.POINTER(C.c_double)
+        self._ck(fn(self.ctx, p.ctypes.data_as(dp), k.ctypes.data_as(dp), n.ctypes.data_as(dp)))
+        return p, k, n
+
+    def compute_power_spectrum(self):
+        return self._pofk_out(self.L.mgp_compute_power_spectrum)
+
+    def step_power_spectrum(self):
+        return self._pofk_out(self.L.mgp_get_step_power_spectrum)
+
+    # ---- grids ----
+    def download_grid(self, gid):
+        n = self.L.mgp_grid_local_values(self.ctx)
+        a = np.empty(n, self.gdtype)
+        self._ck(self.L.mgp_download_grid(self.ctx, gid, _ptr(a)))
+        return a.reshape(self.local_nx + 1, self.N, 2 * (self.N // 2 + 1))
+
+    def download_grid_k(self, gid):
+        """k-space view [kx][ky][kz] (single rank)."""
+        a = self.download_grid(gid)
+        return a.reshape(-1).view(self.cdtype).reshape(self.local_nx + 1, self.N, self.N // 2 + 1)[: self.local_nx]
+
+    def upload_grid(self, gid, arr):
+        a = np.ascontiguousarray(arr, dtype=self.gdtype).reshape(-1)
+        assert a.size == self.L.mgp_grid_local_values(self.ctx)
+        self._ck(self.L.mgp_upload_grid(self.ctx, gid, _ptr(a)))
+
+    def fft_r2c(self, gid):
+        self._ck(self.L.mgp_fft_r2c(self.ctx, gid))
+
+    def fft_c2r(self, gid):
+        self._ck(self.L.mgp_fft_c2r(self.ctx, gid))
+
+    # ---- instrumentation ----
+    def launch_count(self, reset=False):
+        return int(self.L.mgp_launch_count(self.ctx, int(reset)))
+
+    def set_phase_timing(self, on):
+        self._ck(self.L.mgp_set_phase_timing(self.ctx, int(on)))
+
+    def phase_times(self, reset=False):
+        n = self.L.mgp_phase_count()
+        ms = (C.c_double * n)()
+        calls = (C.c_uint64 * n)()
+        self._ck(self.L.mgp_phase_times_ms(self.ctx, ms, calls, int(reset)))
+        return {self.L.mgp_phase_name(i).decode(): (ms[i], int(calls[i])) for i in range(n)}
+
+    @property
+    def stream(self):
+        return self.L.mgp_stream(self.ctx)

@@ -1,0 +1,441 @@
+// extern "C" surface (include/mgpicola.h) and the per-step orchestration that mirrors
+// GetDisplacements (auxPM.c:37-103).
+#include "common.cuh"
+
+#include <cmath>
+#include <mutex>
+
+namespace mgp {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string &m) { g_last_error = m; }
+
+static const char *kPhaseNames[PH_COUNT] = {"MoveParticles", "PtoMesh", "FFT", "ComputeFifthForce", "Forces",
+                                            "MtoParticles", "Kick", "Drift", "Pofk", "Sort", "Comm"};
+
+static bool needs_mg_arrays(const Ctx &c) { return c.cfg.model == MGP_MODEL_FOFR || c.cfg.model == MGP_MODEL_DGP; }
+
+static Ctx *create(const mgp_config *cfg) {
+  REQUIRE(cfg != nullptr, MGP_ERR_INVALID, "mgp_create: cfg is NULL");
+  REQUIRE(cfg->nmesh >= 2 && cfg->nmesh % 2 == 0, MGP_ERR_INVALID, "mgp_create: Nmesh must be even and >= 2");
+  REQUIRE(cfg->nsample >= 1, MGP_ERR_INVALID, "mgp_create: Nsample must be >= 1");
+  REQUIRE(cfg->box > 0, MGP_ERR_INVALID, "mgp_create: Box must be > 0");
+  REQUIRE(cfg->grid_bytes == 4 || cfg->grid_bytes == 8, MGP_ERR_INVALID, "mgp_create: grid_bytes must be 4 or 8");
+  REQUIRE(cfg->nranks >= 1 && cfg->rank >= 0 && cfg->rank < cfg->nranks, MGP_ERR_INVALID, "mgp_create: bad rank/nranks");
+  REQUIRE(cfg->model >= MGP_MODEL_NONE && cfg->model <= MGP_MODEL_GEFF, MGP_ERR_INVALID, "mgp_create: unknown model");
+  REQUIRE(cfg->deposit_mode >= 0 && cfg->deposit_mode <= 2, MGP_ERR_INVALID, "mgp_create: unknown deposit_mode");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  REQUIRE(e == cudaSuccess && ndev > 0, MGP_ERR_CUDA,
+          "mgp_create: no CUDA device (this library has no CPU fallback)");
+  REQUIRE(cfg->device >= 0 && cfg->device < ndev, MGP_ERR_INVALID, "mgp_create: bad device ordinal");
+  CK(cudaSetDevice(cfg->device));
+
+  Ctx *cp = new Ctx();
+  Ctx &c = *cp;
+  try {
+    c.cfg = *cfg;
+    c.cfg.nccl_unique_id = nullptr;
+    c.N = cfg->nmesh; c.NZ = cfg->nmesh / 2 + 1;
+    c.P = cfg->nranks; c.rank = cfg->rank;
+    c.gbytes = cfg->grid_bytes;
+    if (c.P > 1) {
+      REQUIRE(c.N % c.P == 0, MGP_ERR_INVALID, "mgp_create: nranks must divide Nmesh");
+      REQUIRE(cfg->nccl_unique_id != nullptr, MGP_ERR_INVALID, "mgp_create: nccl_unique_id required when nranks > 1");
+    }
+    // slab layout == fftw_mpi_local_size_3d default block distribution (2LPT.c:50)
+    const int block = (c.N + c.P - 1) / c.P;
+    c.x0 = c.rank * block;
+    c.nx = c.x0 >= c.N ? 0 : (c.N - c.x0 < block ? c.N - c.x0 : block);
+    REQUIRE(c.nx >= 1, MGP_ERR_INVALID, "mgp_create: rank owns no mesh planes");
+    c.ny_loc = c.N / c.P; c.y0 = c.rank * c.ny_loc;
+    c.left = (c.rank + c.P - 1) % c.P; c.right = (c.rank + 1) % c.P;
+    // particle planes (initialize_parts, 2LPT.c:118-176)
+    c.npl = 0; c.p0 = cfg->nsample;
+    for (int i = 0; i < cfg->nsample; i++) {
+      const int slab = (int) ((double) ((long long) i * c.N) / (double) cfg->nsample);
+      if (slab >= c.x0 && slab < c.x0 + c.nx) { c.npl++; if (i < c.p0) c.p0 = i; }
+    }
+    const double np0 = (double) c.npl * cfg->nsample * (double) cfg->nsample;
+    const double buf = (c.P == 1) ? 1.0 : (cfg->buffer >= 1.0 ? cfg->buffer : 1.0);
+    c.cap = (uint64_t) ceil(np0 * buf);
+    if (c.cap < 32) c.cap = 32;
+    REQUIRE(c.cap < ((uint64_t) 1 << 32), MGP_ERR_INVALID, "mgp_create: more than 2^32 particles on one rank: use more ranks");
+    c.plane_vals = (size_t) c.N * 2 * c.NZ;
+    c.grid_vals = (size_t) (c.nx + 1) * c.plane_vals;
+
+    CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    for (int d = 0; d < 4; d++) { CK(cudaEventCreate(&c.ev[d][0])); CK(cudaEventCreate(&c.ev[d][1])); }
+
+    CK(cudaMalloc(&c.grid[0], c.grid_bytes()));
+    CK(cudaMalloc(&c.force_block, 3 * c.grid_bytes()));
+    for (int a = 0; a < 3; a++) c.grid[1 + a] = (char *) c.force_block + (size_t) a * c.grid_bytes();
+    if (needs_mg_arrays(c)) {
+      CK(cudaMalloc(&c.grid[4], c.grid_bytes()));
+      CK(cudaMalloc(&c.grid[5], c.grid_bytes()));
+    }
+    CK(cudaMalloc(&c.halo_recv, c.plane_bytes()));
+    particles_alloc(c);
+    if (c.P > 1) {
+      ncclUniqueId id;
+      memcpy(&id, cfg->nccl_unique_id, sizeof(id));
+      CKNCCL(ncclCommInitRank(&c.comm, c.P, id, c.rank));
+    }
+    fft_setup(c);
+    CK(cudaStreamSynchronize(c.stream));
+  } catch (...) {
+    delete cp;   // leaks device memory of a half-built context only on a fatal configuration error
+    throw;
+  }
+  return cp;
+}
+
+static void destroy(Ctx *cp) {
+  if (!cp) return;
+  Ctx &c = *cp;
+  cudaSetDevice(c.cfg.device);
+  cudaStreamSynchronize(c.stream);
+  fft_teardown(c);
+  particles_free(c);
+  cudaFree(c.grid[0]); cudaFree(c.force_block); cudaFree(c.grid[4]); cudaFree(c.grid[5]); cudaFree(c.halo_recv);
+  if (c.comm) ncclCommDestroy(c.comm);
+  for (int d = 0; d < 4; d++) { cudaEventDestroy(c.ev[d][0]); cudaEventDestroy(c.ev[d][1]); }
+  cudaStreamDestroy(c.stream);
+  delete cp;
+}
+
+// ---- per-step path -------------------------------------------------------------------------
+
+static void move_particles(Ctx &c) {
+  {
+    PhaseTimer t(c, PH_MOVE);
+    if (c.P > 1) particles_migrate(c);
+  }
+  if (c.cfg.sort_particles && !c.sorted) particles_sort(c);
+}
+
+static void ptomesh(Ctx &c, const mgp_step_scalars *s) {
+  if (c.cfg.sort_particles && !c.sorted) particles_sort(c);
+  {
+    PhaseTimer t(c, PH_PTOMESH);
+    deposit_density(c);
+    halo_add_density(c, MGP_GRID_DENSITY);
+    if (needs_mg_arrays(c)) real_copy(c, MGP_GRID_MG_TWO, MGP_GRID_DENSITY, 1.0);   // CopyDensityArray (mg.h:381)
+  }
+  fft_r2c(c, MGP_GRID_DENSITY);
+  c.step_pofk_valid = false;
+  if (s && s->compute_pofk) {
+    const int nb = pofk_effective_nbins(c);
+    c.step_pofk.assign(nb, 0.0); c.step_kmean.assign(nb, 0.0); c.step_nmodes.assign(nb, 0.0);
+    pofk_bin(c, MGP_GRID_DENSITY, c.step_pofk.data(), c.step_kmean.data(), c.step_nmodes.data());
+    c.step_pofk_valid = true;
+  }
+}
+
+static void compute_fifth_force(Ctx &c, const mgp_step_scalars *s) {
+  if (c.cfg.model == MGP_MODEL_NONE) return;
+  REQUIRE(s != nullptr, MGP_ERR_INVALID, "mgp_compute_fifth_force: step scalars are NULL");
+  if (c.cfg.model == MGP_MODEL_GEFF) {
+    PhaseTimer t(c, PH_FIFTH);
+    kspace_scale(c, MGP_GRID_DENSITY, s->geff);                 // mg.h:127-137
+    return;
+  }
+  if (c.cfg.model == MGP_MODEL_FOFR) {                          // mg.h:147-189
+    if (!c.cfg.include_screening) {
+      PhaseTimer t(c, PH_FIFTH);
+      kspace_phi_of_k(c, MGP_GRID_DENSITY, s->coupling, s->massterm2);
+      return;
+    }
+    const double n3 = pow((double) c.N, 3);
+    double normfactor = 1.0 / n3;                               // mg.h:27-28
+    normfactor *= 1.5 * c.cfg.omega / s->a * pow(c.cfg.box / 2997.92458 / (2.0 * 3.14159265358979323846), 2);
+    { PhaseTimer t(c, PH_FIFTH); kspace_divide_laplacian(c, normfactor); }
+    fft_c2r(c, MGP_GRID_MG_ONE);
+    { PhaseTimer t(c, PH_FIFTH); real_screen_potential(c, s->phi_crit, true); }
+    fft_r2c(c, MGP_GRID_MG_TWO);
+    { PhaseTimer t(c, PH_FIFTH); kspace_phi_of_k(c, MGP_GRID_MG_TWO, s->coupling, s->massterm2); }
+    return;
+  }
+  // DGP (mg.h:197-260)
+  if (!c.cfg.include_screening) {
+    PhaseTimer t(c, PH_FIFTH);
+    kspace_scale_to(c, MGP_GRID_DENSITY, MGP_GRID_MG_TWO, s->coupling);   // density aliases P3D (mg.h:214-216)
+    return;
+  }
+  { PhaseTimer t(c, PH_FIFTH); kspace_smooth(c, s->rsmooth); }
+  fft_c2r(c, MGP_GRID_MG_ONE);
+  { PhaseTimer t(c, PH_FIFTH); real_screen_density(c, s->coupling, s->dgp_fac0, nullptr); }
+  fft_r2c(c, MGP_GRID_MG_TWO);
+}
+
+static void forces(Ctx &c) {
+  { PhaseTimer t(c, PH_FORCES); kspace_forces(c, needs_mg_arrays(c)); }
+  fft_c2r_forces(c);
+  halo_fill_forces(c);
+}
+
+}  // namespace mgp
+
+using namespace mgp;
+
+#define API_BEGIN try {
+#define API_END                                         \
+  }                                                     \
+  catch (const mgp::Error &e) {                         \
+    mgp::set_last_error(e.what());                      \
+    return e.code;                                      \
+  }                                                     \
+  catch (const std::exception &e) {                     \
+    mgp::set_last_error(e.what());                      \
+    return MGP_ERR_CUDA;                                \
+  }                                                     \
+  return MGP_OK;
+
+#define CTX(ctx)                                                         \
+  REQUIRE(ctx != nullptr, MGP_ERR_INVALID, "context is NULL");          \
+  Ctx &c = *reinterpret_cast<Ctx *>(ctx);                                \
+  CK(cudaSetDevice(c.cfg.device));
+
+extern "C" {
+
+const char *mgp_last_error(void) { return g_last_error.c_str(); }
+int mgp_version(void) { return 100; }
+
+int mgp_nccl_unique_id(void *out128) {
+  API_BEGIN
+  REQUIRE(out128 != nullptr, MGP_ERR_INVALID, "mgp_nccl_unique_id: NULL");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  ncclUniqueId id;
+  CKNCCL(ncclGetUniqueId(&id));
+  memcpy(out128, &id, sizeof(id));
+  API_END
+}
+
+int mgp_create(const mgp_config *cfg, mgp_ctx **out) {
+  API_BEGIN
+  REQUIRE(out != nullptr, MGP_ERR_INVALID, "mgp_create: out is NULL");
+  *out = reinterpret_cast<mgp_ctx *>(create(cfg));
+  API_END
+}
+
+int mgp_destroy(mgp_ctx *ctx) {
+  API_BEGIN
+  destroy(reinterpret_cast<Ctx *>(ctx));
+  API_END
+}
+
+int mgp_get_layout(mgp_ctx *ctx, int *local_nx, int *local_x_start, int *local_np, int *local_p_start, uint64_t *numpart) {
+  API_BEGIN
+  CTX(ctx);
+  if (local_nx) *local_nx = c.nx;
+  if (local_x_start) *local_x_start = c.x0;
+  if (local_np) *local_np = c.npl;
+  if (local_p_start) *local_p_start = c.p0;
+  if (numpart) *numpart = c.np;
+  API_END
+}
+
+int mgp_upload_particles(mgp_ctx *ctx, uint64_t n, const float *pos, const float *vel, const float *D, const float *D2,
+                         const uint64_t *id) {
+  API_BEGIN
+  CTX(ctx);
+  particles_upload(c, n, pos, vel, D, D2, id);
+  API_END
+}
+
+int mgp_download_particles(mgp_ctx *ctx, float *pos, float *vel, float *D, float *D2, uint64_t *id) {
+  API_BEGIN
+  CTX(ctx);
+  particles_download(c, pos, vel, D, D2, id);
+  API_END
+}
+
+int mgp_download_disp(mgp_ctx *ctx, float *disp) {
+  API_BEGIN
+  CTX(ctx);
+  REQUIRE(c.have_disp, MGP_ERR_STATE, "mgp_download_disp: no displacements available");
+  std::vector<float> tmp(c.np);
+  for (int a = 0; a < 3; a++) {
+    CK(cudaMemcpyAsync(tmp.data(), c.disp + (size_t) a * c.cap, c.np * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+    for (size_t i = 0; i < c.np; i++) disp[3 * i + a] = tmp[i];
+  }
+  API_END
+}
+
+int mgp_move_particles(mgp_ctx *ctx) {
+  API_BEGIN
+  CTX(ctx);
+  move_particles(c);
+  CK(cudaStreamSynchronize(c.stream));
+  API_END
+}
+
+int mgp_ptomesh(mgp_ctx *ctx, const mgp_step_scalars *s) {
+  API_BEGIN
+  CTX(ctx);
+  ptomesh(c, s);
+  CK(cudaStreamSynchronize(c.stream));
+  API_END
+}
+
+int mgp_compute_fifth_force(mgp_ctx *ctx, const mgp_step_scalars *s) {
+  API_BEGIN
+  CTX(ctx);
+  compute_fifth_force(c, s);
+  CK(cudaStreamSynchronize(c.stream));
+  API_END
+}
+
+int mgp_forces(mgp_ctx *ctx) {
+  API_BEGIN
+  CTX(ctx);
+  forces(c);
+  CK(cudaStreamSynchronize(c.stream));
+  API_END
+}
+
+int mgp_mtoparticles(mgp_ctx *ctx, double sumDxyz[3]) {
+  API_BEGIN
+  CTX(ctx);
+  REQUIRE(sumDxyz != nullptr, MGP_ERR_INVALID, "mgp_mtoparticles: sumDxyz is NULL");
+  gather_forces(c, sumDxyz);
+  API_END
+}
+
+int mgp_get_displacements(mgp_ctx *ctx, const mgp_step_scalars *s, double sumDxyz[3]) {
+  API_BEGIN
+  CTX(ctx);
+  REQUIRE(sumDxyz != nullptr, MGP_ERR_INVALID, "mgp_get_displacements: sumDxyz is NULL");
+  move_particles(c);
+  ptomesh(c, s);
+  compute_fifth_force(c, s);
+  forces(c);
+  gather_forces(c, sumDxyz);
+  API_END
+}
+
+int mgp_kick(mgp_ctx *ctx, double A, double dda, double ddDddy, double ddD2ddy, const double sumDxyz[3], double sumxyz[3]) {
+  API_BEGIN
+  CTX(ctx);
+  REQUIRE(sumDxyz && sumxyz, MGP_ERR_INVALID, "mgp_kick: NULL argument");
+  particles_kick(c, A, dda, ddDddy, ddD2ddy, sumDxyz, sumxyz);
+  API_END
+}
+
+int mgp_drift(mgp_ctx *ctx, double dyyy, double deltaD, double deltaD2, const double sumxyz[3]) {
+  API_BEGIN
+  CTX(ctx);
+  REQUIRE(sumxyz != nullptr, MGP_ERR_INVALID, "mgp_drift: NULL argument");
+  particles_drift(c, dyyy, deltaD, deltaD2, sumxyz);
+  CK(cudaStreamSynchronize(c.stream));
+  API_END
+}
+
+int mgp_set_pofk_config(mgp_ctx *ctx, const mgp_pofk_config *pc) {
+  API_BEGIN
+  CTX(ctx);
+  REQUIRE(pc != nullptr, MGP_ERR_INVALID, "mgp_set_pofk_config: NULL");
+  c.pofk = *pc;
+  c.pofk_set = true;
+  API_END
+}
+
+int mgp_pofk_nbins(mgp_ctx *ctx) {
+  if (!ctx) return MGP_ERR_INVALID;
+  Ctx &c = *reinterpret_cast<Ctx *>(ctx);
+  if (!c.pofk_set) return MGP_ERR_STATE;
+  return pofk_effective_nbins(c);
+}
+
+int mgp_compute_power_spectrum(mgp_ctx *ctx, double *pofk, double *kmean, double *nmodes) {
+  API_BEGIN
+  CTX(ctx);
+  pofk_bin(c, MGP_GRID_DENSITY, pofk, kmean, nmodes);
+  API_END
+}
+
+int mgp_get_step_power_spectrum(mgp_ctx *ctx, double *pofk, double *kmean, double *nmodes) {
+  API_BEGIN
+  CTX(ctx);
+  REQUIRE(c.step_pofk_valid, MGP_ERR_STATE, "no in-step P(k) available (set mgp_step_scalars.compute_pofk)");
+  const size_t nb = c.step_pofk.size();
+  if (pofk) memcpy(pofk, c.step_pofk.data(), nb * sizeof(double));
+  if (kmean) memcpy(kmean, c.step_kmean.data(), nb * sizeof(double));
+  if (nmodes) memcpy(nmodes, c.step_nmodes.data(), nb * sizeof(double));
+  API_END
+}
+
+size_t mgp_grid_local_values(mgp_ctx *ctx) {
+  if (!ctx) return 0;
+  return reinterpret_cast<Ctx *>(ctx)->grid_vals;
+}
+
+int mgp_download_grid(mgp_ctx *ctx, int grid_id, void *host) {
+  API_BEGIN
+  CTX(ctx);
+  REQUIRE(grid_id >= 0 && grid_id < 6 && c.grid[grid_id], MGP_ERR_INVALID, "mgp_download_grid: grid not allocated");
+  CK(cudaMemcpyAsync(host, c.grid[grid_id], c.grid_bytes(), cudaMemcpyDeviceToHost, c.stream));
+  CK(cudaStreamSynchronize(c.stream));
+  API_END
+}
+
+int mgp_upload_grid(mgp_ctx *ctx, int grid_id, const void *host) {
+  API_BEGIN
+  CTX(ctx);
+  REQUIRE(grid_id >= 0 && grid_id < 6 && c.grid[grid_id], MGP_ERR_INVALID, "mgp_upload_grid: grid not allocated");
+  CK(cudaMemcpyAsync(c.grid[grid_id], host, c.grid_bytes(), cudaMemcpyHostToDevice, c.stream));
+  CK(cudaStreamSynchronize(c.stream));
+  API_END
+}
+
+int mgp_fft_r2c(mgp_ctx *ctx, int grid_id) {
+  API_BEGIN
+  CTX(ctx);
+  REQUIRE(grid_id >= 0 && grid_id < 6 && c.grid[grid_id], MGP_ERR_INVALID, "mgp_fft_r2c: grid not allocated");
+  fft_r2c(c, grid_id);
+  CK(cudaStreamSynchronize(c.stream));
+  API_END
+}
+
+int mgp_fft_c2r(mgp_ctx *ctx, int grid_id) {
+  API_BEGIN
+  CTX(ctx);
+  REQUIRE(grid_id >= 0 && grid_id < 6 && c.grid[grid_id], MGP_ERR_INVALID, "mgp_fft_c2r: grid not allocated");
+  fft_c2r(c, grid_id);
+  CK(cudaStreamSynchronize(c.stream));
+  API_END
+}
+
+uint64_t mgp_launch_count(mgp_ctx *ctx, int reset) {
+  if (!ctx) return 0;
+  Ctx &c = *reinterpret_cast<Ctx *>(ctx);
+  const uint64_t v = c.launches;
+  if (reset) c.launches = 0;
+  return v;
+}
+
+int mgp_phase_count(void) { return PH_COUNT; }
+const char *mgp_phase_name(int i) { return (i >= 0 && i < PH_COUNT) ? kPhaseNames[i] : ""; }
+
+int mgp_phase_times_ms(mgp_ctx *ctx, double *ms, uint64_t *calls, int reset) {
+  API_BEGIN
+  CTX(ctx);
+  for (int i = 0; i < PH_COUNT; i++) {
+    if (ms) ms[i] = c.phase_ms[i];
+    if (calls) calls[i] = c.phase_calls[i];
+    if (reset) { c.phase_ms[i] = 0; c.phase_calls[i] = 0; }
+  }
+  API_END
+}
+
+int mgp_set_phase_timing(mgp_ctx *ctx, int on) {
+  API_BEGIN
+  CTX(ctx);
+  c.phase_timing = on != 0;
+  API_END
+}
+
+void *mgp_stream(mgp_ctx *ctx) { return ctx ? (void *) reinterpret_cast<Ctx *>(ctx)->stream : nullptr; }
+
+}  // extern "C"

@@ -1,0 +1,189 @@
+// Shared declarations of the B200-native COLA particle-mesh library (internal; the public
+// surface is include/mgpicola.h).  Everything here is sm_100a-only: no fallbacks.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cufft.h>
+#include <nccl.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "mgpicola.h"
+
+namespace mgp {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+void set_last_error(const std::string &m);
+
+#define MGP_STR2(x) #x
+#define MGP_STR(x) MGP_STR2(x)
+#define CK(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess)                                                                        \
+      throw mgp::Error(MGP_ERR_CUDA, std::string(__FILE__ ":" MGP_STR(__LINE__) " ") +            \
+                                         cudaGetErrorString(e_));                                 \
+  } while (0)
+#define CKFFT(call)                                                                               \
+  do {                                                                                            \
+    cufftResult r_ = (call);                                                                      \
+    if (r_ != CUFFT_SUCCESS)                                                                      \
+      throw mgp::Error(MGP_ERR_CUDA, std::string(__FILE__ ":" MGP_STR(__LINE__) " cuFFT error ") + \
+                                         std::to_string((int) r_));                               \
+  } while (0)
+#define CKNCCL(call)                                                                              \
+  do {                                                                                            \
+    ncclResult_t r_ = (call);                                                                     \
+    if (r_ != ncclSuccess)                                                                        \
+      throw mgp::Error(MGP_ERR_CUDA, std::string(__FILE__ ":" MGP_STR(__LINE__) " NCCL: ") +      \
+                                         ncclGetErrorString(r_));                                 \
+  } while (0)
+#define REQUIRE(cond, code, msg)                                                                  \
+  do {                                                                                            \
+    if (!(cond)) throw mgp::Error(code, msg);                                                     \
+  } while (0)
+
+// phases, named after the reference's timer.h sub-categories
+enum Phase { PH_MOVE = 0, PH_PTOMESH, PH_FFT, PH_FIFTH, PH_FORCES, PH_MTOP, PH_KICK, PH_DRIFT, PH_POFK, PH_SORT, PH_COMM, PH_COUNT };
+
+constexpr int kSMs = 148;   // B200
+
+struct Ctx {
+  mgp_config cfg{};
+  int N = 0, NZ = 0;          // Nmesh, Nmesh/2+1
+  int P = 1, rank = 0;
+  int nx = 0, x0 = 0;         // Local_nx, Local_x_start
+  int npl = 0, p0 = 0;        // Local_np, Local_p_start
+  int left = 0, right = 0;    // LeftTask / RightTask
+  int gbytes = 8;
+  size_t plane_vals = 0;      // N * 2*NZ reals per x-plane
+  size_t grid_vals = 0;       // (nx+1) * plane_vals
+  void *grid[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  void *force_block = nullptr;   // FX,FY,FZ contiguous (batched c2r)
+  void *halo_send = nullptr, *halo_recv = nullptr;   // 3 planes each
+
+  // FFT
+  cufftHandle plan_r2c = 0, plan_c2r = 0, plan_c2r3 = 0;
+  bool have_plans = false;
+  // distributed FFT (P > 1)
+  cufftHandle plan2d_r2c = 0, plan2d_c2r = 0, plan1d_x = 0;
+  int ny_loc = 0, y0 = 0;     // k-space y-slab of this rank
+  void *tbuf_a = nullptr, *tbuf_b = nullptr;   // transpose pack / unpack buffers
+  void *fft_work = nullptr;                    // cuFFT work area shared by all plans
+
+  // particles (SoA of 16-byte records; see DESIGN.md "data layout")
+  uint64_t np = 0, cap = 0;
+  float4 *pA = nullptr;       // pos.xyz , id low  32 bits
+  float4 *pB = nullptr;       // vel.xyz , id high 32 bits
+  float4 *pC = nullptr;       // D.xyz   , D2.x
+  float4 *pE = nullptr;       // (float2 view) D2.y, D2.z   -- allocated with float4 capacity so
+                              // that all five buffers are interchangeable in the permute rotation
+  float4 *spare = nullptr;
+  float *disp = nullptr;      // [3][cap]
+  bool have_disp = false;
+  bool sorted = false;        // particle order == cell order of current positions
+  uint32_t *key[2] = {nullptr, nullptr};
+  uint32_t *perm[2] = {nullptr, nullptr};
+  uint32_t *row_start = nullptr;   // (nx*N + 1) offsets into the sorted particle list
+  void *cub_temp = nullptr;
+  size_t cub_temp_bytes = 0;
+  int key_zshift = 0;         // cell key drops this many low z bits (0 = full cell sort)
+  int key_bits = 32;
+
+  double *d_red = nullptr;    // device reduction scratch (doubles)
+  double *h_red = nullptr;    // pinned host mirror
+  size_t red_cap = 0;
+  int *d_flag = nullptr, *h_flag = nullptr;
+
+  // P(k)
+  mgp_pofk_config pofk{};
+  bool pofk_set = false;
+  std::vector<double> step_pofk, step_kmean, step_nmodes;
+  bool step_pofk_valid = false;
+
+  cudaStream_t stream = nullptr;
+  ncclComm_t comm = nullptr;
+
+  // instrumentation
+  uint64_t launches = 0;
+  bool phase_timing = false;
+  cudaEvent_t ev[4][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};
+  int ev_depth = 0;           // phase timers may nest (FFT contains its transposes' Comm)
+  double phase_ms[PH_COUNT] = {0};
+  uint64_t phase_calls[PH_COUNT] = {0};
+
+  size_t plane_bytes() const { return plane_vals * (size_t) gbytes; }
+  size_t grid_bytes() const { return grid_vals * (size_t) gbytes; }
+};
+
+struct PhaseTimer {
+  Ctx &c; int ph; bool on; int d;
+  PhaseTimer(Ctx &c_, int ph_) : c(c_), ph(ph_), on(c_.phase_timing && c_.ev_depth < 4), d(0) {
+    if (on) { d = c.ev_depth++; cudaEventRecord(c.ev[d][0], c.stream); }
+  }
+  ~PhaseTimer() {
+    if (on) {
+      cudaEventRecord(c.ev[d][1], c.stream);
+      cudaEventSynchronize(c.ev[d][1]);
+      float ms = 0; cudaEventElapsedTime(&ms, c.ev[d][0], c.ev[d][1]);
+      c.phase_ms[ph] += ms; c.phase_calls[ph]++;
+      c.ev_depth--;
+    }
+  }
+};
+
+inline unsigned grid_for(size_t n, int block, int max_waves = 32) {
+  size_t g = (n + block - 1) / block;
+  size_t cap = (size_t) kSMs * max_waves;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (unsigned) g;
+}
+
+// ---- module entry points (one .cu each) ----
+// particles.cu
+void particles_alloc(Ctx &c);
+void particles_free(Ctx &c);
+void particles_upload(Ctx &c, uint64_t n, const float *pos, const float *vel, const float *D, const float *D2, const uint64_t *id);
+void particles_download(Ctx &c, float *pos, float *vel, float *D, float *D2, uint64_t *id);
+void particles_sort(Ctx &c);
+void particles_kick(Ctx &c, double A, double dda, double ddD, double ddD2, const double sumD[3], double sumV[3]);
+void particles_drift(Ctx &c, double dyyy, double dD, double dD2, const double sumV[3]);
+void particles_migrate(Ctx &c);
+// deposit.cu
+void deposit_density(Ctx &c);
+void gather_forces(Ctx &c, double sumD[3]);
+// fft.cu
+void fft_setup(Ctx &c);
+void fft_teardown(Ctx &c);
+void fft_r2c(Ctx &c, int grid_id);
+void fft_c2r(Ctx &c, int grid_id);
+void fft_c2r_forces(Ctx &c);
+void halo_add_density(Ctx &c, int grid_id);
+void halo_fill_forces(Ctx &c);
+// kspace.cu
+void kspace_forces(Ctx &c, bool add_mg);
+void kspace_divide_laplacian(Ctx &c, double normfactor);
+void kspace_phi_of_k(Ctx &c, int src_grid, double coupling, double massterm2);
+void kspace_smooth(Ctx &c, double rsmooth);
+void kspace_scale(Ctx &c, int grid_id, double f);
+void kspace_scale_to(Ctx &c, int src, int dst, double f);
+void real_copy(Ctx &c, int dst_grid, int src_grid, double scale);
+void real_screen_potential(Ctx &c, double phi_crit, bool screening);
+void real_screen_density(Ctx &c, double coupling, double fac0, double stats[3]);
+void pofk_bin(Ctx &c, int grid_id, double *pofk, double *kmean, double *nmodes);
+int pofk_effective_nbins(const Ctx &c);
+
+// reductions: sum `n` doubles' worth of per-block partials living in c.d_red into host values
+void reduce_alloc(Ctx &c, size_t n);
+
+}  // namespace mgp

@@ -1,0 +1,263 @@
+// FFTs, slab halos and scalar all-reduces.
+//
+// Replaces the seven FFTW-MPI wrappers of wrappers.c:26-96 (plans created once, not per step as
+// MEMORY_MODE does, auxPM.c:46-51, 61-71) and the halo MPI_Sendrecv calls of auxPM.c:350-356
+// (density ghost plane -> right neighbour) and auxPM.c:546-551 (force plane 0 -> left neighbour).
+//
+// Single rank: cuFFT 3-D in-place r2c / c2r on the padded layout [x][y][2*(N/2+1)], identical to
+// the FFTW in-place layout; unnormalised in both directions like FFTW.
+// Several ranks (x-slabs exactly as fftw_mpi_local_size_3d): batched 2-D (y,z) transforms on the
+// local planes, a hand-written pack / unpack pair around an NCCL all-to-all, and batched 1-D
+// transforms along x.  k-space is kept in the transposed layout [ky_local][kz][kx] -- every
+// k-space kernel is pointwise, so FFTW's second transpose back is never needed.
+#include "common.cuh"
+#include "reduce.cuh"
+
+namespace mgp {
+
+typedef long long int lli;
+static size_t make_plan_many(cufftHandle *plan, int rank, lli *n, lli *inembed, lli istride, lli idist, lli *onembed,
+                             lli ostride, lli odist, cufftType type, lli batch, cudaStream_t st) {
+  size_t ws = 0;
+  CKFFT(cufftCreate(plan));
+  CKFFT(cufftSetAutoAllocation(*plan, 0));
+  CKFFT(cufftMakePlanMany64(*plan, rank, n, inembed, istride, idist, onembed, ostride, odist, type, batch, &ws));
+  CKFFT(cufftSetStream(*plan, st));
+  return ws;
+}
+
+void fft_setup(Ctx &c) {
+  const int N = c.N, NZ = c.NZ;
+  const bool f32 = c.gbytes == 4;
+  size_t ws = 0, w;
+  if (c.P == 1) {
+    lli n[3] = {N, N, N};
+    lli rembed[3] = {N, N, 2 * NZ}, cembed[3] = {N, N, NZ};
+    const lli rdist = (lli) c.grid_vals, cdist = (lli) (c.grid_vals / 2);
+    w = make_plan_many(&c.plan_r2c, 3, n, rembed, 1, rdist, cembed, 1, cdist, f32 ? CUFFT_R2C : CUFFT_D2Z, 1, c.stream);
+    ws = w > ws ? w : ws;
+    w = make_plan_many(&c.plan_c2r, 3, n, cembed, 1, cdist, rembed, 1, rdist, f32 ? CUFFT_C2R : CUFFT_Z2D, 1, c.stream);
+    ws = w > ws ? w : ws;
+    w = make_plan_many(&c.plan_c2r3, 3, n, cembed, 1, cdist, rembed, 1, rdist, f32 ? CUFFT_C2R : CUFFT_Z2D, 3, c.stream);
+    ws = w > ws ? w : ws;
+  } else {
+    lli n2[2] = {N, N};
+    lli rembed[2] = {N, 2 * NZ}, cembed[2] = {N, NZ};
+    w = make_plan_many(&c.plan2d_r2c, 2, n2, rembed, 1, N * 2 * NZ, cembed, 1, N * NZ, f32 ? CUFFT_R2C : CUFFT_D2Z, c.nx, c.stream);
+    ws = w > ws ? w : ws;
+    w = make_plan_many(&c.plan2d_c2r, 2, n2, cembed, 1, N * NZ, rembed, 1, N * 2 * NZ, f32 ? CUFFT_C2R : CUFFT_Z2D, c.nx, c.stream);
+    ws = w > ws ? w : ws;
+    lli n1[1] = {N};
+    w = make_plan_many(&c.plan1d_x, 1, n1, n1, 1, N, n1, 1, N, f32 ? CUFFT_C2C : CUFFT_Z2Z, c.ny_loc * NZ, c.stream);
+    ws = w > ws ? w : ws;
+    CK(cudaMalloc(&c.tbuf_a, c.grid_bytes()));
+    CK(cudaMalloc(&c.tbuf_b, c.grid_bytes()));
+  }
+  if (ws) CK(cudaMalloc(&c.fft_work, ws));     // shared cuFFT work area
+  cufftHandle all[6] = {c.plan_r2c, c.plan_c2r, c.plan_c2r3, c.plan2d_r2c, c.plan2d_c2r, c.plan1d_x};
+  for (cufftHandle h : all)
+    if (h && ws) CKFFT(cufftSetWorkArea(h, c.fft_work));
+  c.have_plans = true;
+}
+
+void fft_teardown(Ctx &c) {
+  cufftHandle all[6] = {c.plan_r2c, c.plan_c2r, c.plan_c2r3, c.plan2d_r2c, c.plan2d_c2r, c.plan1d_x};
+  for (cufftHandle h : all)
+    if (h) cufftDestroy(h);
+  cudaFree(c.fft_work); cudaFree(c.tbuf_a); cudaFree(c.tbuf_b);
+}
+
+// ------------------------------------------------------------------ slab transposes (P > 1)
+
+// pack for the forward transpose: in = [nx][N (ky)][NZ] complex; block for rank r holds
+// [nx][ny_r][NZ] at complex offset nx * y0_r * NZ  (equal slabs: ny_r = N / P).
+template <typename C>
+__global__ void k_pack_fwd(const C *__restrict__ in, C *__restrict__ out, int nx, int N, int NZ, int nyb) {
+  const size_t tot = (size_t) nx * N * NZ;
+  for (size_t e = blockIdx.x * (size_t) blockDim.x + threadIdx.x; e < tot; e += (size_t) gridDim.x * blockDim.x) {
+    const int k = (int) (e % NZ);
+    const size_t t = e / NZ;
+    const int j = (int) (t % N), x = (int) (t / N);
+    const int r = j / nyb, jl = j - r * nyb;
+    out[((size_t) r * nx + x) * nyb * NZ + (size_t) jl * NZ + k] = in[e];
+  }
+}
+
+// unpack after the forward all-to-all: in = [s][nx_s][nyl][NZ]  ->  out = [nyl][NZ][N (kx)]
+// 32x32 shared-memory tile transpose over (x, kz) for each ky so that both sides coalesce.
+template <typename C>
+__global__ void k_unpack_fwd(const C *__restrict__ in, C *__restrict__ out, int nxb, int N, int NZ, int nyl) {
+  __shared__ C tile[32][33];
+  const int jl = blockIdx.z;
+  const int x0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int x = x0 + r, k = k0 + threadIdx.x;
+    if (x < N && k < NZ) {
+      const int s = x / nxb, xl = x - s * nxb;
+      tile[r][threadIdx.x] = in[(((size_t) s * nxb + xl) * nyl + jl) * NZ + k];
+    }
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int k = k0 + r, x = x0 + threadIdx.x;
+    if (x < N && k < NZ) out[((size_t) jl * NZ + k) * N + x] = tile[threadIdx.x][r];
+  }
+}
+
+// pack for the backward transpose: in = [nyl][NZ][N (x)]  ->  out = [s][nx_s][nyl][NZ]
+template <typename C>
+__global__ void k_pack_bwd(const C *__restrict__ in, C *__restrict__ out, int nxb, int N, int NZ, int nyl) {
+  __shared__ C tile[32][33];
+  const int jl = blockIdx.z;
+  const int x0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int k = k0 + r, x = x0 + threadIdx.x;
+    if (x < N && k < NZ) tile[r][threadIdx.x] = in[((size_t) jl * NZ + k) * N + x];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int x = x0 + r, k = k0 + threadIdx.x;
+    if (x < N && k < NZ) {
+      const int s = x / nxb, xl = x - s * nxb;
+      out[(((size_t) s * nxb + xl) * nyl + jl) * NZ + k] = tile[threadIdx.x][r];
+    }
+  }
+}
+
+// unpack after the backward all-to-all: in = [r][nx][ny_r][NZ]  ->  out = [nx][N (ky)][NZ]
+template <typename C>
+__global__ void k_unpack_bwd(const C *__restrict__ in, C *__restrict__ out, int nx, int N, int NZ, int nyb) {
+  const size_t tot = (size_t) nx * N * NZ;
+  for (size_t e = blockIdx.x * (size_t) blockDim.x + threadIdx.x; e < tot; e += (size_t) gridDim.x * blockDim.x) {
+    const int k = (int) (e % NZ);
+    const size_t t = e / NZ;
+    const int j = (int) (t % N), x = (int) (t / N);
+    const int r = j / nyb, jl = j - r * nyb;
+    out[e] = in[((size_t) r * nx + x) * nyb * NZ + (size_t) jl * NZ + k];
+  }
+}
+
+static void all_to_all(Ctx &c, const void *send, void *recv, size_t block_bytes) {
+  PhaseTimer t(c, PH_COMM);
+  CKNCCL(ncclGroupStart());
+  for (int r = 0; r < c.P; r++) {
+    CKNCCL(ncclSend((const char *) send + (size_t) r * block_bytes, block_bytes, ncclChar, r, c.comm, c.stream));
+    CKNCCL(ncclRecv((char *) recv + (size_t) r * block_bytes, block_bytes, ncclChar, r, c.comm, c.stream));
+  }
+  CKNCCL(ncclGroupEnd());
+}
+
+template <typename R, typename C>
+static void dist_r2c(Ctx &c, void *g) {
+  const int N = c.N, NZ = c.NZ, nxb = c.nx, nyl = c.ny_loc;
+  if (sizeof(R) == 4) CKFFT(cufftExecR2C(c.plan2d_r2c, (cufftReal *) g, (cufftComplex *) g));
+  else CKFFT(cufftExecD2Z(c.plan2d_r2c, (cufftDoubleReal *) g, (cufftDoubleComplex *) g));
+  const size_t tot = (size_t) nxb * N * NZ;
+  k_pack_fwd<C><<<grid_for(tot, 256), 256, 0, c.stream>>>((const C *) g, (C *) c.tbuf_a, nxb, N, NZ, nyl);
+  all_to_all(c, c.tbuf_a, c.tbuf_b, (size_t) nxb * nyl * NZ * sizeof(C));
+  dim3 gr((N + 31) / 32, (NZ + 31) / 32, nyl), bl(32, 8);
+  k_unpack_fwd<C><<<gr, bl, 0, c.stream>>>((const C *) c.tbuf_b, (C *) g, nxb, N, NZ, nyl);
+  if (sizeof(R) == 4) CKFFT(cufftExecC2C(c.plan1d_x, (cufftComplex *) g, (cufftComplex *) g, CUFFT_FORWARD));
+  else CKFFT(cufftExecZ2Z(c.plan1d_x, (cufftDoubleComplex *) g, (cufftDoubleComplex *) g, CUFFT_FORWARD));
+  c.launches += 5;
+}
+
+template <typename R, typename C>
+static void dist_c2r(Ctx &c, void *g) {
+  const int N = c.N, NZ = c.NZ, nxb = c.nx, nyl = c.ny_loc;
+  if (sizeof(R) == 4) CKFFT(cufftExecC2C(c.plan1d_x, (cufftComplex *) g, (cufftComplex *) g, CUFFT_INVERSE));
+  else CKFFT(cufftExecZ2Z(c.plan1d_x, (cufftDoubleComplex *) g, (cufftDoubleComplex *) g, CUFFT_INVERSE));
+  dim3 gr((N + 31) / 32, (NZ + 31) / 32, nyl), bl(32, 8);
+  k_pack_bwd<C><<<gr, bl, 0, c.stream>>>((const C *) g, (C *) c.tbuf_a, nxb, N, NZ, nyl);
+  all_to_all(c, c.tbuf_a, c.tbuf_b, (size_t) nxb * nyl * NZ * sizeof(C));
+  const size_t tot = (size_t) nxb * N * NZ;
+  k_unpack_bwd<C><<<grid_for(tot, 256), 256, 0, c.stream>>>((const C *) c.tbuf_b, (C *) g, nxb, N, NZ, nyl);
+  if (sizeof(R) == 4) CKFFT(cufftExecC2R(c.plan2d_c2r, (cufftComplex *) g, (cufftReal *) g));
+  else CKFFT(cufftExecZ2D(c.plan2d_c2r, (cufftDoubleComplex *) g, (cufftDoubleReal *) g));
+  c.launches += 5;
+}
+
+// ------------------------------------------------------------------ public (module) entry points
+
+void fft_r2c(Ctx &c, int gid) {
+  PhaseTimer t(c, PH_FFT);
+  void *g = c.grid[gid];
+  if (c.P > 1) {
+    if (c.gbytes == 4) dist_r2c<float, float2>(c, g); else dist_r2c<double, double2>(c, g);
+    return;
+  }
+  if (c.gbytes == 4) CKFFT(cufftExecR2C(c.plan_r2c, (cufftReal *) g, (cufftComplex *) g));
+  else CKFFT(cufftExecD2Z(c.plan_r2c, (cufftDoubleReal *) g, (cufftDoubleComplex *) g));
+  c.launches += 3;
+}
+
+void fft_c2r(Ctx &c, int gid) {
+  PhaseTimer t(c, PH_FFT);
+  void *g = c.grid[gid];
+  if (c.P > 1) {
+    if (c.gbytes == 4) dist_c2r<float, float2>(c, g); else dist_c2r<double, double2>(c, g);
+    return;
+  }
+  if (c.gbytes == 4) CKFFT(cufftExecC2R(c.plan_c2r, (cufftComplex *) g, (cufftReal *) g));
+  else CKFFT(cufftExecZ2D(c.plan_c2r, (cufftDoubleComplex *) g, (cufftDoubleReal *) g));
+  c.launches += 3;
+}
+
+void fft_c2r_forces(Ctx &c) {
+  if (c.P > 1) {
+    for (int a = 0; a < 3; a++) fft_c2r(c, MGP_GRID_FORCE_X + a);
+    return;
+  }
+  PhaseTimer t(c, PH_FFT);
+  void *g = c.force_block;
+  if (c.gbytes == 4) CKFFT(cufftExecC2R(c.plan_c2r3, (cufftComplex *) g, (cufftReal *) g));
+  else CKFFT(cufftExecZ2D(c.plan_c2r3, (cufftDoubleComplex *) g, (cufftDoubleReal *) g));
+  c.launches += 9;
+}
+
+// density[i] += ghost_from_left[i] + 1.0 over plane 0 (auxPM.c:354)
+template <typename T>
+__global__ void k_halo_add(T *__restrict__ plane0, const T *__restrict__ recv, size_t n) {
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+    plane0[i] += (T) (recv[i] + (T) 1.0);
+}
+
+void halo_add_density(Ctx &c, int gid) {
+  if (c.P == 1) return;    // single rank: the deposit wraps x itself
+  PhaseTimer t(c, PH_COMM);
+  char *g = (char *) c.grid[gid];
+  const size_t pb = c.plane_bytes();
+  CKNCCL(ncclGroupStart());
+  CKNCCL(ncclSend(g + (size_t) c.nx * pb, pb, ncclChar, c.right, c.comm, c.stream));
+  CKNCCL(ncclRecv(c.halo_recv, pb, ncclChar, c.left, c.comm, c.stream));
+  CKNCCL(ncclGroupEnd());
+  if (c.gbytes == 4) k_halo_add<float><<<grid_for(c.plane_vals, 256), 256, 0, c.stream>>>((float *) g, (const float *) c.halo_recv, c.plane_vals);
+  else k_halo_add<double><<<grid_for(c.plane_vals, 256), 256, 0, c.stream>>>((double *) g, (const double *) c.halo_recv, c.plane_vals);
+  c.launches++;
+}
+
+void halo_fill_forces(Ctx &c) {
+  const size_t pb = c.plane_bytes();
+  if (c.P == 1) {
+    for (int a = 0; a < 3; a++) {
+      char *g = (char *) c.grid[MGP_GRID_FORCE_X + a];
+      CK(cudaMemcpyAsync(g + (size_t) c.nx * pb, g, pb, cudaMemcpyDeviceToDevice, c.stream));
+    }
+    return;
+  }
+  PhaseTimer t(c, PH_COMM);
+  CKNCCL(ncclGroupStart());
+  for (int a = 0; a < 3; a++) {
+    char *g = (char *) c.grid[MGP_GRID_FORCE_X + a];
+    CKNCCL(ncclSend(g, pb, ncclChar, c.left, c.comm, c.stream));
+    CKNCCL(ncclRecv(g + (size_t) c.nx * pb, pb, ncclChar, c.right, c.comm, c.stream));
+  }
+  CKNCCL(ncclGroupEnd());
+}
+
+void allreduce_sum(Ctx &c, double *dbuf, int n) {
+  if (c.P == 1) return;
+  CKNCCL(ncclAllReduce(dbuf, dbuf, (size_t) n, ncclDouble, ncclSum, c.comm, c.stream));
+}
+
+}  // namespace mgp

@@ -1,0 +1,317 @@
+// Particle store and the streaming particle kernels: cell keys + sort + permute, Kick, Drift.
+//
+// Reference semantics reproduced (all citations relative to the reference's src/):
+//   Kick   main.c:707-739   Disp -= <Disp>; Vel += (-1.5 Omega Disp - UseCOLA (D ddD + D2 ddD2)/A) dda
+//   Drift  main.c:762-783   Pos += (Vel - <Vel>) dyyy; Pos = wrap(Pos + UseCOLA (D dD + D2 dD2))
+//   wrap   auxPM.c:649-655  float arithmetic
+// The reference keeps particle data in float (MEMORY_MODE) and evaluates these expressions in
+// double without FMA contraction (gcc, x86-64); the kernels below use __dmul_rn/__dadd_rn in the
+// same association order so that the stored floats are bit-identical.
+#include "common.cuh"
+#include "reduce.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+
+namespace mgp {
+
+// ------------------------------------------------------------------ allocation
+
+void reduce_alloc(Ctx &c, size_t n) {
+  if (n <= c.red_cap) return;
+  if (c.d_red) CK(cudaFree(c.d_red));
+  if (c.h_red) CK(cudaFreeHost(c.h_red));
+  CK(cudaMalloc(&c.d_red, n * sizeof(double)));
+  CK(cudaMallocHost(&c.h_red, n * sizeof(double)));
+  c.red_cap = n;
+}
+
+void particles_alloc(Ctx &c) {
+  const size_t cap = c.cap;
+  CK(cudaMalloc(&c.pA, cap * sizeof(float4)));
+  CK(cudaMalloc(&c.pB, cap * sizeof(float4)));
+  CK(cudaMalloc(&c.pC, cap * sizeof(float4)));
+  CK(cudaMalloc(&c.pE, cap * sizeof(float4)));
+  CK(cudaMalloc(&c.spare, cap * sizeof(float4)));
+  CK(cudaMalloc(&c.disp, 3 * cap * sizeof(float)));
+  for (int i = 0; i < 2; i++) {
+    CK(cudaMalloc(&c.key[i], cap * sizeof(uint32_t)));
+    CK(cudaMalloc(&c.perm[i], cap * sizeof(uint32_t)));
+  }
+  CK(cudaMalloc(&c.row_start, ((size_t) (c.nx + 1) * c.N + 2) * sizeof(uint32_t)));
+  c.cub_temp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, c.cub_temp_bytes, c.key[0], c.key[1], c.perm[0], c.perm[1],
+                                  (int64_t) cap, 0, 32, c.stream);
+  CK(cudaMalloc(&c.cub_temp, c.cub_temp_bytes));
+  reduce_alloc(c, 8192);
+  CK(cudaMalloc(&c.d_flag, 16 * sizeof(int)));
+  CK(cudaMallocHost(&c.h_flag, 16 * sizeof(int)));
+
+  // key = row-major cell index of the local slab
+  const uint64_t cells = (uint64_t) c.nx * c.N * c.N;
+  int b = 0;
+  while ((1ull << b) < cells) b++;
+  REQUIRE(b <= 32, MGP_ERR_INVALID, "more than 2^32 mesh cells on one rank: use more ranks");
+  c.key_zshift = 0;
+  c.key_bits = b < 1 ? 1 : b;
+}
+
+void particles_free(Ctx &c) {
+  cudaFree(c.pA); cudaFree(c.pB); cudaFree(c.pC); cudaFree(c.pE); cudaFree(c.spare); cudaFree(c.disp);
+  for (int i = 0; i < 2; i++) { cudaFree(c.key[i]); cudaFree(c.perm[i]); }
+  cudaFree(c.row_start); cudaFree(c.cub_temp);
+  cudaFree(c.d_red); if (c.h_red) cudaFreeHost(c.h_red);
+  cudaFree(c.d_flag); if (c.h_flag) cudaFreeHost(c.h_flag);
+}
+
+// ------------------------------------------------------------------ upload / download
+
+__global__ void k_pack(size_t n, size_t off, const float *__restrict__ pos, const float *__restrict__ vel,
+                       const float *__restrict__ D, const float *__restrict__ D2,
+                       const unsigned long long *__restrict__ id, unsigned long long id_base,
+                       float4 *pA, float4 *pB, float4 *pC, float2 *pE) {
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+    unsigned long long pid = id ? id[i] : id_base + i;
+    float d2x = D2 ? D2[3 * i] : 0.f, d2y = D2 ? D2[3 * i + 1] : 0.f, d2z = D2 ? D2[3 * i + 2] : 0.f;
+    float vx = vel ? vel[3 * i] : 0.f, vy = vel ? vel[3 * i + 1] : 0.f, vz = vel ? vel[3 * i + 2] : 0.f;
+    float dx = D ? D[3 * i] : 0.f, dy = D ? D[3 * i + 1] : 0.f, dz = D ? D[3 * i + 2] : 0.f;
+    pA[off + i] = make_float4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], __uint_as_float((unsigned) (pid & 0xffffffffull)));
+    pB[off + i] = make_float4(vx, vy, vz, __uint_as_float((unsigned) (pid >> 32)));
+    pC[off + i] = make_float4(dx, dy, dz, d2x);
+    pE[off + i] = make_float2(d2y, d2z);
+  }
+}
+
+__global__ void k_unpack(size_t n, size_t off, float *pos, float *vel, float *D, float *D2, unsigned long long *id,
+                         const float4 *__restrict__ pA, const float4 *__restrict__ pB,
+                         const float4 *__restrict__ pC, const float2 *__restrict__ pE) {
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+    float4 a = pA[off + i], b = pB[off + i], cc = pC[off + i];
+    float2 e = pE[off + i];
+    if (pos) { pos[3 * i] = a.x; pos[3 * i + 1] = a.y; pos[3 * i + 2] = a.z; }
+    if (vel) { vel[3 * i] = b.x; vel[3 * i + 1] = b.y; vel[3 * i + 2] = b.z; }
+    if (D) { D[3 * i] = cc.x; D[3 * i + 1] = cc.y; D[3 * i + 2] = cc.z; }
+    if (D2) { D2[3 * i] = cc.w; D2[3 * i + 1] = e.x; D2[3 * i + 2] = e.y; }
+    if (id) id[i] = ((unsigned long long) __float_as_uint(b.w) << 32) | (unsigned long long) __float_as_uint(a.w);
+  }
+}
+
+static const size_t kChunk = (size_t) 1 << 24;   // particles per staging chunk
+
+void particles_upload(Ctx &c, uint64_t n, const float *pos, const float *vel, const float *D, const float *D2,
+                      const uint64_t *id) {
+  REQUIRE(n <= c.cap, MGP_ERR_BUFFER, "mgp_upload_particles: more particles than ceil(NumPart*Buffer); increase Buffer");
+  REQUIRE(pos != nullptr, MGP_ERR_INVALID, "mgp_upload_particles: pos is NULL");
+  const size_t ch = n < kChunk ? (n ? n : 1) : kChunk;
+  float *st = nullptr;   // staging: 4 x [ch][3] floats + [ch] u64
+  CK(cudaMalloc(&st, ch * (12 * sizeof(float) + sizeof(uint64_t))));
+  float *s_pos = st, *s_vel = st + 3 * ch, *s_D = st + 6 * ch, *s_D2 = st + 9 * ch;
+  unsigned long long *s_id = (unsigned long long *) (st + 12 * ch);
+  for (size_t off = 0; off < n; off += ch) {
+    const size_t m = (n - off) < ch ? (n - off) : ch;
+    CK(cudaMemcpyAsync(s_pos, pos + 3 * off, m * 12, cudaMemcpyHostToDevice, c.stream));
+    if (vel) CK(cudaMemcpyAsync(s_vel, vel + 3 * off, m * 12, cudaMemcpyHostToDevice, c.stream));
+    if (D) CK(cudaMemcpyAsync(s_D, D + 3 * off, m * 12, cudaMemcpyHostToDevice, c.stream));
+    if (D2) CK(cudaMemcpyAsync(s_D2, D2 + 3 * off, m * 12, cudaMemcpyHostToDevice, c.stream));
+    if (id) CK(cudaMemcpyAsync(s_id, id + off, m * 8, cudaMemcpyHostToDevice, c.stream));
+    k_pack<<<grid_for(m, 256), 256, 0, c.stream>>>(m, off, s_pos, vel ? s_vel : nullptr, D ? s_D : nullptr,
+                                                   D2 ? s_D2 : nullptr, id ? s_id : nullptr, off, c.pA, c.pB, c.pC,
+                                                   (float2 *) c.pE);
+    c.launches++;
+    CK(cudaStreamSynchronize(c.stream));
+  }
+  CK(cudaFree(st));
+  c.np = n;
+  c.sorted = false;
+  c.have_disp = false;
+}
+
+void particles_download(Ctx &c, float *pos, float *vel, float *D, float *D2, uint64_t *id) {
+  const size_t n = c.np;
+  if (!n) return;
+  const size_t ch = n < kChunk ? n : kChunk;
+  float *st = nullptr;
+  CK(cudaMalloc(&st, ch * (12 * sizeof(float) + sizeof(uint64_t))));
+  float *s_pos = st, *s_vel = st + 3 * ch, *s_D = st + 6 * ch, *s_D2 = st + 9 * ch;
+  unsigned long long *s_id = (unsigned long long *) (st + 12 * ch);
+  for (size_t off = 0; off < n; off += ch) {
+    const size_t m = (n - off) < ch ? (n - off) : ch;
+    k_unpack<<<grid_for(m, 256), 256, 0, c.stream>>>(m, off, pos ? s_pos : nullptr, vel ? s_vel : nullptr,
+                                                     D ? s_D : nullptr, D2 ? s_D2 : nullptr, id ? s_id : nullptr,
+                                                     c.pA, c.pB, c.pC, (const float2 *) c.pE);
+    c.launches++;
+    if (pos) CK(cudaMemcpyAsync(pos + 3 * off, s_pos, m * 12, cudaMemcpyDeviceToHost, c.stream));
+    if (vel) CK(cudaMemcpyAsync(vel + 3 * off, s_vel, m * 12, cudaMemcpyDeviceToHost, c.stream));
+    if (D) CK(cudaMemcpyAsync(D + 3 * off, s_D, m * 12, cudaMemcpyDeviceToHost, c.stream));
+    if (D2) CK(cudaMemcpyAsync(D2 + 3 * off, s_D2, m * 12, cudaMemcpyDeviceToHost, c.stream));
+    if (id) CK(cudaMemcpyAsync(id + off, s_id, m * 8, cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+  }
+  CK(cudaFree(st));
+}
+
+// ------------------------------------------------------------------ cell keys, sort, permute
+
+// key = ((ix - x0) * N + iy) * N + iz; cell of a position exactly as PtoMesh computes it
+// (auxPM.c:298-322): X = (double)Pos * (Nmesh/Box); I = (unsigned)X; I >= Nmesh -> 0 for y, z.
+__global__ void k_keys(size_t n, const float4 *__restrict__ pA, double scale, int N, int x0, int nx,
+                       uint32_t *__restrict__ key, uint32_t *__restrict__ perm) {
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+    const float4 a = pA[i];
+    unsigned ix = (unsigned) ((double) a.x * scale);
+    unsigned iy = (unsigned) ((double) a.y * scale);
+    unsigned iz = (unsigned) ((double) a.z * scale);
+    if (iy >= (unsigned) N) iy = 0;
+    if (iz >= (unsigned) N) iz = 0;
+    int lx = (int) ix - x0;
+    if (lx < 0) lx = 0;
+    if (lx >= nx) lx = nx - 1;  // defensive: ownership is established by migrate()
+    key[i] = ((uint32_t) lx * (uint32_t) N + iy) * (uint32_t) N + iz;
+    perm[i] = (uint32_t) i;
+  }
+}
+
+template <typename V>
+__global__ void k_permute(size_t n, const uint32_t *__restrict__ perm, const V *__restrict__ in, V *__restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+    out[i] = in[perm[i]];
+}
+
+// row_start[r] = first sorted particle whose row (= key / zc) is >= r, for r in [0, nrows]
+__global__ void k_row_start(size_t n, const uint32_t *__restrict__ key, unsigned zc, unsigned nrows,
+                            uint32_t *__restrict__ row_start) {
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i <= n; i += (size_t) gridDim.x * blockDim.x) {
+    long long r_prev = (i == 0) ? -1 : (long long) (key[i - 1] / zc);
+    long long r = (i == n) ? (long long) nrows : (long long) (key[i] / zc);
+    for (long long rr = r_prev + 1; rr <= r; rr++) row_start[rr] = (uint32_t) i;
+  }
+}
+
+void particles_sort(Ctx &c) {
+  PhaseTimer t(c, PH_SORT);
+  const size_t n = c.np;
+  const unsigned zc = (unsigned) c.N;
+  const unsigned nrows = (unsigned) (c.nx * c.N);
+  const double scale = (double) c.N / c.cfg.box;
+  if (n == 0) {
+    CK(cudaMemsetAsync(c.row_start, 0, ((size_t) nrows + 1) * sizeof(uint32_t), c.stream));
+    c.sorted = true;
+    return;
+  }
+  k_keys<<<grid_for(n, 256), 256, 0, c.stream>>>(n, c.pA, scale, c.N, c.x0, c.nx, c.key[0], c.perm[0]);
+  size_t tb = c.cub_temp_bytes;
+  CK(cub::DeviceRadixSort::SortPairs(c.cub_temp, tb, c.key[0], c.key[1], c.perm[0], c.perm[1], (int64_t) n, 0,
+                                     c.key_bits, c.stream));
+  const unsigned g = grid_for(n, 256);
+  // rotate the five interchangeable 16-byte buffers: out-of-place gather, then swap names
+  k_permute<float4><<<g, 256, 0, c.stream>>>(n, c.perm[1], c.pA, c.spare);
+  { float4 *t0 = c.pA; c.pA = c.spare; c.spare = t0; }
+  k_permute<float4><<<g, 256, 0, c.stream>>>(n, c.perm[1], c.pB, c.spare);
+  { float4 *t0 = c.pB; c.pB = c.spare; c.spare = t0; }
+  k_permute<float4><<<g, 256, 0, c.stream>>>(n, c.perm[1], c.pC, c.spare);
+  { float4 *t0 = c.pC; c.pC = c.spare; c.spare = t0; }
+  k_permute<float2><<<g, 256, 0, c.stream>>>(n, c.perm[1], (const float2 *) c.pE, (float2 *) c.spare);
+  { float4 *t0 = c.pE; c.pE = c.spare; c.spare = t0; }
+  k_row_start<<<grid_for(n + 1, 256), 256, 0, c.stream>>>(n, c.key[1], zc, nrows, c.row_start);
+  c.launches += 6 + 4;   // + CUB's histogram / onesweep passes (>= 4 launches for <= 32 bits)
+  c.sorted = true;
+  c.have_disp = false;   // Disp was in the old order
+}
+
+// ------------------------------------------------------------------ Kick
+
+__global__ void __launch_bounds__(256)
+k_kick(size_t n, float4 *__restrict__ pB, const float4 *__restrict__ pC, const float2 *__restrict__ pE,
+       float *__restrict__ disp, size_t cap, double sDx, double sDy, double sDz, double m15omega, double usecola,
+       double ddD, double ddD2, double A, double dda, double *__restrict__ partial) {
+  double sx = 0, sy = 0, sz = 0;
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+    float4 v = pB[i];
+    const float4 d = pC[i];
+    const float2 e = pE[i];
+    // Disp[axes][n] -= sumDxyz[axes]   (float storage, double arithmetic)
+    const float gx = (float) __dsub_rn((double) disp[i], sDx);
+    const float gy = (float) __dsub_rn((double) disp[cap + i], sDy);
+    const float gz = (float) __dsub_rn((double) disp[2 * cap + i], sDz);
+    disp[i] = gx; disp[cap + i] = gy; disp[2 * cap + i] = gz;
+    // force = -1.5*Omega*Disp - UseCOLA*(D*ddDddy + D2*ddD2ddy)/A
+    const double fx = __dsub_rn(__dmul_rn(m15omega, (double) gx),
+                                __ddiv_rn(__dmul_rn(usecola, __dadd_rn(__dmul_rn((double) d.x, ddD), __dmul_rn((double) d.w, ddD2))), A));
+    const double fy = __dsub_rn(__dmul_rn(m15omega, (double) gy),
+                                __ddiv_rn(__dmul_rn(usecola, __dadd_rn(__dmul_rn((double) d.y, ddD), __dmul_rn((double) e.x, ddD2))), A));
+    const double fz = __dsub_rn(__dmul_rn(m15omega, (double) gz),
+                                __ddiv_rn(__dmul_rn(usecola, __dadd_rn(__dmul_rn((double) d.z, ddD), __dmul_rn((double) e.y, ddD2))), A));
+    // Vel += force * dda
+    v.x = (float) __dadd_rn((double) v.x, __dmul_rn(fx, dda));
+    v.y = (float) __dadd_rn((double) v.y, __dmul_rn(fy, dda));
+    v.z = (float) __dadd_rn((double) v.z, __dmul_rn(fz, dda));
+    pB[i] = v;
+    sx += (double) v.x; sy += (double) v.y; sz += (double) v.z;
+  }
+  block_sum3(sx, sy, sz);
+  if (threadIdx.x == 0) {
+    partial[3 * blockIdx.x] = sx; partial[3 * blockIdx.x + 1] = sy; partial[3 * blockIdx.x + 2] = sz;
+  }
+}
+
+void particles_kick(Ctx &c, double A, double dda, double ddD, double ddD2, const double sumD[3], double sumV[3]) {
+  PhaseTimer t(c, PH_KICK);
+  REQUIRE(c.have_disp, MGP_ERR_STATE, "mgp_kick: no displacements; call mgp_get_displacements first");
+  const size_t n = c.np;
+  const unsigned g = grid_for(n, 256, 8);
+  reduce_alloc(c, (size_t) g * 3 + 16);
+  double *res = c.d_red + (size_t) g * 3;
+  k_kick<<<g, 256, 0, c.stream>>>(n, c.pB, c.pC, (const float2 *) c.pE, c.disp, c.cap, sumD[0], sumD[1], sumD[2],
+                                  -1.5 * c.cfg.omega, (double) c.cfg.use_cola, ddD, ddD2, A, dda, c.d_red);
+  k_final_reduce<<<1, 256, 0, c.stream>>>(c.d_red, (int) g, 3, 3, 1.0, res);
+  c.launches += 2;
+  allreduce_sum(c, res, 3);
+  CK(cudaMemcpyAsync(c.h_red, res, 3 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  CK(cudaStreamSynchronize(c.stream));
+  const double tot = (double) c.cfg.nsample * (double) c.cfg.nsample * (double) c.cfg.nsample;
+  for (int a = 0; a < 3; a++) sumV[a] = c.h_red[a] / tot;   // sumxyz /= TotNumPart (main.c:738)
+}
+
+// ------------------------------------------------------------------ Drift
+
+__device__ inline float periodic_wrap_f(float x, float box) {
+  while (x >= box) x -= box;
+  while (x < 0) x += box;
+  if (x == box) x = 0.0f;
+  return x;
+}
+
+__global__ void __launch_bounds__(256)
+k_drift(size_t n, float4 *__restrict__ pA, const float4 *__restrict__ pB, const float4 *__restrict__ pC,
+        const float2 *__restrict__ pE, double sVx, double sVy, double sVz, double dyyy, double usecola, double dD,
+        double dD2, float boxf) {
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+    float4 p = pA[i];
+    const float4 v = pB[i];
+    const float4 d = pC[i];
+    const float2 e = pE[i];
+    // Pos += (Vel - sumxyz) * dyyy            (stored back to float)
+    float x = (float) __dadd_rn((double) p.x, __dmul_rn(__dsub_rn((double) v.x, sVx), dyyy));
+    float y = (float) __dadd_rn((double) p.y, __dmul_rn(__dsub_rn((double) v.y, sVy), dyyy));
+    float z = (float) __dadd_rn((double) p.z, __dmul_rn(__dsub_rn((double) v.z, sVz), dyyy));
+    // Pos = periodic_wrap(Pos + UseCOLA*(D*deltaD + D2*deltaD2))   (argument converted to float)
+    x = periodic_wrap_f((float) __dadd_rn((double) x, __dmul_rn(usecola, __dadd_rn(__dmul_rn((double) d.x, dD), __dmul_rn((double) d.w, dD2)))), boxf);
+    y = periodic_wrap_f((float) __dadd_rn((double) y, __dmul_rn(usecola, __dadd_rn(__dmul_rn((double) d.y, dD), __dmul_rn((double) e.x, dD2)))), boxf);
+    z = periodic_wrap_f((float) __dadd_rn((double) z, __dmul_rn(usecola, __dadd_rn(__dmul_rn((double) d.z, dD), __dmul_rn((double) e.y, dD2)))), boxf);
+    p.x = x; p.y = y; p.z = z;
+    pA[i] = p;
+  }
+}
+
+void particles_drift(Ctx &c, double dyyy, double dD, double dD2, const double sumV[3]) {
+  PhaseTimer t(c, PH_DRIFT);
+  const size_t n = c.np;
+  if (n) {
+    k_drift<<<grid_for(n, 256), 256, 0, c.stream>>>(n, c.pA, c.pB, c.pC, (const float2 *) c.pE, sumV[0], sumV[1],
+                                                    sumV[2], dyyy, (double) c.cfg.use_cola, dD, dD2, (float) c.cfg.box);
+    c.launches++;
+  }
+  c.sorted = false;
+  c.have_disp = false;
+}
+
+}  // namespace mgp

@@ -1,0 +1,364 @@
+"""CPU restatement (numpy, float64) of MG-PICOLA's per-step COLA particle-mesh force path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product library imports this module; it may be used by
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg as the checker.
+
+Every function cites the reference lines (relative to the reference's src/) it restates.  The
+restatement is pinned against the unmodified reference compiled into oracle/_ref (see
+oracle/Makefile, oracle/ref_lib.py) by tests/test_oracle_vs_ref.py and against the committed
+fixtures in tests/golden/ (generated from oracle/_ref by oracle/make_golden.py).
+
+Particle data are float32 and grids float64, i.e. the reference's default build
+(MEMORY_MODE on, SINGLE_PRECISION off; Makefile:121-122, 155-156); pass grid_dtype=np.float32 for
+the -DSINGLE_PRECISION variant.  Single task (NTask = 1): Local_nx = Nmesh, Local_x_start = 0.
+"""
+import numpy as np
+import scipy.fft as sfft
+
+INVERSE_H0_MPCH = 2997.92458   # vars.h:64
+PI = 3.14159265358979323846    # vars.h:60
+
+
+# ----------------------------------------------------------------------------- CIC
+
+def _cic(pos, nmesh, box, wpar=1.0):
+    """Cell indices and weights exactly as auxPM.c:298-330 / 576-603 compute them."""
+    scale = np.float64(nmesh) / np.float64(box)
+    X = pos[:, 0].astype(np.float64) * scale
+    Y = pos[:, 1].astype(np.float64) * scale
+    Z = pos[:, 2].astype(np.float64) * scale
+    IX = X.astype(np.uint32).astype(np.int64)
+    IY = Y.astype(np.uint32).astype(np.int64)
+    IZ = Z.astype(np.uint32).astype(np.int64)
+    DX = X - IX
+    DY = Y - IY
+    DZ = Z - IZ
+    TX = 1.0 - DX
+    TY = 1.0 - DY
+    TZ = 1.0 - DZ
+    DY = DY * wpar
+    TY = TY * wpar
+    IY[IY >= nmesh] = 0
+    IZ[IZ >= nmesh] = 0
+    IXn = IX + 1                      # no wrap: ghost slice on the right (auxPM.c:325-326)
+    IYn = IY + 1
+    IZn = IZ + 1
+    IYn[IYn >= nmesh] = 0
+    IZn[IZn >= nmesh] = 0
+    return (IX, IY, IZ, IXn, IYn, IZn, DX, DY, DZ, TX, TY, TZ)
+
+
+def ptomesh_deposit(pos, nmesh, nsample, box, grid_dtype=np.float64):
+    """PtoMesh up to (not including) the FFT: auxPM.c:288-356.
+
+    Returns the padded real grid [Nmesh][Nmesh][2*(Nmesh/2+1)] holding delta (the ghost slice has
+    been folded into slice 0 as the self-Sendrecv of a single task does)."""
+    N = nmesh
+    nzp = 2 * (N // 2 + 1)
+    wpar = (np.float64(N) / np.float64(nsample)) ** 3          # auxPM.c:289
+    IX, IY, IZ, IXn, IYn, IZn, DX, DY, DZ, TX, TY, TZ = _cic(pos, N, box, wpar)
+    size = (N + 1) * N * nzp
+    grid = np.zeros(size, dtype=np.float64)
+
+    def add(ix, iy, iz, w):
+        idx = (ix * N + iy) * nzp + iz
+        grid[:] += np.bincount(idx, weights=w, minlength=size)
+
+    add(IX, IY, IZ, TX * TY * TZ)        # auxPM.c:335-342
+    add(IX, IY, IZn, TX * TY * DZ)
+    add(IX, IYn, IZ, TX * DY * TZ)
+    add(IX, IYn, IZn, TX * DY * DZ)
+    add(IXn, IY, IZ, DX * TY * TZ)
+    add(IXn, IY, IZn, DX * TY * DZ)
+    add(IXn, IYn, IZ, DX * DY * TZ)
+    add(IXn, IYn, IZn, DX * DY * DZ)
+    grid = (grid - 1.0).astype(grid_dtype).reshape(N + 1, N, nzp)   # density starts at -1 (auxPM.c:292)
+    # ghost slice -> slice 0:  density[i] += temp[i] + 1.0   (auxPM.c:350-355)
+    grid[0] += (grid[N] + grid_dtype(1.0)).astype(grid_dtype)
+    return np.ascontiguousarray(grid[:N])
+
+
+def r2c(grid_real, nmesh):
+    """my_fftw_execute on an r2c plan (wrappers.c:42-46): unnormalised, half spectrum [kx][ky][kz<=N/2]."""
+    N = nmesh
+    out = sfft.rfftn(grid_real[:, :, :N].astype(np.float64), workers=-1)
+    return out
+
+
+def c2r(grid_k, nmesh):
+    """Unnormalised c2r over a half spectrum that need not be Hermitian on the kz = 0, N/2 planes:
+    c2c over x, y first, c2r over z last (FFTW and cuFFT order); irfftn does exactly this."""
+    N = nmesh
+    return sfft.irfftn(grid_k, s=(N, N, N), axes=(0, 1, 2), workers=-1) * (np.float64(N) ** 3)
+
+
+def _dvec(nmesh):
+    N = nmesh
+    i = np.arange(N)
+    d = np.where(i > N // 2, i - N, i).astype(np.float64)       # auxPM.c:478: iglobal > Nmesh/2 ? iglobal-Nmesh
+    dz = np.arange(N // 2 + 1).astype(np.float64)
+    return d[:, None, None], d[None, :, None], dz[None, None, :]
+
+
+def forces_kspace(P3D, nmesh, box, mg_phik=None):
+    """Forces() before the inverse FFTs: auxPM.c:450-535.  Returns FN11, FN12, FN13 (complex)."""
+    N = nmesh
+    if mg_phik is not None:
+        P3D = P3D + mg_phik                                      # auxPM.c:450-455
+    d0, d1, d2 = _dvec(N)
+    RK = d0 * d0 + d1 * d1 + d2 * d2
+    with np.errstate(divide="ignore"):
+        KK = -1.0 / RK
+    scale = 2.0 * np.pi / box                                    # Scale (auxPM.c:441)
+    n3 = np.float64(N) ** 3
+    out = []
+    with np.errstate(invalid="ignore"):
+        dens0 = (P3D.real * KK) / n3                             # auxPM.c:497-498
+        dens1 = (-1.0 * P3D.imag * KK) / n3
+        for d in (d0, d1, d2):
+            f = (dens1 * d / scale) + 1j * (dens0 * d / scale)   # auxPM.c:503-508
+            f[0, 0, 0] = 0.0                                     # auxPM.c:465-470
+            out.append(f)
+    return out
+
+
+def forces(P3D, nmesh, box, mg_phik=None):
+    """Forces(): k-space kernel + 3 c2r (auxPM.c:437-555).  Returns N11, N12, N13 real [N][N][N]."""
+    return [c2r(f, nmesh) for f in forces_kspace(P3D, nmesh, box, mg_phik)]
+
+
+def mtoparticles(pos, N11, N12, N13, nmesh, box, tot_numpart=None):
+    """MtoParticles: auxPM.c:560-644.  Disp is float32 (MEMORY_MODE), sums in double."""
+    N = nmesh
+    IX, IY, IZ, IXn, IYn, IZn, DX, DY, DZ, TX, TY, TZ = _cic(pos, N, box, 1.0)
+    IXn = IXn % N      # ghost slice == slice 0 of the (only) task (auxPM.c:546-551)
+    disp = np.empty((pos.shape[0], 3), dtype=np.float32)
+    for a, F in enumerate((N11, N12, N13)):
+        v = (F[IX, IY, IZ] * TX * TY * TZ + F[IX, IY, IZn] * TX * TY * DZ +
+             F[IX, IYn, IZ] * TX * DY * TZ + F[IX, IYn, IZn] * TX * DY * DZ +
+             F[IXn, IY, IZ] * DX * TY * TZ + F[IXn, IY, IZn] * DX * TY * DZ +
+             F[IXn, IYn, IZ] * DX * DY * TZ + F[IXn, IYn, IZn] * DX * DY * DZ)
+        disp[:, a] = v.astype(np.float32)
+    tot = pos.shape[0] if tot_numpart is None else tot_numpart
+    sumD = disp.astype(np.float64).sum(axis=0) / np.float64(tot)   # auxPM.c:632-640
+    return disp, sumD
+
+
+# ----------------------------------------------------------------------------- Kick / Drift
+
+def kick(vel, disp, D, D2, sumDxyz, omega, use_cola, A, dda, ddDddy, ddD2ddy, tot_numpart=None):
+    """Kick particle loop, non-SCALEDEPENDENT branch: main.c:721-739.  Mutates nothing; returns
+    (vel_new float32, disp_new float32 [mean-subtracted, as the reference leaves it], sumxyz)."""
+    disp_new = (disp.astype(np.float64) - np.asarray(sumDxyz, dtype=np.float64)[None, :]).astype(np.float32)
+    force = (-1.5 * omega) * disp_new.astype(np.float64) - \
+        (np.float64(use_cola) * (D.astype(np.float64) * ddDddy + D2.astype(np.float64) * ddD2ddy)) / A
+    vel_new = (vel.astype(np.float64) + force * dda).astype(np.float32)
+    tot = vel.shape[0] if tot_numpart is None else tot_numpart
+    sumxyz = vel_new.astype(np.float64).sum(axis=0) / np.float64(tot)
+    return vel_new, disp_new, sumxyz
+
+
+def periodic_wrap(x, box):
+    """auxPM.c:649-655 in float arithmetic (x: float32 array)."""
+    x = x.astype(np.float32).copy()
+    b = np.float32(box)
+    for _ in range(1000):
+        m = x >= b
+        if not m.any():
+            break
+        x[m] = x[m] - b
+    for _ in range(1000):
+        m = x < 0
+        if not m.any():
+            break
+        x[m] = x[m] + b
+    x[x == b] = np.float32(0.0)
+    return x
+
+
+def drift(pos, vel, D, D2, sumxyz, box, use_cola, dyyy, deltaD, deltaD2):
+    """Drift particle loop, non-SCALEDEPENDENT branch: main.c:773-783."""
+    p = (pos.astype(np.float64) + (vel.astype(np.float64) - np.asarray(sumxyz, dtype=np.float64)[None, :]) * dyyy
+         ).astype(np.float32)
+    arg = p.astype(np.float64) + np.float64(use_cola) * (D.astype(np.float64) * deltaD + D2.astype(np.float64) * deltaD2)
+    return periodic_wrap(arg.astype(np.float32), box)
+
+
+# ----------------------------------------------------------------------------- modified gravity (mg.h)
+
+def _rk(nmesh):
+    d0, d1, d2 = _dvec(nmesh)
+    return d0 * d0 + d1 * d1 + d2 * d2
+
+
+def divide_by_laplacian(P3D, nmesh, box, omega, a):
+    """DivideByLaplacian: mg.h:21-64."""
+    N = nmesh
+    normfactor = 1.0 / np.float64(N) ** 3
+    normfactor *= 1.5 * omega / a * (box / INVERSE_H0_MPCH / (2.0 * PI)) ** 2
+    RK = _rk(N)
+    with np.errstate(divide="ignore"):
+        KK = -1.0 / RK
+    with np.errstate(invalid="ignore"):
+        out = normfactor * P3D * KK
+    out[0, 0, 0] = 0.0
+    return out
+
+
+def eff_density_to_phik(dk, nmesh, coupling, massterm2):
+    """EffDensitykToPhiofk: mg.h:74-116."""
+    RK = _rk(nmesh)
+    KK = RK / (RK + massterm2)
+    out = coupling * dk * KK
+    out[0, 0, 0] = 0.0
+    return out
+
+
+def fofr_scalars(a, omega, box, fofr0, nfofr):
+    """phicrit (udf:731), coupling = 2 beta^2 with beta = 1/sqrt(6) (udf:462-470, 587-591),
+    massterm2 (mg.h:80 with mass2_of_a udf:490-498)."""
+    phicrit = 1.5 * fofr0 * ((omega + 4.0 * (1.0 - omega)) / (1.0 / (a * a * a) * omega + 4.0 * (1.0 - omega))) ** (nfofr + 1.0)
+    beta = 1.0 / np.sqrt(6.0)
+    coupling = 2.0 * beta * beta
+    a3 = a * a * a
+    fac = omega / a3 + 4.0 * (1.0 - omega)
+    fac0 = omega + 4.0 * (1.0 - omega)
+    mass2 = fac0 * (fac / fac0) ** (nfofr + 2.0) / ((1.0 + nfofr) * fofr0)
+    massterm2 = a ** 2 * mass2 / ((2.0 * PI) * INVERSE_H0_MPCH / box) ** 2
+    return phicrit, coupling, massterm2
+
+
+def fifth_force_potential_screening(P3D, dens_real, nmesh, box, omega, a, phicrit, coupling, massterm2, screening=True):
+    """ComputeFifthForce_PotentialScreening: mg.h:147-189.  dens_real = copy of delta(x) [N][N][N].
+    Returns phi_k to be added to P3D in Forces (= P3D_mgarray_two)."""
+    if not screening:
+        return eff_density_to_phik(P3D, nmesh, coupling, massterm2)
+    phik = divide_by_laplacian(P3D, nmesh, box, omega, a)
+    phi = c2r(phik, nmesh)
+    s = np.ones_like(phi)
+    neg = ~(phi >= 0.0)
+    sf = np.abs(phicrit / phi[neg])
+    s[neg] = np.minimum(sf, 1.0)                                  # udf:725-737
+    deff = dens_real * s                                          # mg.h:174-176
+    deffk = sfft.rfftn(deff, workers=-1)
+    return eff_density_to_phik(deffk, nmesh, coupling, massterm2)
+
+
+def dgp_scalars(a, omega, rcH0):
+    """beta_DGP (udf:453-455 with LCDM hubble udf:427, 445), coupling (udf:593-595), fac0 (udf:762)."""
+    H = np.sqrt(omega / (a * a * a) + 1.0 - omega)
+    dH = 1.0 / (2.0 * H) * (-3.0 * omega / (a * a * a * a))
+    beta = 1.0 + 2.0 * rcH0 * (H + a * dH / 3.0)
+    coupling = 1.0 / (3.0 * beta)
+    fac0 = 8.0 / 9.0 * omega * (rcH0 / beta) ** 2
+    return coupling, fac0
+
+
+def fifth_force_density_screening(P3D, dens_real, nmesh, box, coupling, fac0, rsmooth, screening=True):
+    """ComputeFifthForce_DensityScreening with the Gaussian filter: mg.h:197-260, 268-309, 318-322."""
+    N = nmesh
+    if not screening:
+        return P3D * coupling                                      # mg.h:212-217 (density aliases P3D)
+    RK = _rk(N)
+    kR = np.sqrt(RK) * 2.0 * PI / box * rsmooth
+    smooth = np.exp(-0.5 * kR * kR) * (1.0 / np.float64(N) ** 3)
+    ds = c2r(P3D * smooth, N)
+    fac = fac0 * (1.0 + ds)                                       # udf:762-765
+    with np.errstate(invalid="ignore", divide="ignore"):
+        sf = np.where(fac < 1e-5, 1.0, 2.0 * (np.sqrt(1.0 + fac) - 1.0) / fac)
+    deff = dens_real * (coupling * sf)                            # mg.h:243
+    return sfft.rfftn(deff, workers=-1)
+
+
+# ----------------------------------------------------------------------------- P(k) (compute_pofk.c)
+
+def adjust_pofk_parameters(nmesh, box, nbins, bintype, subtract_shotnoise, kmin_hmpc, kmax_hmpc):
+    """compute_pofk.c:86-104 + 758-805; k limits returned in integer-k units."""
+    kmin = kmin_hmpc * box / (2.0 * np.pi)
+    kmax = kmax_hmpc * box / (2.0 * np.pi)
+    if bintype not in (0, 1):
+        bintype = 0
+    if subtract_shotnoise not in (0, 1):
+        subtract_shotnoise = 1
+    if nbins <= 0:
+        nbins = nmesh
+    if kmax <= kmin:
+        kmin = 0.0 if bintype == 0 else 1.0
+        kmax = float(nmesh)
+    if kmin < 0.0:
+        kmin = 0.0 if bintype == 0 else 1.0
+    if bintype == 1 and kmin == 0.0:
+        kmin = 1.0
+    if kmax > np.sqrt(3.0) * nmesh:
+        kmax = float(nmesh)
+    return nbins, bintype, subtract_shotnoise, kmin, kmax
+
+
+def pofk_bin_index(kmag, kmin, kmax, nbins, bintype):
+    """compute_pofk.c:30-46 (C truncation of the (int) cast)."""
+    if bintype == 0:
+        return np.trunc((kmag - kmin) / (kmax - kmin) * nbins + 0.5).astype(np.int64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        idx = np.trunc(np.log(kmag / kmin) / np.log(kmax / kmin) * nbins + 0.5)
+    idx = np.where(kmag <= 0.0, -1, idx)
+    return idx.astype(np.int64)
+
+
+def compute_power_spectrum(P3D, nmesh, nsample, box, nbins, bintype, subtract_shotnoise, kmin_hmpc, kmax_hmpc):
+    """compute_power_spectrum: compute_pofk.c:71-236.  Returns (pofk, k_mean, n_modes) per bin."""
+    N = nmesh
+    nbins, bintype, shot, kmin, kmax = adjust_pofk_parameters(N, box, nbins, bintype, subtract_shotnoise, kmin_hmpc, kmax_hmpc)
+    i = np.arange(N)
+    dxy = np.where(i > N // 2, N - i, i)                           # |kx|, |ky| (compute_pofk.c:127, 135 + mirror rows)
+    dz = np.arange(N // 2 + 1)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        gxy = np.where(dxy == 0, 1.0, np.sin((PI * dxy) / float(N)) / ((PI * dxy) / float(N)))
+        gz = np.where(dz == 0, 1.0, np.sin((PI * dz) / float(N)) / ((PI * dz) / float(N)))
+    gz[N // 2] = 2.0 / PI                                          # compute_pofk.c:169
+    kmag = np.sqrt((dxy[:, None, None] ** 2 + dxy[None, :, None] ** 2 + dz[None, None, :] ** 2).astype(np.float64))
+    nk = pofk_bin_index(kmag, kmin, kmax, nbins, bintype)
+    corr = 1.0 / (gxy[:, None, None] * gxy[None, :, None] * gz[None, None, :]) ** 4.0 * (1.0 / np.float64(N) ** 6)
+    p = (P3D.real * P3D.real + P3D.imag * P3D.imag) * corr
+    w = np.full(N // 2 + 1, 2.0)
+    w[0] = 1.0
+    w[N // 2] = 1.0
+    w = np.broadcast_to(w[None, None, :], p.shape)
+    ok = (nk >= 0) & (nk < nbins)
+    pofk_bin = np.bincount(nk[ok], weights=(w * p)[ok], minlength=nbins)
+    k_bin = np.bincount(nk[ok], weights=(w * kmag)[ok], minlength=nbins)
+    n_bin = np.bincount(nk[ok], weights=w[ok], minlength=nbins)
+    pofk = np.zeros(nbins)
+    kmean = np.zeros(nbins)
+    good = n_bin > 0
+    pofk[good] = pofk_bin[good] / n_bin[good] * box ** 3
+    if shot:
+        pofk[good] -= (box / float(nsample)) ** 3
+    kmean[good] = k_bin[good] / n_bin[good] * 2.0 * np.pi / box
+    return pofk, kmean, n_bin
+
+
+# ----------------------------------------------------------------------------- one full step
+
+def get_displacements(pos, nmesh, nsample, box, model="none", mg=None, grid_dtype=np.float64, pofk=None):
+    """GetDisplacements for a single task: auxPM.c:37-103.  mg = dict of per-step scalars.
+    Returns dict(disp, sumDxyz, density_k, pofk)."""
+    N = nmesh
+    dens = ptomesh_deposit(pos, N, nsample, box, grid_dtype)
+    dens_real = dens[:, :, :N].astype(np.float64)
+    P3D = r2c(dens, N)
+    out = {}
+    if pofk is not None:
+        out["pofk"] = compute_power_spectrum(P3D, N, nsample, box, **pofk)
+    phik = None
+    if model == "fofr":
+        phik = fifth_force_potential_screening(P3D, dens_real, N, box, mg["omega"], mg["a"], mg["phi_crit"],
+                                               mg["coupling"], mg["massterm2"], mg.get("screening", True))
+    elif model == "dgp":
+        phik = fifth_force_density_screening(P3D, dens_real, N, box, mg["coupling"], mg["dgp_fac0"], mg["rsmooth"],
+                                             mg.get("screening", True))
+    elif model == "geff":
+        P3D = P3D * mg["geff"]
+    N11, N12, N13 = forces(P3D, N, box, phik)
+    disp, sumD = mtoparticles(pos, N11, N12, N13, N, box)
+    out.update(disp=disp, sumDxyz=sumD, density_k=P3D, force_grids=(N11, N12, N13), density=dens)
+    return out
