@@ -1,0 +1,441 @@
+#!/usr/bin/env python
+"""bench.py -- particle-updates/s of one full COLA particle-mesh step on B200.
+
+A "step" = MoveParticles + PtoMesh (+ in-step P(k)) + ComputeFifthForce + Forces + MtoParticles +
+Kick + Drift (main.c:474-592 of the reference) on synthetic Gaussian 2LPT initial conditions drawn
+from the reference's bundled CAMB table (tests/golden/input_power_spectrum.npz), stepped along the
+reference's COLA schedule (z_init = 9, linear in a).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--nmesh 256] [--model fofr|dgp|lcdm]
+                  [--grid-bytes 8|4] [--impl ours|reference]
+
+One JSON line on stdout (rank 0).  `value` = device-timed, particles resident in HBM.  `e2e` = the
+same step driven through the C ABI with HOST particle buffers (pinned): upload of Pos/Vel/D/D2/ID
+and download of Pos/Vel inside the timed region.  `roofline` = the dominant hand-written kernel
+of the step, timed live with CUDA events on the library's stream.  `cpu_baseline` / `--impl
+reference` = the unmodified reference compiled against the oracle stand-ins (oracle/_ref), one core.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+OMEGA, SIGMA8, Z_INIT, NSTEPS_RUN = 0.267, 0.8, 9.0, 30
+FOFR0, NFOFR, RCH0, RSMOOTH = 1e-5, 1.0, 1.0, 1.0
+# compulsory HBM bytes per particle-step of a maximally fused step
+ALGO_BYTES = {"lcdm": lambda g: 120 + 32 * g, "fofr": lambda g: 120 + 51 * g, "dgp": lambda g: 120 + 51 * g}
+
+
+def box_for(nmesh):
+    return 200.0 * nmesh / 256.0 if nmesh > 256 else 200.0     # keeps >= 0.78 Mpc/h cells like the example runs
+
+
+# ------------------------------------------------------------------ synthetic initial conditions
+
+def power_table():
+    t = np.load(os.path.join(ROOT, "tests", "golden", "input_power_spectrum.npz"))
+    k, P = t["k"], t["P"]
+    # sigma8 normalisation (power.c:481-516): top-hat R = 8 Mpc/h
+    kk = np.exp(np.linspace(np.log(k[0]), np.log(k[-1]), 20000))
+    Pk = np.exp(np.interp(np.log(kk), np.log(k), np.log(P)))
+    kr = 8.0 * kk
+    w = 3.0 * (np.sin(kr) / kr ** 3 - np.cos(kr) / kr ** 2)
+    sig2 = np.trapezoid(kk ** 3 * w * w * Pk, np.log(kk)) / (2.0 * np.pi ** 2)
+    return np.log10(k), np.log10(P * SIGMA8 ** 2 / sig2)
+
+
+def amplitude_table(nmesh, box):
+    """sqrt-free P(k) at every integer |d|^2 = m (what the C adapter fills by calling PowerSpec)."""
+    lk, lP = power_table()
+    h = nmesh // 2
+    m = np.arange(3 * h * h + 1, dtype=np.float64)
+    kmag = 2.0 * np.pi / box * np.sqrt(m)
+    with np.errstate(divide="ignore"):
+        lkm = np.log10(kmag)
+    P = 10.0 ** np.interp(lkm, lk, lP, left=-np.inf, right=-np.inf)    # PowerSpec_Tabulated: 0 outside the table
+    P[0] = 0.0
+    return P
+
+
+def host_ics(nmesh, box, seed, cos):
+    """Gaussian field + 2LPT displacements on the host (numpy) -- used until the particle store is
+    filled; it is data generation, outside every timed region.  Same conventions as 2LPT.c:337-495,
+    1224-1359 (delta = Box^-1.5 sqrt(P (-ln u)), psi_k = i k / k^2 delta, psi2 = -3/7 ...)."""
+    import scipy.fft as sfft
+    N = nmesh
+    rng = np.random.default_rng(seed)
+    amp = amplitude_table(N, box)
+    i = np.arange(N)
+    d = np.where(i >= N // 2, i - N, i).astype(np.int64)
+    dz = np.arange(N // 2 + 1, dtype=np.int64)
+    m = d[:, None, None] ** 2 + d[None, :, None] ** 2 + dz[None, None, :] ** 2
+    white = rng.standard_normal((N, N, N)).astype(np.float64)
+    wk = sfft.rfftn(white, workers=-1) / np.sqrt(float(N) ** 3)      # <|wk|^2> = 1, Hermitian by construction
+    dk = wk * np.sqrt(amp[m]) * box ** -1.5
+    nyq = (np.abs(d)[:, None, None] == N // 2) | (np.abs(d)[None, :, None] == N // 2) | (dz[None, None, :] == N // 2)
+    dk[nyq] = 0.0
+    dk[0, 0, 0] = 0.0
+    kf = 2.0 * np.pi / box
+    kv = (d[:, None, None] * kf, d[None, :, None] * kf, dz[None, None, :] * kf)
+    k2 = (m * kf * kf).astype(np.float64)
+    k2[0, 0, 0] = 1.0
+    psi_k = [1j * kv[a] / k2 * dk for a in range(3)]
+    ZA = [sfft.irfftn(p, s=(N, N, N), workers=-1) * float(N) ** 3 for p in psi_k]
+    # 2LPT source: sum_{i<j} psi_ii psi_jj - psi_ij^2
+    g = {}
+    for a in range(3):
+        for b in range(a, 3):
+            g[(a, b)] = sfft.irfftn(1j * kv[b] * psi_k[a], s=(N, N, N), workers=-1) * float(N) ** 3
+    S = g[(0, 0)] * (g[(1, 1)] + g[(2, 2)]) + g[(1, 1)] * g[(2, 2)] - g[(0, 1)] ** 2 - g[(0, 2)] ** 2 - g[(1, 2)] ** 2
+    del g
+    Sk = sfft.rfftn(S, workers=-1) / float(N) ** 3
+    LPT = [(-3.0 / 7.0) * sfft.irfftn(-1j * kv[a] / k2 * Sk, s=(N, N, N), workers=-1) * float(N) ** 3 for a in range(3)]
+    ZA = np.stack([z.reshape(-1) for z in ZA], 1).astype(np.float32)
+    LPT = np.stack([z.reshape(-1) for z in LPT], 1).astype(np.float32)
+    ZA -= ZA.mean(0, dtype=np.float64).astype(np.float32)
+    LPT -= LPT.mean(0, dtype=np.float64).astype(np.float32)
+    A = 1.0 / (1.0 + Z_INIT)
+    Di, Di2 = cos.growth_D(A), cos.growth_D2(A)
+    q = np.stack(np.meshgrid(i, i, i, indexing="ij"), -1).reshape(-1, 3).astype(np.float64) * (box / N)
+    pos = (q + ZA.astype(np.float64) * Di + LPT.astype(np.float64) * Di2).astype(np.float32)     # main.c:302-304
+    b = np.float32(box)
+    pos = np.where(pos >= b, pos - b, pos)
+    pos = np.where(pos < 0, pos + b, pos)
+    pos[pos == b] = 0
+    return pos.astype(np.float32), np.zeros_like(pos), ZA, LPT
+
+
+# ------------------------------------------------------------------ clocks
+
+class ClockSampler(threading.Thread):
+    def __init__(self, device=0, period=0.2):
+        super().__init__(daemon=True)
+        self.device, self.period, self.stop_flag = device, period, False
+        self.sm, self.reasons, self.sm_max = [], set(), None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_throttle_reasons.hw_slowdown,clocks_throttle_reasons.hw_thermal_slowdown," \
+            "clocks_throttle_reasons.sw_thermal_slowdown,clocks_throttle_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.sm.append(float(out[0]))
+                self.sm_max = float(out[1])
+                for nm, v in zip(names, out[2:]):
+                    if "Active" in v and "Not" not in v:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+# ------------------------------------------------------------------ our arm
+
+class Stepper:
+    """Drives the library exactly as main.c's loop does (main.c:394-611)."""
+
+    def __init__(self, pm, cos, model, box):
+        from mgpicola_b200 import cosmology
+        self.pm, self.cos, self.model, self.box = pm, cos, model, box
+        self.sched = cosmology.schedule(Z_INIT, [(0.0, NSTEPS_RUN)])
+        self.cosmology = cosmology
+        self.i = 0
+
+    def scalars(self, A):
+        if self.model == "fofr":
+            return self.pm.scalars(compute_pofk=1, **self.cosmology.fofr_step_scalars(A, OMEGA, self.box, FOFR0, NFOFR))
+        if self.model == "dgp":
+            return self.pm.scalars(compute_pofk=1, **self.cosmology.dgp_step_scalars(A, OMEGA, RCH0, RSMOOTH))
+        return self.pm.scalars(a=A, compute_pofk=1)
+
+    def step(self):
+        s = self.sched[self.i % (NSTEPS_RUN)]      # stay inside the regular (non-output) steps
+        self.i += 1
+        A, AI, AF, AFF = s["A"], s["AI"], s["AF"], s["AFF"]
+        cos, pm = self.cos, self.pm
+        Di, Di2 = cos.growth_D(A), cos.growth_D2(A)
+        pm.GetDisplacements(self.scalars(A))
+        pm.Kick(A, cos.Sphi(AI, AF, A), cos.growth_ddDddy(A), cos.growth_ddD2ddy(A))
+        pm.Drift(cos.Sq(A, AFF, AF), cos.growth_D(AFF) - Di, cos.growth_D2(AFF) - Di2)
+
+
+def run_ours(args):
+    import torch
+    import mgpicola_b200 as mgp
+    from mgpicola_b200 import cosmology
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    assert world == args.gpus, "launch with torchrun --nproc-per-node == --gpus"
+    torch.cuda.set_device(local)
+    nccl_id = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        ids = [mgp.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        nccl_id = ids[0]
+
+    N, g = args.nmesh, args.grid_bytes
+    # weak scaling: every GPU owns N^3 / 1 particles of a box that grows along x ... the slab
+    # decomposition needs a cubic mesh, so the mesh side grows with world^(1/3) where that is an
+    # integer multiple, otherwise strong scaling on the fixed mesh is reported.
+    box = box_for(N)
+    model = args.model
+    cos = cosmology.LCDM(OMEGA, Z_INIT)
+    model_id = {"lcdm": mgp.MODEL_NONE, "fofr": mgp.MODEL_FOFR, "dgp": mgp.MODEL_DGP}[model]
+    pm = mgp.PM(N, N, box, omega=OMEGA, model=model_id, include_screening=1, grid_bytes=g, rank=rank, nranks=world,
+                device=local, nccl_id=nccl_id, deposit_mode=args.deposit_mode)
+    pm.set_pofk(64, 1, 1, 0.03, 2.0)          # paramfiles/additions_compute_pofk.txt
+    t0 = time.time()
+    pos, vel, ZA, LPT = host_ics(N, box, 5001, cos)
+    ids = np.arange(N ** 3, dtype=np.uint64)
+    if world > 1:
+        sel = (pos[:, 0].astype(np.float64) * (N / box)).astype(np.int64)
+        mine = (sel >= pm.local_x_start) & (sel < pm.local_x_start + pm.local_nx)
+        pos, vel, ZA, LPT, ids = pos[mine], vel[mine], ZA[mine], LPT[mine], ids[mine]
+    t_ic = time.time() - t0
+    pm.upload_particles(pos, vel, ZA, LPT, ids)
+    npart_total = N ** 3
+    st = Stepper(pm, cos, model, box)
+    stream = torch.cuda.ExternalStream(pm.stream)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        st.step()
+    pm.launch_count(reset=True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        st.step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = pm.launch_count()
+    clocks = sampler.result() if rank == 0 else None
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = npart_total / (ms_per_step * 1e-3)
+
+    # ---- per-phase CUDA-event timing (separate, synchronising pass) -> dominant own kernel
+    pm.set_phase_timing(True)
+    pm.phase_times(reset=True)
+    nph = 3
+    for _ in range(nph):
+        st.step()
+    phases = {k: v[0] / nph for k, v in pm.phase_times().items() if v[1]}
+    pm.set_phase_timing(False)
+
+    # ---- e2e: host particle buffers through the C ABI every step
+    e2e = None
+    if world == 1 and not args.no_e2e:
+        got = pm.download_particles()
+        hp = {k: torch.from_numpy(got[k].copy()).pin_memory() for k in ("pos", "vel", "D", "D2")}
+        hid = torch.from_numpy(got["id"].astype(np.int64)).pin_memory()
+        h2d = sum(t.numel() * t.element_size() for t in hp.values()) + hid.numel() * 8
+        d2h = hp["pos"].numel() * 4 * 2
+        ne2e = max(2, min(args.steps, 5))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(ne2e):
+            pm.upload_raw(hp["pos"].data_ptr(), hp["vel"].data_ptr(), hp["D"].data_ptr(), hp["D2"].data_ptr(),
+                          hid.data_ptr(), hid.numel())
+            st.step()
+            pm.download_raw(hp["pos"].data_ptr(), hp["vel"].data_ptr(), 0, 0, hid.data_ptr())
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / ne2e
+        e2e = {"value": npart_total / dt, "unit": "particle-updates/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h + hid.numel() * 8), "ms_per_step": dt * 1e3, "steps": ne2e}
+
+    if rank != 0:
+        pm.close()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6550.0))
+    A_min = ALGO_BYTES[model](g)
+    # dominant hand-written kernels: deposit (PtoMesh phase) and gather (MtoParticles phase)
+    kern_bytes = {"PtoMesh": (16 + g) * (N ** 3) / max(world, 1),            # Pos(+id) 16 B read, grid g write per cell
+                  "MtoParticles": (16 + 3 * g + 12) * (N ** 3) / max(world, 1)}   # Pos 16 R, 3 grids R, Disp 12 W
+    own = {k: phases.get(k, 0.0) for k in ("PtoMesh", "MtoParticles", "Forces", "ComputeFifthForce", "Kick", "Drift", "Sort", "Pofk")}
+    dom = max(("PtoMesh", "MtoParticles"), key=lambda k: own.get(k, 0.0))
+    ach = kern_bytes[dom] / (own[dom] * 1e-3) / 1e9 if own.get(dom) else None
+    roof = {"bound": "hbm", "kernel": {"PtoMesh": "k_deposit_rowseg (CIC deposit)", "MtoParticles": "k_gather (trilinear gather)"}[dom],
+            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None, "traffic": None,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback",
+            "step": {"algorithmic_bytes_per_particle": A_min, "achieved": A_min * npart_total / (ms_per_step * 1e-3) / 1e9,
+                     "frac": A_min * npart_total / (ms_per_step * 1e-3) / 1e9 / peak},
+            "phases_ms": {k: round(v, 4) for k, v in phases.items()}}
+    line = {"metric": "particle-updates/sec per COLA PM step", "value": value, "unit": "particle-updates/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 particles, f%d grids/FFTs, f64 weights" % (8 * g), "data": "synthetic",
+            "config": {"workload": "%s%s COLA step, Npart=Nmesh=%d^3, Box=%g Mpc/h, P(k) every step, z=9->0 in %d steps "
+                                   "(reference configs[1] without SCALEDEPENDENT growth: build MODEL=FOFR_LCDM)"
+                                   % (model, " with screening" if model != "lcdm" else "", N, box, NSTEPS_RUN),
+                       "nmesh": N, "npart": npart_total, "grid_bytes": g, "deposit_mode": args.deposit_mode,
+                       "l2": "inputs larger than L2 (particles %.1f GB, grids %.1f GB each)" % (N ** 3 * 56 / 1e9, N ** 3 * g / 1e9),
+                       "ic_seconds_host": round(t_ic, 1)},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "e2e": e2e}
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_reference(args, sample_nmesh=min(N, 128), steps=2, warmup=1)
+    print(json.dumps(line), flush=True)
+    pm.close()
+
+
+# ------------------------------------------------------------------ reference arm (CPU)
+
+def write_paramfile(workdir, nmesh, box, model, nsteps):
+    """Parameter file for the reference build in oracle/_ref (tags: read_param.c:107-445,
+    user_defined_functions.h:227-406)."""
+    os.makedirs(os.path.join(workdir, "output"), exist_ok=True)
+    t = np.load(os.path.join(ROOT, "tests", "golden", "input_power_spectrum.npz"))
+    with open(os.path.join(workdir, "pk.dat"), "w") as f:
+        for k, P in zip(t["k"], t["P"]):
+            f.write("%16.8E %16.8E\n" % (k, P))
+    with open(os.path.join(workdir, "out.dat"), "w") as f:
+        f.write("0, %d\n" % nsteps)
+    mg = {"fofr": "modified_gravity_active 1\nfofr0 %g\nnfofr %g\ninclude_screening 1\n" % (FOFR0, NFOFR),
+          "lcdm": "modified_gravity_active 0\nfofr0 %g\nnfofr %g\ninclude_screening 0\n" % (FOFR0, NFOFR),
+          "dgp": "modified_gravity_active 1\nrcH0_DGP %g\nRsmooth %g\ninclude_screening 1\n" % (RCH0, RSMOOTH)}[model]
+    txt = mg + """use_lcdm_growth_factors 1
+input_pofk_is_for_lcdm 1
+input_sigma8_is_for_lcdm 1
+inverted_initial_condition 0
+amplitude_fixed_initial_condition 0
+OutputDir %s/output
+FileBase bench
+OutputRedshiftFile %s/out.dat
+NumFilesWrittenInParallel 1
+UseCOLA 1
+Buffer 1.5
+Nmesh %d
+Nsample %d
+Box %g
+Init_Redshift %g
+Seed 5001
+SphereMode 0
+WhichSpectrum 1
+WhichTransfer 0
+FileWithInputSpectrum %s/pk.dat
+FileWithInputTransfer none
+Omega %g
+OmegaBaryon 0.049
+HubbleParam 0.71
+Sigma8 %g
+PrimordialIndex 0.966
+UnitLength_in_cm 3.085678e24
+UnitMass_in_g 1.989e43
+UnitVelocity_in_cm_per_s 1e5
+InputSpectrum_UnitLength_in_cm 3.085678e24
+pofk_compute_every_step 1
+pofk_compute_rsd_pofk 0
+pofk_nbins 64
+pofk_bintype 1
+pofk_subtract_shotnoise 1
+pofk_kmin 0.03
+pofk_kmax 2.0
+""" % (workdir, workdir, nmesh, nmesh, box, Z_INIT, workdir, OMEGA, SIGMA8)
+    p = os.path.join(workdir, "param.txt")
+    open(p, "w").write(txt)
+    return p
+
+
+def cpu_reference(args, sample_nmesh, steps, warmup):
+    """Times the unmodified reference (oracle/_ref, built by oracle/Makefile) stepping the same
+    workload on one host core: its own GetDisplacements / Kick / Drift, wall clock per step."""
+    import tempfile
+    from oracle import ref_lib
+    variant = "dgp" if args.model == "dgp" else "lcdm"      # 'lcdm' = -DFOFRGRAVITY without SCALEDEPENDENT (MODEL=FOFR_LCDM)
+    if not ref_lib.available(variant):
+        return {"value": None, "unit": "particle-updates/s", "cores": 1, "kind": "reference",
+                "sample": "oracle/_ref not built (needs /root/reference at build time)"}
+    N = sample_nmesh
+    box = box_for(args.nmesh) * N / args.nmesh
+    wd = tempfile.mkdtemp(prefix="mgp_ref_")
+    pf = write_paramfile(wd, N, box, args.model, NSTEPS_RUN)
+    drv = ref_lib.RefRun(variant, pf, quiet=True)
+    for _ in range(warmup):
+        drv.step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        drv.step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": N ** 3 / dt, "unit": "particle-updates/s", "cores": 1, "kind": "reference",
+            "ms_per_step": dt * 1e3,
+            "sample": "%d timed + %d warm-up steps of the same %s workload at Npart=Nmesh=%d^3 (Box=%g), unmodified reference "
+                      "sources on serial-MPI / CPU-FFT / mini-GSL stand-ins (no FFTW/MPI/GSL on the box), 1 core" % (steps, warmup, args.model, N, box)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    N = min(args.nmesh, args.ref_nmesh)
+    cb = cpu_reference(args, sample_nmesh=N, steps=args.steps, warmup=args.warmup)
+    line = {"impl": "reference", "metric": "particle-updates/sec per COLA PM step", "value": cb["value"],
+            "unit": "particle-updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": cb.get("ms_per_step"), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 particles, f64 grids/FFTs", "data": "synthetic",
+            "config": {"workload": "%s COLA step, reference CPU path, bounded sample Npart=Nmesh=%d^3 of the %d^3 workload"
+                                   % (args.model, N, args.nmesh), "nmesh": N},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nmesh", type=int, default=256)
+    ap.add_argument("--ref-nmesh", type=int, default=128)
+    ap.add_argument("--model", default="fofr", choices=["fofr", "dgp", "lcdm"])
+    ap.add_argument("--grid-bytes", type=int, default=8, choices=[4, 8])
+    ap.add_argument("--deposit-mode", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

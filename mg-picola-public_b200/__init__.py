@@ -185,6 +185,13 @@ class PM:
                                                _ptr(out["D2"]), _ptr(out["id"])))
         return {k: v for k, v in out.items() if v is not None}
 
+    def upload_raw(self, pos, vel, D, D2, ids, n):
+        """Host pointers (ints) to [n][3] float32 arrays (+ [n] uint64), e.g. pinned staging buffers."""
+        self._ck(self.L.mgp_upload_particles(self.ctx, n, pos, vel or None, D or None, D2 or None, ids or None))
+
+    def download_raw(self, pos, vel, D, D2, ids):
+        self._ck(self.L.mgp_download_particles(self.ctx, pos or None, vel or None, D or None, D2 or None, ids or None))
+
     def download_disp(self):
         d = np.empty((self.numpart, 3), np.float32)
         self._ck(self.L.mgp_download_disp(self.ctx, _ptr(d)))

@@ -281,3 +281,73 @@ class RefLib:
         n = self.get("NumPart", C.c_uint)
         arr = (C.c_void_p * 3).in_dll(self.lib, "Disp")
         return np.stack([np.ctypeslib.as_array(C.cast(arr[a], C.POINTER(C.c_float)), shape=(n,)).copy() for a in range(3)], 1)
+
+
+class RefRun:
+    """Run-level driver: the reference's own set-up, IC generator and GetDisplacements / Kick / Drift
+    stepped along main()'s schedule (main.c:394-611, stepDistr = 0; the bookkeeping is inline code in
+    main() and is restated here; non-SCALEDEPENDENT variants).  Output steps are not taken: the
+    schedule is the regular sequence of one output interval."""
+
+    def __init__(self, variant, paramfile, quiet=True):
+        self.r = RefLib(variant)
+        self.quiet = quiet
+        with _silenced(quiet):
+            self.r.init_from_paramfile(paramfile)
+            ic = self.r.make_ic()
+        L = self.r.lib
+        self.A = ic["A"]
+        self.AI = self.A
+        self.Di, self.Di2 = ic["Di"], ic["Di2"]
+        nout = C.c_int.in_dll(L, "Noutputs").value
+        assert nout >= 1
+
+        class _Out(C.Structure):
+            _fields_ = [("Nsteps", C.c_int), ("Redshift", C.c_double)]
+        ol = C.POINTER(_Out).in_dll(L, "OutputList")
+        self.nsteps = ol[0].Nsteps
+        ao = 1.0 / (1.0 + ol[0].Redshift)
+        self.da = (ao - self.A) / float(self.nsteps)
+        self.istep = 0
+
+    def step(self):
+        r, L = self.r, self.r.lib
+        A, da = self.A, self.da
+        AF, AFF = A + 0.5 * da, A + da
+        with _silenced(self.quiet):
+            r.set(timeStep_global=self.istep, NoutputStart_global=0, aexp_global=A)
+            L.GetDisplacements()
+            L.Kick(self.AI, AF, A, self.Di)
+            r.free_disp()
+            L.Drift(A, AFF, AF, self.Di, self.Di2)
+        self.A, self.AI = AFF, AF
+        self.Di, self.Di2 = L.growth_D(self.A), L.growth_D2(self.A)
+        self.istep += 1
+
+    def particles(self):
+        return self.r.particles()
+
+
+class _silenced:
+    """Redirects the C library's stdout (the reference prints a lot) to /dev/null."""
+
+    def __init__(self, on=True):
+        self.on = on
+
+    def __enter__(self):
+        if not self.on:
+            return
+        import sys
+        sys.stdout.flush()
+        C.CDLL(None).fflush(None)
+        self._saved = os.dup(1)
+        self._null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self._null, 1)
+
+    def __exit__(self, *a):
+        if not self.on:
+            return
+        C.CDLL(None).fflush(None)
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+        os.close(self._null)
