@@ -124,6 +124,8 @@ int mgp_upload_particles(mgp_ctx *ctx, uint64_t n, const float *pos, const float
 int mgp_download_particles(mgp_ctx *ctx, float *pos, float *vel, float *D, float *D2, uint64_t *id);
 /* Disp[3][NumPart] of MtoParticles (auxPM.c:605-630), as [n][3] */
 int mgp_download_disp(mgp_ctx *ctx, float *disp);
+/* the inverse: load Disp[3][NumPart] from the host as [n][3] (a driver that keeps its own Disp, tests) */
+int mgp_upload_disp(mgp_ctx *ctx, const float *disp);
 
 /* ---- the per-step force path ---- */
 /* MoveParticles (auxPM.c:108-275): slab ownership + migration; also (re)sorts by cell */

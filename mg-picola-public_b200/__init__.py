@@ -69,6 +69,7 @@ def load_library(path=None):
     L.mgp_upload_particles.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mgp_download_particles.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mgp_download_disp.argtypes = [C.c_void_p, C.c_void_p]
+    L.mgp_upload_disp.argtypes = [C.c_void_p, C.c_void_p]
     L.mgp_move_particles.argtypes = [C.c_void_p]
     L.mgp_ptomesh.argtypes = [C.c_void_p, C.POINTER(StepScalars)]
     L.mgp_compute_fifth_force.argtypes = [C.c_void_p, C.POINTER(StepScalars)]
@@ -196,6 +197,11 @@ class PM:
         d = np.empty((self.numpart, 3), np.float32)
         self._ck(self.L.mgp_download_disp(self.ctx, _ptr(d)))
         return d
+
+    def upload_disp(self, disp):
+        d = _f32(disp)
+        assert d.shape == (self.numpart, 3)
+        self._ck(self.L.mgp_upload_disp(self.ctx, _ptr(d)))
 
     # ---- the reference's per-step functions ----
     @staticmethod

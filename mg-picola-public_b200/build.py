@@ -46,8 +46,19 @@ def build(verbose=False, force=False):
             if r.returncode:
                 raise RuntimeError("nvcc failed: " + " ".join(cmd))
     if jobs or not os.path.exists(LIB):
+        # NCCL: link the copy PyTorch bundles when there is one (2.28.x), so that a process that loads both
+        # this library and torch sees ONE libnccl.so.2; the system library (2.27.x) otherwise.
+        nccl = ["-lnccl"]
+        try:
+            import importlib.util
+            sp = importlib.util.find_spec("nvidia.nccl")
+            d = os.path.join(list(sp.submodule_search_locations)[0], "lib")
+            if os.path.exists(os.path.join(d, "libnccl.so.2")):
+                nccl = ["-Xlinker", os.path.join(d, "libnccl.so.2"), "-Xlinker", "-rpath," + d]
+        except Exception:
+            pass
         cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + [
-            "-lcufft", "-lnccl", "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
+            "-lcufft"] + nccl + ["-Xlinker", "-rpath,/usr/local/cuda/lib64"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode:
             sys.stderr.write(r.stdout + r.stderr)

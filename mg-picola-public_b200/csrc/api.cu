@@ -263,6 +263,20 @@ int mgp_download_disp(mgp_ctx *ctx, float *disp) {
   API_END
 }
 
+int mgp_upload_disp(mgp_ctx *ctx, const float *disp) {
+  API_BEGIN
+  CTX(ctx);
+  REQUIRE(disp != nullptr, MGP_ERR_INVALID, "mgp_upload_disp: NULL");
+  std::vector<float> tmp(c.np);
+  for (int a = 0; a < 3; a++) {
+    for (size_t i = 0; i < c.np; i++) tmp[i] = disp[3 * i + a];
+    CK(cudaMemcpyAsync(c.disp + (size_t) a * c.cap, tmp.data(), c.np * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+  }
+  c.have_disp = true;
+  API_END
+}
+
 int mgp_move_particles(mgp_ctx *ctx) {
   API_BEGIN
   CTX(ctx);

@@ -351,3 +351,21 @@ class _silenced:
         os.dup2(self._saved, 1)
         os.close(self._saved)
         os.close(self._null)
+
+
+def tap_reset(reflib):
+    reflib.lib.mgp_shim_tap_reset()
+
+
+def tap_arrays(reflib):
+    """Payloads of the MPI_Allreduce calls (arrays of >= 4 doubles) since tap_reset, oldest first."""
+    L = reflib.lib
+    L.mgp_shim_tap_total.restype = C.c_long
+    L.mgp_shim_tap_get.argtypes = [C.c_long, C.POINTER(C.c_double)]
+    tot = L.mgp_shim_tap_total()
+    out = []
+    buf = (C.c_double * 8192)()
+    for i in range(max(0, tot - 16), tot):
+        n = L.mgp_shim_tap_get(i, buf)
+        out.append(np.array(buf[:n]))
+    return out

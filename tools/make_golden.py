@@ -1,0 +1,125 @@
+"""Generates tests/golden/*.npz from the UNMODIFIED reference compiled into oracle/_ref.
+
+Run in the build container (needs oracle/_ref, i.e. /root/reference at build time):
+    python tools/make_golden.py
+The fixtures are what lets the oracle and the CUDA path be checked against the reference's own
+results on machines where the reference cannot be built.  Sizes are small on purpose (16^3).
+
+  step_<model>.npz   one force evaluation on a seeded clustered particle set: inputs (pos, vel, D, D2,
+                     step scalars) and the reference's density_k, phi_k (MG), Disp, sumDxyz, P(k) sums
+  kickdrift.npz      Kick + Drift on seeded inputs (bit-exact floats)
+  run_fofr.npz       reference ICs (seed 5001) + 3 full COLA steps with f(R) screening: particle
+                     state before / after and the per-step in-code P(k) sums
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from oracle import ref_lib                    # noqa: E402
+from oracle import pm_oracle as po            # noqa: E402
+import test_oracle_vs_ref as T                # noqa: E402
+import bench                                  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+OMEGA = T.OMEGA
+POFK = dict(pofk_nbins=24, pofk_bintype=1, pofk_subtract_shotnoise=1, pofk_kmin=0.05, pofk_kmax=2.0)
+
+
+def one_step(model, variant, N=16, box=50.0, a=0.7, seed=101, extra=None):
+    pos, vel, D, D2 = T.particles(N, box, seed)
+    g = dict(POFK)
+    g.update(extra or {})
+    mg = model != "lcdm"
+    r = T.ref_setup(variant, N, box, pos, vel, D, D2, mg=mg, aexp_global=a, **g)
+    r.set_str("OutputDir", "/tmp")
+    r.set_str("FileBase", "golden")
+    with ref_lib._silenced(True):
+        r.lib.PtoMesh()
+        dk = r.grid_k("density").copy()
+        ref_lib.tap_reset(r)
+        r.lib.compute_power_spectrum(r._keep["density"].ctypes.data, a, b"CDM")
+        sums = ref_lib.tap_arrays(r)[-3:]
+        phik = None
+        if mg:
+            r.lib.ComputeFifthForce()
+            phik = r.grid_k("mgarray_two").copy()
+        r.lib.Forces()
+        F = np.stack([r.grid(nm)[:N, :, :N].copy() for nm in ("N11", "N12", "N13")])
+        r.alloc_disp()
+        r.lib.MtoParticles()
+    out = dict(N=N, box=box, a=a, omega=OMEGA, pos=pos, vel=vel, D=D, D2=D2, density_k=dk, force=F, disp=r.disp(),
+               sumDxyz=r.get3("sumDxyz"), pofk_sum=sums[0], pofk_n=sums[1], pofk_ksum=sums[2],
+               pofk_cfg=np.array([g["pofk_nbins"], g["pofk_bintype"], g["pofk_subtract_shotnoise"], g["pofk_kmin"], g["pofk_kmax"]]))
+    if phik is not None:
+        out["phik"] = phik
+    if extra:
+        for k, v in extra.items():
+            out["par_" + k] = v
+    np.savez_compressed(os.path.join(OUT, "step_%s.npz" % model), **out)
+    print("step_%s" % model, {k: getattr(v, "shape", v) for k, v in out.items() if k in ("density_k", "disp")})
+
+
+def kickdrift(N=12, box=40.0):
+    pos, vel, D, D2 = T.particles(N, box, 5)
+    n = pos.shape[0]
+    r = T.ref_setup("lcdm", N, box, pos, vel, D, D2)
+    with ref_lib._silenced(True):
+        r.init_from_paramfile(T._paramfile(N, box))
+        r.set(TotNumPart=n)
+        r.set_particles(pos, vel, D, D2)
+    L = r.lib
+    disp = (np.random.default_rng(0).standard_normal((n, 3)) * 0.3).astype(np.float32)
+    bufs = r.alloc_disp()
+    for a in range(3):
+        bufs[a][:n] = disp[:, a]
+    sumD = np.array([1e-3, -2e-3, 5e-4])
+    r.set3("sumDxyz", sumD)
+    AI, AF, A, AFF = 0.31, 0.33, 0.32, 0.34
+    Di, Di2 = L.growth_D(A), L.growth_D2(A)
+    sc = dict(A=A, dda=L.Sphi(AI, AF, A), ddDddy=L.growth_ddDddy(A), ddD2ddy=L.growth_ddD2ddy(A), dyyy=L.Sq(A, AFF, AF),
+              deltaD=L.growth_D(AFF) - Di, deltaD2=L.growth_D2(AFF) - Di2)
+    L.Kick(AI, AF, A, Di)
+    vel1 = r.particles()["Vel"].copy()
+    sumxyz = r.get3("sumxyz")
+    L.Drift(A, AFF, AF, Di, Di2)
+    pos1 = r.particles()["Pos"].copy()
+    np.savez_compressed(os.path.join(OUT, "kickdrift.npz"), N=N, box=box, omega=OMEGA, pos=pos, vel=vel, D=D, D2=D2, disp=disp,
+                        sumDxyz=sumD, vel_after=vel1, disp_after=r.disp(), sumxyz=sumxyz, pos_after=pos1, **sc)
+    print("kickdrift", n)
+
+
+def run_fofr(N=16, box=60.0, nsteps=3):
+    pf = bench.write_paramfile("/tmp/mgp_golden_run", N, box, "fofr", 10)
+    run = ref_lib.RefRun("lcdm", pf)
+    run.r.set(**POFK)
+    L = run.r.lib
+    P0 = run.particles().copy()
+    steps = []
+    pk = []
+    for it in range(nsteps):
+        A, AI, da, Di, Di2 = run.A, run.AI, run.da, run.Di, run.Di2
+        AF, AFF = A + 0.5 * da, A + da
+        steps.append([A, L.Sphi(AI, AF, A), L.growth_ddDddy(A), L.growth_ddD2ddy(A), L.Sq(A, AFF, AF), L.growth_D(AFF) - Di,
+                      L.growth_D2(AFF) - Di2])
+        ref_lib.tap_reset(run.r)
+        run.step()
+        taps = [t for t in ref_lib.tap_arrays(run.r) if len(t) == POFK["pofk_nbins"]]
+        pk.append(np.stack(taps[:3]))
+    P1 = run.particles().copy()
+    np.savez_compressed(os.path.join(OUT, "run_fofr.npz"), N=N, box=box, omega=OMEGA, fofr0=1e-5, nfofr=1.0,
+                        id0=P0["ID"], pos0=P0["Pos"], vel0=P0["Vel"], D=P0["D"], D2=P0["D2"],
+                        id1=P1["ID"], pos1=P1["Pos"], vel1=P1["Vel"], steps=np.array(steps), pofk_sums=np.stack(pk),
+                        pofk_cfg=np.array([POFK["pofk_nbins"], POFK["pofk_bintype"], 1, POFK["pofk_kmin"], POFK["pofk_kmax"]]))
+    print("run_fofr", P0.shape, np.stack(pk).shape)
+
+
+if __name__ == "__main__":
+    one_step("lcdm", "lcdm")
+    one_step("fofr", "lcdm", extra=dict(include_screening=1, fofr0=1e-5, nfofr=1.0))
+    one_step("dgp", "dgp", a=0.8, extra=dict(include_screening=1, rcH0_DGP=1.2, Rsmooth_global=1.0))
+    kickdrift()
+    run_fofr()
