@@ -156,6 +156,13 @@ class Stepper:
         self.sched = cosmology.schedule(Z_INIT, [(0.0, NSTEPS_RUN)])
         self.cosmology = cosmology
         self.i = 0
+        # the per-step host scalars (what main.c / cosmo.c compute) for every step of the schedule
+        self.pre = []
+        for s in self.sched[:NSTEPS_RUN]:
+            A, AI, AF, AFF = s["A"], s["AI"], s["AF"], s["AFF"]
+            Di, Di2 = cos.growth_D(A), cos.growth_D2(A)
+            self.pre.append((self.scalars(A), A, cos.Sphi(AI, AF, A), cos.growth_ddDddy(A), cos.growth_ddD2ddy(A),
+                             cos.Sq(A, AFF, AF), cos.growth_D(AFF) - Di, cos.growth_D2(AFF) - Di2))
 
     def scalars(self, A):
         if self.model == "fofr":
@@ -165,14 +172,12 @@ class Stepper:
         return self.pm.scalars(a=A, compute_pofk=1)
 
     def step(self):
-        s = self.sched[self.i % (NSTEPS_RUN)]      # stay inside the regular (non-output) steps
+        sc, A, dda, ddD, ddD2, dyyy, dD, dD2 = self.pre[self.i % NSTEPS_RUN]   # stay inside the regular (non-output) steps
         self.i += 1
-        A, AI, AF, AFF = s["A"], s["AI"], s["AF"], s["AFF"]
-        cos, pm = self.cos, self.pm
-        Di, Di2 = cos.growth_D(A), cos.growth_D2(A)
-        pm.GetDisplacements(self.scalars(A))
-        pm.Kick(A, cos.Sphi(AI, AF, A), cos.growth_ddDddy(A), cos.growth_ddD2ddy(A))
-        pm.Drift(cos.Sq(A, AFF, AF), cos.growth_D(AFF) - Di, cos.growth_D2(AFF) - Di2)
+        pm = self.pm
+        pm.GetDisplacements(sc)
+        pm.Kick(A, dda, ddD, ddD2)
+        pm.Drift(dyyy, dD, dD2)
 
 
 def run_ours(args):
@@ -202,7 +207,7 @@ def run_ours(args):
     cos = cosmology.LCDM(OMEGA, Z_INIT)
     model_id = {"lcdm": mgp.MODEL_NONE, "fofr": mgp.MODEL_FOFR, "dgp": mgp.MODEL_DGP}[model]
     pm = mgp.PM(N, N, box, omega=OMEGA, model=model_id, include_screening=1, grid_bytes=g, rank=rank, nranks=world,
-                device=local, nccl_id=nccl_id, deposit_mode=args.deposit_mode)
+                device=local, nccl_id=nccl_id, deposit_mode=args.deposit_mode, sort_particles=args.sort_interval)
     pm.set_pofk(64, 1, 1, 0.03, 2.0)          # paramfiles/additions_compute_pofk.txt
     t0 = time.time()
     pos, vel, ZA, LPT = host_ics(N, box, 5001, cos)
@@ -293,7 +298,8 @@ def run_ours(args):
     own = {k: phases.get(k, 0.0) for k in ("PtoMesh", "MtoParticles", "Forces", "ComputeFifthForce", "Kick", "Drift", "Sort", "Pofk")}
     dom = max(("PtoMesh", "MtoParticles"), key=lambda k: own.get(k, 0.0))
     ach = kern_bytes[dom] / (own[dom] * 1e-3) / 1e9 if own.get(dom) else None
-    roof = {"bound": "hbm", "kernel": {"PtoMesh": "k_deposit_rowseg (CIC deposit)", "MtoParticles": "k_gather (trilinear gather)"}[dom],
+    roof = {"bound": "hbm", "kernel": {"PtoMesh": ["k_deposit_atomic", "k_deposit_tile", "k_deposit_rowseg"][args.deposit_mode] + " (CIC deposit)",
+                       "MtoParticles": "k_gather (trilinear gather)"}[dom],
             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None, "traffic": None,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback",
             "step": {"algorithmic_bytes_per_particle": A_min, "achieved": A_min * npart_total / (ms_per_step * 1e-3) / 1e9,
@@ -306,7 +312,7 @@ def run_ours(args):
             "config": {"workload": "%s%s COLA step, Npart=Nmesh=%d^3, Box=%g Mpc/h, P(k) every step, z=9->0 in %d steps "
                                    "(reference configs[1] without SCALEDEPENDENT growth: build MODEL=FOFR_LCDM)"
                                    % (model, " with screening" if model != "lcdm" else "", N, box, NSTEPS_RUN),
-                       "nmesh": N, "npart": npart_total, "grid_bytes": g, "deposit_mode": args.deposit_mode,
+                       "nmesh": N, "npart": npart_total, "grid_bytes": g, "deposit_mode": args.deposit_mode, "sort_interval": args.sort_interval,
                        "l2": "inputs larger than L2 (particles %.1f GB, grids %.1f GB each)" % (N ** 3 * 56 / 1e9, N ** 3 * g / 1e9),
                        "ic_seconds_host": round(t_ic, 1)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "e2e": e2e}
@@ -427,7 +433,8 @@ def main():
     ap.add_argument("--ref-nmesh", type=int, default=128)
     ap.add_argument("--model", default="fofr", choices=["fofr", "dgp", "lcdm"])
     ap.add_argument("--grid-bytes", type=int, default=8, choices=[4, 8])
-    ap.add_argument("--deposit-mode", type=int, default=2)
+    ap.add_argument("--deposit-mode", type=int, default=0, help="0 atomic (warp-aggregated), 1 shared-memory tile, 2 deterministic")
+    ap.add_argument("--sort-interval", type=int, default=4, help="re-sort particles by cell every k-th step (0 never)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

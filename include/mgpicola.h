@@ -71,7 +71,8 @@ typedef struct mgp_config {
   int include_screening;     /* include_screening */
   int grid_bytes;            /* 8 = double grids (reference default), 4 = -DSINGLE_PRECISION */
   int deposit_mode;          /* enum mgp_deposit_mode */
-  int sort_particles;        /* 1: re-sort particles by mesh cell every step (recommended) */
+  int sort_particles;        /* 0: never; k >= 1: re-sort particles by mesh cell every k-th step (the TILE and
+                                DETERMINISTIC deposits always sort; ATOMIC only needs locality) */
   int rank, nranks;          /* slab decomposition: ThisTask / NTask */
   int device;                /* CUDA device ordinal */
   const void *nccl_unique_id;/* 128-byte ncclUniqueId shared by all ranks (NULL if nranks == 1) */

@@ -98,6 +98,9 @@ static void destroy(Ctx *cp) {
   fft_teardown(c);
   particles_free(c);
   cudaFree(c.grid[0]); cudaFree(c.force_block); cudaFree(c.grid[4]); cudaFree(c.grid[5]); cudaFree(c.halo_recv);
+  cudaFree(c.mig_dev); if (c.mig_host) cudaFreeHost(c.mig_host);
+  cudaFree(c.pofk_bins_d); cudaFree(c.pofk_sinc_d); cudaFree(c.pofk_out_d);
+  if (c.pofk_out_h) cudaFreeHost(c.pofk_out_h);
   if (c.comm) ncclCommDestroy(c.comm);
   for (int d = 0; d < 4; d++) { cudaEventDestroy(c.ev[d][0]); cudaEventDestroy(c.ev[d][1]); }
   cudaStreamDestroy(c.stream);
@@ -106,23 +109,41 @@ static void destroy(Ctx *cp) {
 
 // ---- per-step path -------------------------------------------------------------------------
 
+// Particle order policy.  sort_particles = 0: never sort; k >= 1: re-sort by mesh cell once at least k
+// drifts have happened since the last sort.  The TILE and DETERMINISTIC deposits need the exact cell
+// order and therefore sort whenever the order is stale; the ATOMIC deposit and the gather only need
+// spatial locality, which the Lagrangian / last-sorted order keeps for several steps.
+static void ensure_order(Ctx &c) {
+  if (!c.cfg.sort_particles || c.sorted) return;
+  const bool need_exact = c.cfg.deposit_mode != MGP_DEPOSIT_ATOMIC;
+  if (need_exact || c.drifts_since_sort >= c.cfg.sort_particles) particles_sort(c);
+}
+
 static void move_particles(Ctx &c) {
   {
     PhaseTimer t(c, PH_MOVE);
     if (c.P > 1) particles_migrate(c);
   }
-  if (c.cfg.sort_particles && !c.sorted) particles_sort(c);
+  if (c.np_after_sort != SIZE_MAX) particles_sort(c);   // closes the holes the leavers left
+  else ensure_order(c);
 }
 
 static void ptomesh(Ctx &c, const mgp_step_scalars *s) {
-  if (c.cfg.sort_particles && !c.sorted) particles_sort(c);
-  {
-    PhaseTimer t(c, PH_PTOMESH);
-    deposit_density(c);
-    halo_add_density(c, MGP_GRID_DENSITY);
-    if (needs_mg_arrays(c)) real_copy(c, MGP_GRID_MG_TWO, MGP_GRID_DENSITY, 1.0);   // CopyDensityArray (mg.h:381)
+  ensure_order(c);
+  if (needs_mg_arrays(c) && c.P == 1) {
+    // CopyDensityArray (mg.h:381) without the copy: deposit straight into mgarray_two and transform
+    // out of place into P3D, which leaves delta(x) in mgarray_two exactly as the reference has it
+    { PhaseTimer t(c, PH_PTOMESH); deposit_density(c, MGP_GRID_MG_TWO); }
+    fft_r2c_to(c, MGP_GRID_MG_TWO, MGP_GRID_DENSITY);
+  } else {
+    {
+      PhaseTimer t(c, PH_PTOMESH);
+      deposit_density(c, MGP_GRID_DENSITY);
+      halo_add_density(c, MGP_GRID_DENSITY);
+      if (needs_mg_arrays(c)) real_copy(c, MGP_GRID_MG_TWO, MGP_GRID_DENSITY, 1.0);   // CopyDensityArray (mg.h:381)
+    }
+    fft_r2c(c, MGP_GRID_DENSITY);
   }
-  fft_r2c(c, MGP_GRID_DENSITY);
   c.step_pofk_valid = false;
   if (s && s->compute_pofk) {
     const int nb = pofk_effective_nbins(c);

@@ -72,7 +72,7 @@ struct Ctx {
   void *halo_send = nullptr, *halo_recv = nullptr;   // 3 planes each
 
   // FFT
-  cufftHandle plan_r2c = 0, plan_c2r = 0, plan_c2r3 = 0;
+  cufftHandle plan_r2c = 0, plan_c2r = 0, plan_c2r3 = 0, plan_r2c_oop = 0;
   bool have_plans = false;
   // distributed FFT (P > 1)
   cufftHandle plan2d_r2c = 0, plan2d_c2r = 0, plan1d_x = 0;
@@ -85,12 +85,19 @@ struct Ctx {
   float4 *pA = nullptr;       // pos.xyz , id low  32 bits
   float4 *pB = nullptr;       // vel.xyz , id high 32 bits
   float4 *pC = nullptr;       // D.xyz   , D2.x
-  float4 *pE = nullptr;       // (float2 view) D2.y, D2.z   -- allocated with float4 capacity so
-                              // that all five buffers are interchangeable in the permute rotation
-  float4 *spare = nullptr;
+  float4 *pE = nullptr;       // (float2 storage) D2.y, D2.z
+  float4 *pA2 = nullptr, *pB2 = nullptr, *pC2 = nullptr, *pE2 = nullptr;   // sort destination set (swapped in)
   float *disp = nullptr;      // [3][cap]
   bool have_disp = false;
   bool sorted = false;        // particle order == cell order of current positions
+  bool exact_cell_order = false;   // sorted by cell (radix) rather than by bucket
+  uint32_t *bucket_start = nullptr;  // (nbuckets + 1) counts -> offsets
+  size_t nbuckets = 0;
+  int bucket_zshift = 0;
+  int drifts_since_sort = 1 << 30;
+  size_t np_after_sort = SIZE_MAX;   // set by MoveParticles: live count once the next sort has dropped the leavers
+  unsigned *mig_dev = nullptr, *mig_host = nullptr;
+  unsigned long long last_moved = 0; // particles exchanged (all ranks) by the last MoveParticles   // forces a sort at the first opportunity after an upload
   uint32_t *key[2] = {nullptr, nullptr};
   uint32_t *perm[2] = {nullptr, nullptr};
   uint32_t *row_start = nullptr;   // (nx*N + 1) offsets into the sorted particle list
@@ -109,6 +116,11 @@ struct Ctx {
   bool pofk_set = false;
   std::vector<double> step_pofk, step_kmean, step_nmodes;
   bool step_pofk_valid = false;
+  int *pofk_bins_d = nullptr;                 // bin index of every integer |d|^2
+  double *pofk_sinc_d = nullptr, *pofk_out_d = nullptr, *pofk_out_h = nullptr;
+  bool pofk_tables_valid = false;
+  int pofk_tab_nbins = 0, pofk_tab_bintype = 0;
+  double pofk_tab_kmin = 0, pofk_tab_kmax = 0;
 
   cudaStream_t stream = nullptr;
   ncclComm_t comm = nullptr;
@@ -160,13 +172,14 @@ void particles_kick(Ctx &c, double A, double dda, double ddD, double ddD2, const
 void particles_drift(Ctx &c, double dyyy, double dD, double dD2, const double sumV[3]);
 void particles_migrate(Ctx &c);
 // deposit.cu
-void deposit_density(Ctx &c);
+void deposit_density(Ctx &c, int grid_id);
 void gather_forces(Ctx &c, double sumD[3]);
 // fft.cu
 void fft_setup(Ctx &c);
 void fft_teardown(Ctx &c);
 void fft_r2c(Ctx &c, int grid_id);
 void fft_c2r(Ctx &c, int grid_id);
+void fft_r2c_to(Ctx &c, int src_grid, int dst_grid);
 void fft_c2r_forces(Ctx &c);
 void halo_add_density(Ctx &c, int grid_id);
 void halo_fill_forces(Ctx &c);

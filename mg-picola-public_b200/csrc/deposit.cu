@@ -125,22 +125,23 @@ k_deposit_atomic(size_t n, const float4 *__restrict__ pA, T *__restrict__ grid, 
 #pragma unroll
       for (int k = 0; k < 8; k++) w[k] = 0.0;
     }
+    // warp aggregation: maximal runs of ADJACENT lanes with the same cell are summed by a segmented
+    // scan and written once by the last lane of the run (equal cells need not be contiguous overall)
     bool writer = live;
     if (aggregate) {
       const long long prev = __shfl_up_sync(0xffffffffu, cell, 1);
-      const bool dup = lane > 0 && prev == cell;
-      if (__any_sync(0xffffffffu, dup)) {
+      const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || prev != cell);
+      if (heads != 0xffffffffu) {
+        const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));   // first lane of my run
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-          const long long cz = __shfl_up_sync(0xffffffffu, cell, o);
 #pragma unroll
           for (int k = 0; k < 8; k++) {
             const double a = shfl_up_d(w[k], o);
-            if (lane >= o && cz == cell) w[k] += a;
+            if (lane - o >= start) w[k] += a;
           }
         }
-        const long long nxt = __shfl_down_sync(0xffffffffu, cell, 1);
-        writer = live && (lane == 31 || nxt != cell);
+        writer = live && (lane == 31 || ((heads >> (lane + 1)) & 1u));
       }
     }
     if (writer) {
@@ -197,19 +198,18 @@ k_deposit_tile(const float4 *__restrict__ pA, const uint32_t *__restrict__ row_s
       }
       bool writer = live;
       const int prev = __shfl_up_sync(0xffffffffu, cell, 1);
-      const bool dup = lane > 0 && prev == cell;
-      if (__any_sync(0xffffffffu, dup)) {
+      const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || prev != cell);
+      if (heads != 0xffffffffu) {
+        const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));   // first lane of my run
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-          const int cz = __shfl_up_sync(0xffffffffu, cell, o);
 #pragma unroll
           for (int k = 0; k < 8; k++) {
             const double a = shfl_up_d(w[k], o);
-            if (lane >= o && cz == cell) w[k] += a;
+            if (lane - o >= start) w[k] += a;
           }
         }
-        const int nxt = __shfl_down_sync(0xffffffffu, cell, 1);
-        writer = live && (lane == 31 || nxt != cell);
+        writer = live && (lane == 31 || ((heads >> (lane + 1)) & 1u));
       }
       if (writer) {
         const int iz1 = (iz + 1 == N) ? 0 : iz + 1;
@@ -242,14 +242,15 @@ k_deposit_tile(const float4 *__restrict__ pA, const uint32_t *__restrict__ row_s
 // ------------------------------------------------------------------ dispatch
 
 template <typename T>
-static void deposit_t(Ctx &c) {
-  T *grid = (T *) c.grid[MGP_GRID_DENSITY];
+static void deposit_t(Ctx &c, int gid) {
+  T *grid = (T *) c.grid[gid];
   const double scale = (double) c.N / c.cfg.box;
   const double r = (double) c.N / (double) c.cfg.nsample;
   const double W = r * r * r;     // pow((double)Nmesh/(double)Nsample, 3)
   const int single = c.P == 1;
   int mode = c.cfg.deposit_mode;
-  if (!c.sorted) mode = MGP_DEPOSIT_ATOMIC;
+  if (!c.sorted) mode = MGP_DEPOSIT_ATOMIC;      // TILE / DETERMINISTIC need row_start of the current order
+  if (mode == MGP_DEPOSIT_DETERMINISTIC && !c.exact_cell_order) mode = MGP_DEPOSIT_ATOMIC;
   const size_t n = c.np;
   if (mode == MGP_DEPOSIT_DETERMINISTIC) {
     int wpb = 8;
@@ -288,12 +289,12 @@ static void deposit_t(Ctx &c) {
     return;
   }
   k_deposit_atomic<T><<<grid_for(n, 256), 256, 0, c.stream>>>(n, c.pA, grid, c.N, c.NZ, c.nx, c.x0, single, scale, W,
-                                                              c.sorted ? 1 : 0);
+                                                              1);
   c.launches++;
 }
 
-void deposit_density(Ctx &c) {
-  if (c.gbytes == 4) deposit_t<float>(c); else deposit_t<double>(c);
+void deposit_density(Ctx &c, int grid_id) {
+  if (c.gbytes == 4) deposit_t<float>(c, grid_id); else deposit_t<double>(c, grid_id);
 }
 
 // ------------------------------------------------------------------ gather (MtoParticles)

@@ -38,6 +38,9 @@ void fft_setup(Ctx &c) {
     ws = w > ws ? w : ws;
     w = make_plan_many(&c.plan_c2r, 3, n, cembed, 1, cdist, rembed, 1, rdist, f32 ? CUFFT_C2R : CUFFT_Z2D, 1, c.stream);
     ws = w > ws ? w : ws;
+    // same transform, separate plan handle for out-of-place use (real input grid is preserved)
+    w = make_plan_many(&c.plan_r2c_oop, 3, n, rembed, 1, rdist, cembed, 1, cdist, f32 ? CUFFT_R2C : CUFFT_D2Z, 1, c.stream);
+    ws = w > ws ? w : ws;
     w = make_plan_many(&c.plan_c2r3, 3, n, cembed, 1, cdist, rembed, 1, rdist, f32 ? CUFFT_C2R : CUFFT_Z2D, 3, c.stream);
     ws = w > ws ? w : ws;
   } else {
@@ -54,14 +57,14 @@ void fft_setup(Ctx &c) {
     CK(cudaMalloc(&c.tbuf_b, c.grid_bytes()));
   }
   if (ws) CK(cudaMalloc(&c.fft_work, ws));     // shared cuFFT work area
-  cufftHandle all[6] = {c.plan_r2c, c.plan_c2r, c.plan_c2r3, c.plan2d_r2c, c.plan2d_c2r, c.plan1d_x};
+  cufftHandle all[7] = {c.plan_r2c, c.plan_c2r, c.plan_c2r3, c.plan2d_r2c, c.plan2d_c2r, c.plan1d_x, c.plan_r2c_oop};
   for (cufftHandle h : all)
     if (h && ws) CKFFT(cufftSetWorkArea(h, c.fft_work));
   c.have_plans = true;
 }
 
 void fft_teardown(Ctx &c) {
-  cufftHandle all[6] = {c.plan_r2c, c.plan_c2r, c.plan_c2r3, c.plan2d_r2c, c.plan2d_c2r, c.plan1d_x};
+  cufftHandle all[7] = {c.plan_r2c, c.plan_c2r, c.plan_c2r3, c.plan2d_r2c, c.plan2d_c2r, c.plan1d_x, c.plan_r2c_oop};
   for (cufftHandle h : all)
     if (h) cufftDestroy(h);
   cudaFree(c.fft_work); cudaFree(c.tbuf_a); cudaFree(c.tbuf_b);
@@ -188,6 +191,15 @@ void fft_r2c(Ctx &c, int gid) {
   }
   if (c.gbytes == 4) CKFFT(cufftExecR2C(c.plan_r2c, (cufftReal *) g, (cufftComplex *) g));
   else CKFFT(cufftExecD2Z(c.plan_r2c, (cufftDoubleReal *) g, (cufftDoubleComplex *) g));
+  c.launches += 3;
+}
+
+// single rank only: dst(k) = r2c(src(x)), src is left untouched
+void fft_r2c_to(Ctx &c, int src, int dst) {
+  PhaseTimer t(c, PH_FFT);
+  REQUIRE(c.P == 1, MGP_ERR_STATE, "out-of-place r2c is a single-rank path");
+  if (c.gbytes == 4) CKFFT(cufftExecR2C(c.plan_r2c_oop, (cufftReal *) c.grid[src], (cufftComplex *) c.grid[dst]));
+  else CKFFT(cufftExecD2Z(c.plan_r2c_oop, (cufftDoubleReal *) c.grid[src], (cufftDoubleComplex *) c.grid[dst]));
   c.launches += 3;
 }
 

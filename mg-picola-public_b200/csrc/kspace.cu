@@ -296,17 +296,26 @@ void pofk_bin(Ctx &c, int gid, double *pofk, double *kmean, double *nmodes) {
   REQUIRE((size_t) 3 * nbins * sizeof(double) <= 200 * 1024, MGP_ERR_INVALID, "pofk_nbins too large");
   const int N = c.N, h = N / 2;
   const size_t mmax = (size_t) 3 * h * h + 1;
-  std::vector<int> bins(mmax);
-  for (size_t m = 0; m < mmax; m++) bins[m] = bin_index(sqrt((double) m), kmin, kmax, nbins, bintype);
-  std::vector<double> sinc(h + 1);
-  sinc[0] = 1.0;
-  for (int d = 1; d <= h; d++) sinc[d] = sin((M_PI * d) / (double) N) / ((M_PI * d) / (double) N);
-  int *d_bins = nullptr; double *d_sinc = nullptr, *d_out = nullptr;
-  CK(cudaMalloc(&d_bins, mmax * sizeof(int)));
-  CK(cudaMalloc(&d_sinc, (h + 1) * sizeof(double)));
-  CK(cudaMalloc(&d_out, (size_t) 3 * nbins * sizeof(double)));
-  CK(cudaMemcpyAsync(d_bins, bins.data(), mmax * sizeof(int), cudaMemcpyHostToDevice, c.stream));
-  CK(cudaMemcpyAsync(d_sinc, sinc.data(), (h + 1) * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+  // bin-of-|d|^2 and sinc tables live on the device until the binning parameters change
+  if (!c.pofk_tables_valid || c.pofk_tab_nbins != nbins || c.pofk_tab_bintype != bintype || c.pofk_tab_kmin != kmin ||
+      c.pofk_tab_kmax != kmax) {
+    std::vector<int> bins(mmax);
+    for (size_t m = 0; m < mmax; m++) bins[m] = bin_index(sqrt((double) m), kmin, kmax, nbins, bintype);
+    std::vector<double> sinc(h + 1);
+    sinc[0] = 1.0;
+    for (int d = 1; d <= h; d++) sinc[d] = sin((M_PI * d) / (double) N) / ((M_PI * d) / (double) N);
+    if (c.pofk_bins_d) { CK(cudaFree(c.pofk_bins_d)); CK(cudaFree(c.pofk_sinc_d)); CK(cudaFree(c.pofk_out_d)); CK(cudaFreeHost(c.pofk_out_h)); }
+    CK(cudaMalloc(&c.pofk_bins_d, mmax * sizeof(int)));
+    CK(cudaMalloc(&c.pofk_sinc_d, (h + 1) * sizeof(double)));
+    CK(cudaMalloc(&c.pofk_out_d, (size_t) 3 * nbins * sizeof(double)));
+    CK(cudaMallocHost(&c.pofk_out_h, (size_t) 3 * nbins * sizeof(double)));
+    CK(cudaMemcpyAsync(c.pofk_bins_d, bins.data(), mmax * sizeof(int), cudaMemcpyHostToDevice, c.stream));
+    CK(cudaMemcpyAsync(c.pofk_sinc_d, sinc.data(), (h + 1) * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+    c.pofk_tables_valid = true;
+    c.pofk_tab_nbins = nbins; c.pofk_tab_bintype = bintype; c.pofk_tab_kmin = kmin; c.pofk_tab_kmax = kmax;
+  }
+  int *d_bins = c.pofk_bins_d; double *d_sinc = c.pofk_sinc_d, *d_out = c.pofk_out_d;
   CK(cudaMemsetAsync(d_out, 0, (size_t) 3 * nbins * sizeof(double), c.stream));
   const KL L = layout_of(c);
   const double n3 = (double) N * (double) N * (double) N;
@@ -322,10 +331,9 @@ void pofk_bin(Ctx &c, int gid, double *pofk, double *kmean, double *nmodes) {
   }
   c.launches++;
   allreduce_sum(c, d_out, 3 * nbins);
-  std::vector<double> hout((size_t) 3 * nbins);
-  CK(cudaMemcpyAsync(hout.data(), d_out, hout.size() * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  double *hout = c.pofk_out_h;
+  CK(cudaMemcpyAsync(hout, d_out, (size_t) 3 * nbins * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
   CK(cudaStreamSynchronize(c.stream));
-  CK(cudaFree(d_bins)); CK(cudaFree(d_sinc)); CK(cudaFree(d_out));
   // normalise and subtract shot noise (compute_pofk.c:230-236)
   const double box3 = pow(c.cfg.box, 3);
   const double shotv = pow(c.cfg.box / (double) c.cfg.nsample, 3);

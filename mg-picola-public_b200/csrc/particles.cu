@@ -11,6 +11,7 @@
 #include "reduce.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 namespace mgp {
 
@@ -30,8 +31,11 @@ void particles_alloc(Ctx &c) {
   CK(cudaMalloc(&c.pA, cap * sizeof(float4)));
   CK(cudaMalloc(&c.pB, cap * sizeof(float4)));
   CK(cudaMalloc(&c.pC, cap * sizeof(float4)));
-  CK(cudaMalloc(&c.pE, cap * sizeof(float4)));
-  CK(cudaMalloc(&c.spare, cap * sizeof(float4)));
+  CK(cudaMalloc(&c.pE, cap * sizeof(float2)));
+  CK(cudaMalloc(&c.pA2, cap * sizeof(float4)));
+  CK(cudaMalloc(&c.pB2, cap * sizeof(float4)));
+  CK(cudaMalloc(&c.pC2, cap * sizeof(float4)));
+  CK(cudaMalloc(&c.pE2, cap * sizeof(float2)));
   CK(cudaMalloc(&c.disp, 3 * cap * sizeof(float)));
   for (int i = 0; i < 2; i++) {
     CK(cudaMalloc(&c.key[i], cap * sizeof(uint32_t)));
@@ -46,19 +50,32 @@ void particles_alloc(Ctx &c) {
   CK(cudaMalloc(&c.d_flag, 16 * sizeof(int)));
   CK(cudaMallocHost(&c.h_flag, 16 * sizeof(int)));
 
+  // bucket sort (see particles_sort): buckets of 2^bucket_zshift consecutive z-cells of one (x, y) row
+  c.bucket_zshift = (c.N % 8 == 0) ? 3 : 0;
+  c.nbuckets = (size_t) c.nx * c.N * (size_t) (c.N >> c.bucket_zshift);
+  CK(cudaMalloc(&c.bucket_start, (c.nbuckets + 2) * sizeof(uint32_t)));    // + the "no longer mine" bucket + end
+  size_t scan_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, c.bucket_start, c.bucket_start, (int64_t) (c.nbuckets + 2), c.stream);
+  if (scan_bytes > c.cub_temp_bytes) {
+    CK(cudaFree(c.cub_temp));
+    c.cub_temp_bytes = scan_bytes;
+    CK(cudaMalloc(&c.cub_temp, c.cub_temp_bytes));
+  }
+
   // key = row-major cell index of the local slab
   const uint64_t cells = (uint64_t) c.nx * c.N * c.N;
   int b = 0;
-  while ((1ull << b) < cells) b++;
-  REQUIRE(b <= 32, MGP_ERR_INVALID, "more than 2^32 mesh cells on one rank: use more ranks");
+  while ((1ull << b) <= cells) b++;      // keys 0 .. cells (cells itself = "no longer mine")
+  REQUIRE(b <= 32, MGP_ERR_INVALID, "2^32 or more mesh cells on one rank: use more ranks");
   c.key_zshift = 0;
   c.key_bits = b < 1 ? 1 : b;
 }
 
 void particles_free(Ctx &c) {
-  cudaFree(c.pA); cudaFree(c.pB); cudaFree(c.pC); cudaFree(c.pE); cudaFree(c.spare); cudaFree(c.disp);
+  cudaFree(c.pA); cudaFree(c.pB); cudaFree(c.pC); cudaFree(c.pE); cudaFree(c.disp);
+  cudaFree(c.pA2); cudaFree(c.pB2); cudaFree(c.pC2); cudaFree(c.pE2);
   for (int i = 0; i < 2; i++) { cudaFree(c.key[i]); cudaFree(c.perm[i]); }
-  cudaFree(c.row_start); cudaFree(c.cub_temp);
+  cudaFree(c.row_start); cudaFree(c.cub_temp); cudaFree(c.bucket_start);
   cudaFree(c.d_red); if (c.h_red) cudaFreeHost(c.h_red);
   cudaFree(c.d_flag); if (c.h_flag) cudaFreeHost(c.h_flag);
 }
@@ -122,6 +139,7 @@ void particles_upload(Ctx &c, uint64_t n, const float *pos, const float *vel, co
   CK(cudaFree(st));
   c.np = n;
   c.sorted = false;
+  c.drifts_since_sort = 1 << 30;
   c.have_disp = false;
 }
 
@@ -153,8 +171,8 @@ void particles_download(Ctx &c, float *pos, float *vel, float *D, float *D2, uin
 
 // key = ((ix - x0) * N + iy) * N + iz; cell of a position exactly as PtoMesh computes it
 // (auxPM.c:298-322): X = (double)Pos * (Nmesh/Box); I = (unsigned)X; I >= Nmesh -> 0 for y, z.
-__global__ void k_keys(size_t n, const float4 *__restrict__ pA, double scale, int N, int x0, int nx,
-                       uint32_t *__restrict__ key, uint32_t *__restrict__ perm) {
+__global__ void k_keys(size_t n, const float4 *__restrict__ pA, double scale, int N, int x0, int nx, int drop_foreign,
+                       uint32_t dead_key, uint32_t *__restrict__ key, uint32_t *__restrict__ perm) {
   for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
     const float4 a = pA[i];
     unsigned ix = (unsigned) ((double) a.x * scale);
@@ -162,10 +180,15 @@ __global__ void k_keys(size_t n, const float4 *__restrict__ pA, double scale, in
     unsigned iz = (unsigned) ((double) a.z * scale);
     if (iy >= (unsigned) N) iy = 0;
     if (iz >= (unsigned) N) iz = 0;
+    if (ix >= (unsigned) N) ix = N - 1;
     int lx = (int) ix - x0;
-    if (lx < 0) lx = 0;
-    if (lx >= nx) lx = nx - 1;  // defensive: ownership is established by migrate()
-    key[i] = ((uint32_t) lx * (uint32_t) N + iy) * (uint32_t) N + iz;
+    if (drop_foreign && (lx < 0 || lx >= nx)) {
+      key[i] = dead_key;          // sent away by MoveParticles: sorts behind every live particle
+    } else {
+      if (lx < 0) lx = 0;
+      if (lx >= nx) lx = nx - 1;
+      key[i] = ((uint32_t) lx * (uint32_t) N + iy) * (uint32_t) N + iz;
+    }
     perm[i] = (uint32_t) i;
   }
 }
@@ -186,34 +209,132 @@ __global__ void k_row_start(size_t n, const uint32_t *__restrict__ key, unsigned
   }
 }
 
-void particles_sort(Ctx &c) {
-  PhaseTimer t(c, PH_SORT);
+// ---- bucket (counting) sort: the default order for the ATOMIC / TILE deposits and the gather -----
+//
+// A bucket is a run of 2^zs consecutive z-cells of one (x, y) row (64 bytes of a double grid row).
+// Pass 1 ranks every particle inside its bucket with one warp-aggregated atomic per (warp, bucket);
+// an exclusive scan of the bucket counts gives the bucket offsets; pass 2 moves all particle
+// fields to bucket_start[bucket] + rank in one kernel.  About 150 bytes of traffic per particle against
+// about 330 for key generation + 3 radix passes + 4 permutes.  The order inside a bucket is not
+// reproducible, so the DETERMINISTIC deposit keeps using the stable radix sort below.
+__global__ void __launch_bounds__(256)
+k_bucket_rank(size_t n, const float4 *__restrict__ pA, double scale, int N, int x0, int nx, int zs, int drop_foreign,
+              unsigned dead_bucket, uint32_t *__restrict__ count, uint32_t *__restrict__ bucket_of,
+              uint32_t *__restrict__ rank_of) {
+  const unsigned lane = threadIdx.x & 31;
+  const size_t nround = (n + 31) / 32 * 32;
+  const unsigned nbz = (unsigned) N >> zs;
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < nround; i += (size_t) gridDim.x * blockDim.x) {
+    unsigned b = 0xffffffffu - lane;                 // idle lanes: distinct sentinels
+    if (i < n) {
+      const float4 a = pA[i];
+      unsigned ix = (unsigned) ((double) a.x * scale);
+      unsigned iy = (unsigned) ((double) a.y * scale);
+      unsigned iz = (unsigned) ((double) a.z * scale);
+      if (iy >= (unsigned) N) iy = 0;
+      if (iz >= (unsigned) N) iz = 0;
+      if (ix >= (unsigned) N) ix = N - 1;            // cannot happen for float positions in [0, Box)
+      int lx = (int) ix - x0;
+      if (drop_foreign && (lx < 0 || lx >= nx)) {
+        b = dead_bucket;                             // sent away by MoveParticles: sorted behind the live particles
+      } else {
+        if (lx < 0) lx = 0;
+        if (lx >= nx) lx = nx - 1;
+        b = ((unsigned) lx * (unsigned) N + iy) * nbz + (iz >> zs);
+      }
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, b);
+    const int leader = __ffs(peers) - 1;
+    unsigned base = 0;
+    if ((int) lane == leader && i < n) base = atomicAdd(&count[b], (unsigned) __popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (i < n) {
+      bucket_of[i] = b;
+      rank_of[i] = base + (unsigned) __popc(peers & ((1u << lane) - 1u));
+    }
+  }
+}
+
+// src_of[bucket_start[b] + rank] = i  (4-byte scatter; the 56-byte payload is then GATHERED, which
+// keeps every payload store full-width and coalesced)
+__global__ void __launch_bounds__(256)
+k_bucket_invert(size_t n, const uint32_t *__restrict__ bucket_of, const uint32_t *__restrict__ rank_of,
+                const uint32_t *__restrict__ start, uint32_t *__restrict__ src_of) {
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+    src_of[(size_t) start[bucket_of[i]] + rank_of[i]] = (uint32_t) i;
+}
+
+__global__ void __launch_bounds__(256)
+k_permute_all(size_t n, const uint32_t *__restrict__ src_of, const float4 *__restrict__ iA, const float4 *__restrict__ iB,
+              const float4 *__restrict__ iC, const float2 *__restrict__ iE, float4 *__restrict__ oA,
+              float4 *__restrict__ oB, float4 *__restrict__ oC, float2 *__restrict__ oE) {
+  for (size_t d = blockIdx.x * (size_t) blockDim.x + threadIdx.x; d < n; d += (size_t) gridDim.x * blockDim.x) {
+    const uint32_t i = src_of[d];
+    const float4 a = iA[i], b = iB[i], cc = iC[i];
+    const float2 e = iE[i];
+    oA[d] = a; oB[d] = b; oC[d] = cc; oE[d] = e;
+  }
+}
+
+// row_start[r] = bucket_start[r * nbz] for r in [0, nrows]
+__global__ void k_rows_from_buckets(unsigned nrows, unsigned nbz, const uint32_t *__restrict__ start, uint32_t *__restrict__ row_start) {
+  for (size_t r = blockIdx.x * (size_t) blockDim.x + threadIdx.x; r <= nrows; r += (size_t) gridDim.x * blockDim.x)
+    row_start[r] = start[(size_t) r * nbz];
+}
+
+static void bucket_sort(Ctx &c) {
+  const size_t n = c.np;
+  const unsigned nrows = (unsigned) (c.nx * c.N);
+  const unsigned nbz = (unsigned) c.N >> c.bucket_zshift;
+  const double scale = (double) c.N / c.cfg.box;
+  REQUIRE(c.pA2 != nullptr, MGP_ERR_STATE, "bucket sort buffers missing");
+  CK(cudaMemsetAsync(c.bucket_start, 0, (c.nbuckets + 2) * sizeof(uint32_t), c.stream));
+  k_bucket_rank<<<grid_for(n, 256), 256, 0, c.stream>>>(n, c.pA, scale, c.N, c.x0, c.nx, c.bucket_zshift, c.P > 1,
+                                                      (unsigned) c.nbuckets, c.bucket_start, c.key[0], c.perm[0]);
+  size_t tb = c.cub_temp_bytes;
+  CK(cub::DeviceScan::ExclusiveSum(c.cub_temp, tb, c.bucket_start, c.bucket_start, (int64_t) (c.nbuckets + 2), c.stream));
+  k_bucket_invert<<<grid_for(n, 256), 256, 0, c.stream>>>(n, c.key[0], c.perm[0], c.bucket_start, c.perm[1]);
+  k_permute_all<<<grid_for(n, 256), 256, 0, c.stream>>>(n, c.perm[1], c.pA, c.pB, c.pC, (const float2 *) c.pE, c.pA2, c.pB2,
+                                                      c.pC2, (float2 *) c.pE2);
+  std::swap(c.pA, c.pA2); std::swap(c.pB, c.pB2); std::swap(c.pC, c.pC2); std::swap(c.pE, c.pE2);
+  k_rows_from_buckets<<<grid_for((size_t) nrows + 1, 256), 256, 0, c.stream>>>(nrows, nbz, c.bucket_start, c.row_start);
+  c.launches += 4 + 2;   // + CUB's scan (2 launches)
+}
+
+static void radix_sort(Ctx &c) {
   const size_t n = c.np;
   const unsigned zc = (unsigned) c.N;
   const unsigned nrows = (unsigned) (c.nx * c.N);
   const double scale = (double) c.N / c.cfg.box;
-  if (n == 0) {
-    CK(cudaMemsetAsync(c.row_start, 0, ((size_t) nrows + 1) * sizeof(uint32_t), c.stream));
-    c.sorted = true;
-    return;
-  }
-  k_keys<<<grid_for(n, 256), 256, 0, c.stream>>>(n, c.pA, scale, c.N, c.x0, c.nx, c.key[0], c.perm[0]);
+  k_keys<<<grid_for(n, 256), 256, 0, c.stream>>>(n, c.pA, scale, c.N, c.x0, c.nx, c.P > 1,
+                                                 (uint32_t) ((uint64_t) c.nx * c.N * c.N), c.key[0], c.perm[0]);
   size_t tb = c.cub_temp_bytes;
   CK(cub::DeviceRadixSort::SortPairs(c.cub_temp, tb, c.key[0], c.key[1], c.perm[0], c.perm[1], (int64_t) n, 0,
                                      c.key_bits, c.stream));
-  const unsigned g = grid_for(n, 256);
-  // rotate the five interchangeable 16-byte buffers: out-of-place gather, then swap names
-  k_permute<float4><<<g, 256, 0, c.stream>>>(n, c.perm[1], c.pA, c.spare);
-  { float4 *t0 = c.pA; c.pA = c.spare; c.spare = t0; }
-  k_permute<float4><<<g, 256, 0, c.stream>>>(n, c.perm[1], c.pB, c.spare);
-  { float4 *t0 = c.pB; c.pB = c.spare; c.spare = t0; }
-  k_permute<float4><<<g, 256, 0, c.stream>>>(n, c.perm[1], c.pC, c.spare);
-  { float4 *t0 = c.pC; c.pC = c.spare; c.spare = t0; }
-  k_permute<float2><<<g, 256, 0, c.stream>>>(n, c.perm[1], (const float2 *) c.pE, (float2 *) c.spare);
-  { float4 *t0 = c.pE; c.pE = c.spare; c.spare = t0; }
-  k_row_start<<<grid_for(n + 1, 256), 256, 0, c.stream>>>(n, c.key[1], zc, nrows, c.row_start);
-  c.launches += 6 + 4;   // + CUB's histogram / onesweep passes (>= 4 launches for <= 32 bits)
+  // out-of-place gather into the second buffer set, then swap names
+  k_permute_all<<<grid_for(n, 256), 256, 0, c.stream>>>(n, c.perm[1], c.pA, c.pB, c.pC, (const float2 *) c.pE, c.pA2, c.pB2,
+                                                      c.pC2, (float2 *) c.pE2);
+  std::swap(c.pA, c.pA2); std::swap(c.pB, c.pB2); std::swap(c.pC, c.pC2); std::swap(c.pE, c.pE2);
+  const size_t nlive = c.np_after_sort != SIZE_MAX ? c.np_after_sort : n;
+  k_row_start<<<grid_for(nlive + 1, 256), 256, 0, c.stream>>>(nlive, c.key[1], zc, nrows, c.row_start);
+  c.launches += 3 + 4;   // + CUB's histogram / onesweep passes (>= 4 launches for <= 32 bits)
+}
+
+void particles_sort(Ctx &c) {
+  PhaseTimer t(c, PH_SORT);
+  const unsigned nrows = (unsigned) (c.nx * c.N);
+  if (c.np == 0) {
+    CK(cudaMemsetAsync(c.row_start, 0, ((size_t) nrows + 1) * sizeof(uint32_t), c.stream));
+  } else if (c.cfg.deposit_mode == MGP_DEPOSIT_DETERMINISTIC) {
+    radix_sort(c);
+    c.exact_cell_order = true;
+  } else {
+    bucket_sort(c);
+    c.exact_cell_order = false;
+  }
+  if (c.np_after_sort != SIZE_MAX) { c.np = c.np_after_sort; c.np_after_sort = SIZE_MAX; }   // leavers dropped
   c.sorted = true;
+  c.drifts_since_sort = 0;
   c.have_disp = false;   // Disp was in the old order
 }
 
@@ -311,6 +432,7 @@ void particles_drift(Ctx &c, double dyyy, double dD, double dD2, const double su
     c.launches++;
   }
   c.sorted = false;
+  if (c.drifts_since_sort < (1 << 30)) c.drifts_since_sort++;
   c.have_disp = false;
 }
 
