@@ -1,0 +1,66 @@
+"""Worker for the multi-GPU parity tests: one process per GPU (torchrun), x-slab decomposition.
+Every rank starts from a deliberately WRONG share of a seeded particle set (round-robin by index), so
+the first MoveParticles migrates almost everything; then COLA steps are taken and each rank saves its
+particles.  The parent test compares against the single-task oracle."""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--nmesh", type=int, default=32)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--model", default="fofr")
+    ap.add_argument("--gb", type=int, default=8)
+    ap.add_argument("--mode", type=int, default=0)
+    ap.add_argument("--out", required=True)
+    a = ap.parse_args()
+    import torch
+    import mgpicola_b200 as mgp
+    from mgpicola_b200 import dist as mdist
+    from oracle import pm_oracle as po            # only for the per-step scalar helpers (host numbers)
+    import test_gpu_parity as T
+    rank, world, local = mdist.init_process_group("nccl")
+    torch.cuda.set_device(local)
+    N, box, om = a.nmesh, 100.0, 0.267
+    pos, vel, D, D2 = T.make_particles(N, box, 77, clustered=True)
+    ids = np.arange(N ** 3, dtype=np.uint64)
+    mine = (np.arange(N ** 3) % world) == rank
+    nid = mdist.share_from_rank0(mgp.nccl_unique_id)
+    mid = {"lcdm": mgp.MODEL_NONE, "fofr": mgp.MODEL_FOFR, "dgp": mgp.MODEL_DGP}[a.model]
+    pm = mgp.PM(N, N, box, omega=om, model=mid, include_screening=1, grid_bytes=a.gb, deposit_mode=a.mode, buffer=2.5,
+                rank=rank, nranks=world, device=local, nccl_id=nid)
+    pm.set_pofk(16, 0, 1, 0.0, 0.0)
+    pm.upload_particles(pos[mine], vel[mine], D[mine], D2[mine], ids[mine])
+    pks = []
+    for it in range(a.steps):
+        A = 0.5 + 0.1 * it
+        if a.model == "fofr":
+            pc, c, m2 = po.fofr_scalars(A, om, box, 1e-5, 1.0)
+            s = pm.scalars(a=A, phi_crit=pc, coupling=c, massterm2=m2, compute_pofk=1)
+        elif a.model == "dgp":
+            c, f0 = po.dgp_scalars(A, om, 1.2)
+            s = pm.scalars(a=A, coupling=c, dgp_fac0=f0, rsmooth=1.0, compute_pofk=1)
+        else:
+            s = pm.scalars(a=A, compute_pofk=1)
+        pm.GetDisplacements(s)
+        pks.append(np.stack(pm.step_power_spectrum()))
+        pm.Kick(A, 0.02, 1.3, -0.4)
+        pm.Drift(0.5, 0.03, -0.01)
+    pm.MoveParticles()                  # final ownership
+    got = pm.download_particles()
+    np.savez(os.path.join(a.out, "rank%d.npz" % rank), pks=np.stack(pks), x0=pm.local_x_start, nx=pm.local_nx,
+             launches=pm.launch_count(), **got)
+    mdist.barrier()
+    pm.close()
+
+
+if __name__ == "__main__":
+    main()
