@@ -73,6 +73,8 @@ typedef struct mgp_config {
   int deposit_mode;          /* enum mgp_deposit_mode */
   int sort_particles;        /* 0: never; k >= 1: re-sort particles by mesh cell every k-th step (the TILE and
                                 DETERMINISTIC deposits always sort; ATOMIC only needs locality) */
+  int scale_dependent;       /* -DSCALEDEPENDENT: keep delta1_k / delta2_k and rebuild the displacement fields every
+                                step from k-dependent growth factors (2LPT.c:1539-2005) */
   int rank, nranks;          /* slab decomposition: ThisTask / NTask */
   int device;                /* CUDA device ordinal */
   const void *nccl_unique_id;/* 128-byte ncclUniqueId shared by all ranks (NULL if nranks == 1) */
@@ -127,6 +129,31 @@ int mgp_download_particles(mgp_ctx *ctx, float *pos, float *vel, float *D, float
 int mgp_download_disp(mgp_ctx *ctx, float *disp);
 /* the inverse: load Disp[3][NumPart] from the host as [n][3] (a driver that keeps its own Disp, tests) */
 int mgp_upload_disp(mgp_ctx *ctx, const float *disp);
+
+/* ---- initial conditions (2LPT.c:185-1520 Gaussian branch, main.c:257-309) ---- */
+typedef struct mgp_ic_config {
+  unsigned seed;             /* Seed */
+  int sphere_mode;           /* SphereMode */
+  int amplitude_fixed;       /* amplitude_fixed_initial_condition */
+  int inverted;              /* inverted_initial_condition */
+  /* P(k) [(Mpc/h)^3] for every integer m = |d|^2 in [0, 3 (Nmesh/2)^2], k = 2 pi sqrt(m) / Box: the
+   * adapter fills it with PowerSpec(k) [* mg_pofk_ratio(k,1) / sigma8 ratio^2] exactly as
+   * 2LPT.c:388-407 evaluates it per mode */
+  const double *power_by_k2;
+  size_t n_power;
+  /* optional Nmesh*Nmesh seed table filled by the driver's own gsl_rng in the order of 2LPT.c:259-271;
+   * NULL: the library fills it from `seed` with its ranlxd1 restatement */
+  const unsigned *seedtable;
+} mgp_ic_config;
+/* displacement_fields(): delta_k, the six displacement gradients, the 2LPT source, and the ZA / 2LPT
+ * displacements read out at the Lagrangian points of this rank's particle planes (13 FFTs) */
+int mgp_ic_generate(mgp_ctx *ctx, const mgp_ic_config *ic);
+/* main.c:257-309: IDs, D = ZA, D2 = LPT, Vel (0 for COLA), Pos = wrap(q + D Di + D2 Di2) */
+int mgp_init_particles(mgp_ctx *ctx, double Di, double Di2, double dDdy, double dD2dy);
+/* the seed table of 2LPT.c:259-271 (Nmesh*Nmesh unsigned) and the n-th draw of ranlxd1(seed): test hooks
+ * that pin the generator against GSL's published known-answer values */
+int mgp_seedtable(unsigned seed, int nmesh, unsigned *out);
+double mgp_ranlxd1_draw(unsigned long seed, long n);
 
 /* ---- the per-step force path ---- */
 /* MoveParticles (auxPM.c:108-275): slab ownership + migration; also (re)sorts by cell */

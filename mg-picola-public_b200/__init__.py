@@ -35,7 +35,12 @@ class Config(C.Structure):
     _fields_ = [("nmesh", C.c_int), ("nsample", C.c_int), ("box", C.c_double), ("buffer", C.c_double),
                 ("omega", C.c_double), ("use_cola", C.c_int), ("model", C.c_int), ("include_screening", C.c_int),
                 ("grid_bytes", C.c_int), ("deposit_mode", C.c_int), ("sort_particles", C.c_int),
-                ("rank", C.c_int), ("nranks", C.c_int), ("device", C.c_int), ("nccl_unique_id", C.c_void_p)]
+                ("scale_dependent", C.c_int), ("rank", C.c_int), ("nranks", C.c_int), ("device", C.c_int), ("nccl_unique_id", C.c_void_p)]
+
+
+class IcConfig(C.Structure):
+    _fields_ = [("seed", C.c_uint), ("sphere_mode", C.c_int), ("amplitude_fixed", C.c_int), ("inverted", C.c_int),
+                ("power_by_k2", C.c_void_p), ("n_power", C.c_size_t), ("seedtable", C.c_void_p)]
 
 
 class PofkConfig(C.Structure):
@@ -70,6 +75,11 @@ def load_library(path=None):
     L.mgp_download_particles.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mgp_download_disp.argtypes = [C.c_void_p, C.c_void_p]
     L.mgp_upload_disp.argtypes = [C.c_void_p, C.c_void_p]
+    L.mgp_ic_generate.argtypes = [C.c_void_p, C.POINTER(IcConfig)]
+    L.mgp_init_particles.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]
+    L.mgp_seedtable.argtypes = [C.c_uint, C.c_int, C.c_void_p]
+    L.mgp_ranlxd1_draw.argtypes = [C.c_ulong, C.c_long]
+    L.mgp_ranlxd1_draw.restype = C.c_double
     L.mgp_move_particles.argtypes = [C.c_void_p]
     L.mgp_ptomesh.argtypes = [C.c_void_p, C.POINTER(StepScalars)]
     L.mgp_compute_fifth_force.argtypes = [C.c_void_p, C.POINTER(StepScalars)]
@@ -109,6 +119,19 @@ def declared_symbols(header=HEADER_PATH):
     return sorted(set(re.findall(r"\b(mgp_[a-z0-9_]+)\s*\(", txt)))
 
 
+def seedtable(seed, nmesh):
+    L = load_library()
+    out = np.zeros((nmesh, nmesh), np.uint32)
+    rc = L.mgp_seedtable(seed, nmesh, out.ctypes.data)
+    if rc:
+        raise MgpError(rc, L.mgp_last_error().decode())
+    return out
+
+
+def ranlxd1_draw(seed, n):
+    return load_library().mgp_ranlxd1_draw(seed, n)
+
+
 def nccl_unique_id():
     L = load_library()
     buf = C.create_string_buffer(128)
@@ -131,11 +154,11 @@ class PM:
 
     def __init__(self, nmesh, nsample, box, omega=0.267, use_cola=1, model=MODEL_NONE, include_screening=0,
                  grid_bytes=8, deposit_mode=DEPOSIT_DETERMINISTIC, sort_particles=1, buffer=1.5, rank=0, nranks=1,
-                 device=0, nccl_id=None):
+                 device=0, nccl_id=None, scale_dependent=0):
         self.L = load_library()
         self._idbuf = C.create_string_buffer(nccl_id, 128) if nccl_id is not None else None
         self.cfg = Config(nmesh, nsample, box, buffer, omega, use_cola, model, include_screening, grid_bytes,
-                          deposit_mode, sort_particles, rank, nranks, device,
+                          deposit_mode, sort_particles, scale_dependent, rank, nranks, device,
                           C.cast(self._idbuf, C.c_void_p) if self._idbuf is not None else None)
         self.ctx = C.c_void_p()
         self._ck(self.L.mgp_create(C.byref(self.cfg), C.byref(self.ctx)))
@@ -197,6 +220,17 @@ class PM:
         d = np.empty((self.numpart, 3), np.float32)
         self._ck(self.L.mgp_download_disp(self.ctx, _ptr(d)))
         return d
+
+    # ---- initial conditions ----
+    def ic_generate(self, power_by_k2, seed=5001, sphere_mode=0, amplitude_fixed=0, inverted=0, seedtable=None):
+        """displacement_fields(): power_by_k2[m] = P(k = 2 pi sqrt(m) / Box), m = 0 .. 3 (Nmesh/2)^2."""
+        pw = np.ascontiguousarray(power_by_k2, dtype=np.float64)
+        st = None if seedtable is None else np.ascontiguousarray(seedtable, dtype=np.uint32)
+        ic = IcConfig(seed, sphere_mode, amplitude_fixed, inverted, pw.ctypes.data, pw.size, None if st is None else st.ctypes.data)
+        self._ck(self.L.mgp_ic_generate(self.ctx, C.byref(ic)))
+
+    def init_particles(self, Di, Di2, dDdy=0.0, dD2dy=0.0):
+        self._ck(self.L.mgp_init_particles(self.ctx, Di, Di2, dDdy, dD2dy))
 
     def upload_disp(self, disp):
         d = _f32(disp)

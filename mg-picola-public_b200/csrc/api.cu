@@ -74,6 +74,10 @@ static Ctx *create(const mgp_config *cfg) {
       CK(cudaMalloc(&c.grid[4], c.grid_bytes()));
       CK(cudaMalloc(&c.grid[5], c.grid_bytes()));
     }
+    if (cfg->scale_dependent) {
+      CK(cudaMalloc(&c.sd_delta[0], c.grid_bytes()));
+      CK(cudaMalloc(&c.sd_delta[1], c.grid_bytes()));
+    }
     CK(cudaMalloc(&c.halo_recv, c.plane_bytes()));
     particles_alloc(c);
     if (c.P > 1) {
@@ -98,6 +102,7 @@ static void destroy(Ctx *cp) {
   fft_teardown(c);
   particles_free(c);
   cudaFree(c.grid[0]); cudaFree(c.force_block); cudaFree(c.grid[4]); cudaFree(c.grid[5]); cudaFree(c.halo_recv);
+  cudaFree(c.sd_delta[0]); cudaFree(c.sd_delta[1]);
   cudaFree(c.mig_dev); if (c.mig_host) cudaFreeHost(c.mig_host);
   cudaFree(c.pofk_bins_d); cudaFree(c.pofk_sinc_d); cudaFree(c.pofk_out_d);
   if (c.pofk_out_h) cudaFreeHost(c.pofk_out_h);
@@ -283,6 +288,29 @@ int mgp_download_disp(mgp_ctx *ctx, float *disp) {
   }
   API_END
 }
+
+int mgp_ic_generate(mgp_ctx *ctx, const mgp_ic_config *ic) {
+  API_BEGIN
+  CTX(ctx);
+  ic_generate(c, ic);
+  API_END
+}
+
+int mgp_init_particles(mgp_ctx *ctx, double Di, double Di2, double dDdy, double dD2dy) {
+  API_BEGIN
+  CTX(ctx);
+  ic_init_particles(c, Di, Di2, dDdy, dD2dy);
+  API_END
+}
+
+int mgp_seedtable(unsigned seed, int nmesh, unsigned *out) {
+  API_BEGIN
+  REQUIRE(out != nullptr && nmesh >= 2 && nmesh % 2 == 0, MGP_ERR_INVALID, "mgp_seedtable: bad arguments");
+  ic_seedtable(seed, nmesh, out);
+  API_END
+}
+
+double mgp_ranlxd1_draw(unsigned long seed, long n) { return ic_ranlxd1_draw(seed, n); }
 
 int mgp_upload_disp(mgp_ctx *ctx, const float *disp) {
   API_BEGIN

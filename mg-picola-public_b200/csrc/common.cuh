@@ -106,6 +106,11 @@ struct Ctx {
   int key_zshift = 0;         // cell key drops this many low z bits (0 = full cell sort)
   int key_bits = 32;
 
+  // initial conditions / scale-dependent growth
+  double ic_means[6] = {0, 0, 0, 0, 0, 0};
+  bool ic_ready = false;
+  void *sd_delta[2] = {nullptr, nullptr};    // delta1_k, delta2_k (cdelta_cdm, cdelta_cdm2; vars.h:272-273)
+
   double *d_red = nullptr;    // device reduction scratch (doubles)
   double *h_red = nullptr;    // pinned host mirror
   size_t red_cap = 0;
@@ -195,6 +200,12 @@ void real_screen_potential(Ctx &c, double phi_crit, bool screening);
 void real_screen_density(Ctx &c, double coupling, double fac0, double stats[3]);
 void pofk_bin(Ctx &c, int grid_id, double *pofk, double *kmean, double *nmodes);
 int pofk_effective_nbins(const Ctx &c);
+
+// ic.cu
+void ic_generate(Ctx &c, const mgp_ic_config *ic);
+void ic_init_particles(Ctx &c, double Di, double Di2, double dDdy, double dD2dy);
+void ic_seedtable(unsigned seed, int N, unsigned *out);
+double ic_ranlxd1_draw(unsigned long seed, long n);
 
 // reductions: sum `n` doubles' worth of per-block partials living in c.d_red into host values
 void reduce_alloc(Ctx &c, size_t n);

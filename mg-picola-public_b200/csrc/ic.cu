@@ -1,0 +1,440 @@
+// Initial conditions on the GPU: Gaussian random field + 2LPT displacement fields and the particle
+// initialisation loop.  Replaces displacement_fields() (2LPT.c:185-495, 1204-1520, Gaussian branch)
+// and main.c:257-309.
+//
+// Random numbers.  The reference draws every (i, j) row of Fourier modes from its own stream of
+// GSL's ranlxd1 generator, seeded from a table that is itself filled from ranlxd1(Seed) in the
+// N-GenIC order (2LPT.c:259-271, 344-353).  The generator is restated here with 48-bit integers
+// (Luescher's subtract-with-borrow, lags 12 / 5, luxury 202; the GSL double arithmetic is exact, so
+// the integer form is bit-identical); the known-answer values of GSL's own test suite pin it
+// (tests/test_ic.py).  One GPU thread owns one row: N^2 independent streams.
+//
+// Memory.  Only the scalar field delta_k is stored (one complex grid); the Zel'dovich field
+// psi_a = i k_a / k^2 delta, its six gradients and the second-order field are formed on the fly in
+// the three force grids, so the whole 13-FFT pipeline needs one grid more than a time step does.
+#include "common.cuh"
+#include "klayout.cuh"
+#include "reduce.cuh"
+
+#include <cmath>
+
+namespace mgp {
+
+// ------------------------------------------------------------------ ranlxd1
+
+struct Ranlxd {
+  long long x[12];          // 48-bit fractions
+  unsigned ir, jr, ir_old;
+  long long carry;
+};
+
+__host__ __device__ inline void ranlxd_set(Ranlxd &r, unsigned long s) {
+  if (s == 0) s = 1;
+  unsigned bits = (unsigned) (s & 0x7FFFFFFFUL);     // xbit[k] = bit k
+  int ibit = 0, jbit = 18;
+  for (int k = 0; k < 12; k++) {
+    long long x = 0;
+    for (int l = 1; l <= 48; l++) {
+      const unsigned bi = (bits >> ibit) & 1u, bj = (bits >> jbit) & 1u;
+      x = 2 * x + (long long) (bi ^ 1u);
+      bits = (bits & ~(1u << ibit)) | (((bi + bj) & 1u) << ibit);
+      ibit = ibit == 30 ? 0 : ibit + 1;
+      jbit = jbit == 30 ? 0 : jbit + 1;
+    }
+    r.x[k] = x;
+  }
+  r.carry = 0; r.ir = 11; r.jr = 7; r.ir_old = 0;
+}
+
+__host__ __device__ inline double ranlxd_uniform(Ranlxd &r) {
+  r.ir = r.ir == 11 ? 0 : r.ir + 1;
+  if (r.ir == r.ir_old) {
+    unsigned ir = r.ir, jr = r.jr;
+    long long carry = r.carry;
+    for (int k = 0; k < 202; k++) {                   // luxury level of ranlxd1
+      long long y = r.x[jr] - r.x[ir] - carry;
+      if (y < 0) { carry = 1; y += (1LL << 48); } else carry = 0;
+      r.x[ir] = y;
+      ir = ir == 11 ? 0 : ir + 1;
+      jr = jr == 11 ? 0 : jr + 1;
+    }
+    r.ir = ir; r.ir_old = ir; r.jr = jr; r.carry = carry;
+  }
+  return (double) r.x[r.ir] * (1.0 / 281474976710656.0);
+}
+
+// seedtable in the order of 2LPT.c:259-271
+static void make_seedtable(unsigned seed, int N, std::vector<unsigned> &t) {
+  t.assign((size_t) N * N, 0u);
+  Ranlxd r;
+  ranlxd_set(r, seed);
+  auto draw = [&]() { return (unsigned) (0x7fffffff * ranlxd_uniform(r)); };
+  for (int i = 0; i < N / 2; i++) {
+    int j;
+    for (j = 0; j < i; j++) t[(size_t) i * N + j] = draw();
+    for (j = 0; j < i + 1; j++) t[(size_t) j * N + i] = draw();
+    for (j = 0; j < i; j++) t[(size_t) (N - 1 - i) * N + j] = draw();
+    for (j = 0; j < i + 1; j++) t[(size_t) (N - 1 - j) * N + i] = draw();
+    for (j = 0; j < i; j++) t[(size_t) i * N + (N - 1 - j)] = draw();
+    for (j = 0; j < i + 1; j++) t[(size_t) j * N + (N - 1 - i)] = draw();
+    for (j = 0; j < i; j++) t[(size_t) (N - 1 - i) * N + (N - 1 - j)] = draw();
+    for (j = 0; j < i + 1; j++) t[(size_t) (N - 1 - j) * N + (N - 1 - i)] = draw();
+  }
+}
+
+// ------------------------------------------------------------------ delta_k
+
+__device__ __forceinline__ bool kl_encode(const KL &L, int i, int j, int k, size_t &e) {
+  if (!L.transposed) { e = ((size_t) i * L.N + j) * L.NZ + k; return true; }
+  const int jl = j - L.j0;
+  if (jl < 0 || jl >= L.nyl) return false;
+  e = ((size_t) jl * L.NZ + k) * L.N + i;
+  return true;
+}
+
+// One thread per (i, j) row of modes (2LPT.c:337-495).  power[m] = P(k) at integer |d|^2 = m,
+// already multiplied by whatever the driver applies (mg_pofk_ratio, sigma8 ratio; 2LPT.c:388-407).
+template <typename T>
+__global__ void __launch_bounds__(128)
+k_ic_delta(KL L, const unsigned *__restrict__ seedtable, const double *__restrict__ power, int nsample, double box,
+           int sphere_mode, int amplitude_fixed, int inverted, typename Cpx<T>::type *__restrict__ dk) {
+  typedef typename Cpx<T>::type C;
+  const int N = L.N, h = N / 2;
+  const long long row = blockIdx.x * (long long) blockDim.x + threadIdx.x;
+  if (row >= (long long) N * N) return;
+  const int i = (int) (row / N), j = (int) (row % N);
+  const int ii = i == 0 ? 0 : N - i, jj = j == 0 ? 0 : N - j;
+  if (L.transposed) {     // this rank stores ky in [j0, j0 + nyl): the row itself and its k = 0 conjugate row
+    const bool a = j >= L.j0 && j < L.j0 + L.nyl, b = jj >= L.j0 && jj < L.j0 + L.nyl;
+    if (!a && !b) return;
+  }
+  Ranlxd rng;
+  ranlxd_set(rng, seedtable[row]);
+  const double PI = 3.14159265358979323846;
+  const double fac = pow(box, -1.5);
+  for (int k = 0; k < h; k++) {
+    const double phase = ranlxd_uniform(rng) * 2 * PI;
+    double ampl = 0.0;
+    if (!amplitude_fixed) {
+      do { ampl = ranlxd_uniform(rng); } while (ampl == 0);
+    }
+    if (i == h || j == h || k == h) continue;
+    if (i == 0 && j == 0 && k == 0) continue;
+    const int d0 = i < h ? i : i - N, d1 = j < h ? j : j - N, d2 = k;
+    const double kv0 = d0 * 2 * PI / box, kv1 = d1 * 2 * PI / box, kv2 = d2 * 2 * PI / box;
+    const double kmag2 = kv0 * kv0 + kv1 * kv1 + kv2 * kv2;
+    const double kmag = sqrt(kmag2);
+    if (sphere_mode == 1) {
+      if (kmag * box / (2 * PI) > nsample / 2) continue;
+    } else {
+      if (fabs(kv0) * box / (2 * PI) > nsample / 2) continue;
+      if (fabs(kv1) * box / (2 * PI) > nsample / 2) continue;
+      if (fabs(kv2) * box / (2 * PI) > nsample / 2) continue;
+    }
+    double p_of_k = power[(long long) d0 * d0 + (long long) d1 * d1 + (long long) d2 * d2];
+    if (!amplitude_fixed) p_of_k *= -log(ampl);
+    double delta = fac * sqrt(p_of_k);
+    if (inverted) delta *= -1.0;
+    const double re = delta * cos(phase), im = delta * sin(phase);
+    size_t e;
+    C v, vc;
+    v.x = (T) re; v.y = (T) im; vc.x = (T) re; vc.y = (T) -im;
+    if (k > 0) {
+      if (kl_encode(L, i, j, k, e)) dk[e] = v;
+    } else if (i == 0) {
+      if (j >= h) continue;
+      if (kl_encode(L, i, j, k, e)) dk[e] = v;
+      if (kl_encode(L, i, jj, k, e)) dk[e] = vc;       // Psi(i,j,k) = Psi*(-i,-j,-k)
+    } else {
+      if (i >= h) continue;
+      if (kl_encode(L, i, j, k, e)) dk[e] = v;
+      if (kl_encode(L, ii, jj, k, e)) dk[e] = vc;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ k-space kernels of the 2LPT pipeline
+
+// wave vector with the IC code's Nyquist convention: idx < N/2 ? idx : idx - N  (2LPT.c:1229-1245)
+__device__ __forceinline__ void ic_kvec(const KL &L, int i, int j, int k, double box, double kv[3]) {
+  const int N = L.N, h = N / 2;
+  const double PI = 3.14159265358979323846;
+  kv[0] = (i < h ? i : i - N) * 2 * PI / box;
+  kv[1] = (j < h ? j : j - N) * 2 * PI / box;
+  kv[2] = (k < h ? k : k - N) * 2 * PI / box;
+}
+
+// MODE 0: psi_a          = (-kv_a/k^2 * d.im,  kv_a/k^2 * d.re)                        (2LPT.c:417-421)
+// MODE 1: psi_a,a        = (-psi_a.im * kv_a,  psi_a.re * kv_a), a = 0,1,2              (2LPT.c:1252-1268)
+// MODE 2: psi_0,1 psi_0,2 psi_1,2
+// MODE 3: psi2_a         = ( s.im * kv_a / k^2, -s.re * kv_a / k^2)                      (2LPT.c:1348-1355)
+// MODE 4: scale-dependent fields: (-d.im * kv_a/k^2 * G[m], d.re * kv_a/k^2 * G[m])      (2LPT.c:1618-1626)
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256)
+k_ic_kernel(KL L, const typename Cpx<T>::type *__restrict__ src, typename Cpx<T>::type *__restrict__ o0,
+            typename Cpx<T>::type *__restrict__ o1, typename Cpx<T>::type *__restrict__ o2, double box,
+            const double *__restrict__ gtab, double norm) {
+  typedef typename Cpx<T>::type C;
+  KLOOP(e, L) {
+    int i, j, k;
+    kl_decode(L, e, i, j, k);
+    double kv[3];
+    ic_kvec(L, i, j, k, box, kv);
+    const double kmag2 = kv[0] * kv[0] + kv[1] * kv[1] + kv[2] * kv[2];
+    const C s = src[e];
+    C out[3];
+    if (!(kmag2 > 0.0)) {
+      out[0].x = out[0].y = out[1].x = out[1].y = out[2].x = out[2].y = (T) 0;
+    } else if (MODE == 0) {
+#pragma unroll
+      for (int a = 0; a < 3; a++) { out[a].x = (T) (-kv[a] / kmag2 * (double) s.y); out[a].y = (T) (kv[a] / kmag2 * (double) s.x); }
+    } else if (MODE == 1 || MODE == 2) {
+      T pre[3], pim[3];
+#pragma unroll
+      for (int a = 0; a < 3; a++) { pre[a] = (T) (-kv[a] / kmag2 * (double) s.y); pim[a] = (T) (kv[a] / kmag2 * (double) s.x); }
+      const int A[3] = {0, MODE == 1 ? 1 : 0, MODE == 1 ? 2 : 1}, B[3] = {MODE == 1 ? 0 : 1, MODE == 1 ? 1 : 2, 2};
+#pragma unroll
+      for (int q = 0; q < 3; q++) { out[q].x = (T) (-(double) pim[A[q]] * kv[B[q]]); out[q].y = (T) ((double) pre[A[q]] * kv[B[q]]); }
+    } else if (MODE == 3) {
+#pragma unroll
+      for (int a = 0; a < 3; a++) { out[a].x = (T) ((double) s.y * kv[a] / kmag2); out[a].y = (T) (-(double) s.x * kv[a] / kmag2); }
+    } else {
+      const int N = L.N;
+      const int d0 = i < N / 2 ? i : i - N, d1 = j < N / 2 ? j : j - N, d2 = k < N / 2 ? k : k - N;
+      const double g = norm * gtab[(long long) d0 * d0 + (long long) d1 * d1 + (long long) d2 * d2];
+#pragma unroll
+      for (int a = 0; a < 3; a++) { out[a].x = (T) (-(double) s.y * kv[a] / kmag2 * g); out[a].y = (T) ((double) s.x * kv[a] / kmag2 * g); }
+    }
+    o0[e] = out[0]; o1[e] = out[1]; o2[e] = out[2];
+  }
+}
+
+// second-order source, two passes over real space (2LPT.c:1282-1290):
+//   pass 0: S  = g00 (g11 + g22) + g11 g22         pass 1: S = S - g01^2 - g02^2 - g12^2
+template <typename T>
+__global__ void k_ic_source(T *__restrict__ S, const T *__restrict__ a, const T *__restrict__ b, const T *__restrict__ cc,
+                            size_t n, int pass) {
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+    const T x = a[i], y = b[i], z = cc[i];
+    if (pass == 0) S[i] = x * (y + z) + y * z;
+    else S[i] = S[i] - x * x - y * y - z * z;
+  }
+}
+
+// stored second-order scalar: delta2_k = -S_k, zero mode cleared (2LPT.c:1336-1344)
+template <typename C>
+__global__ void k_ic_neg(const C *__restrict__ s, C *__restrict__ o, size_t n, size_t zero_index) {
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+    C v = s[i];
+    v.x = -v.x; v.y = -v.y;
+    if (i == zero_index) { v.x = 0; v.y = 0; }
+    o[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------ read-out at the Lagrangian points
+
+// trilinear read-out of three real grids at q = (n + p0, m, p) * Nmesh / Nsample (2LPT.c:1419-1488)
+// out[axis * stride + coord] = value * scale (float);  partial[3 * block + axis] = sum (double)
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_ic_readout(size_t nloc, int ns, int p0, int N, int NZ, int x0, int nx, const T *__restrict__ g0, const T *__restrict__ g1,
+             const T *__restrict__ g2, double scale, float *__restrict__ out, size_t stride, double *__restrict__ partial) {
+  double s0 = 0, s1 = 0, s2 = 0;
+  const size_t rz = (size_t) 2 * NZ;
+  for (size_t c = blockIdx.x * (size_t) blockDim.x + threadIdx.x; c < nloc; c += (size_t) gridDim.x * blockDim.x) {
+    const int p = (int) (c % ns);
+    const size_t t = c / ns;
+    const int m = (int) (t % ns), n = (int) (t / ns);
+    double u = (double) ((long long) (n + p0) * N) / (double) ns;
+    double v = (double) ((long long) m * N) / (double) ns;
+    double w = (double) ((long long) p * N) / (double) ns;
+    int i = (int) u, j = (int) v, k = (int) w;
+    if (i == x0 + nx) i = x0 + nx - 1;
+    if (i < x0) i = x0;
+    if (j == N) j = N - 1;
+    if (k == N) k = N - 1;
+    u -= i; v -= j; w -= k;
+    i -= x0;
+    const int i2 = i + 1;
+    int j2 = j + 1, k2 = k + 1;
+    if (j2 >= N) j2 -= N;
+    if (k2 >= N) k2 -= N;
+    const double f1 = (1 - u) * (1 - v) * (1 - w), f2 = (1 - u) * (1 - v) * w, f3 = (1 - u) * v * (1 - w), f4 = (1 - u) * v * w;
+    const double f5 = u * (1 - v) * (1 - w), f6 = u * (1 - v) * w, f7 = u * v * (1 - w), f8 = u * v * w;
+    const size_t a = ((size_t) i * N + j) * rz, b = ((size_t) i * N + j2) * rz, cc = ((size_t) i2 * N + j) * rz,
+                 d = ((size_t) i2 * N + j2) * rz;
+#define RD(G)                                                                                                     \
+  ((double) G[a + k] * f1 + (double) G[a + k2] * f2 + (double) G[b + k] * f3 + (double) G[b + k2] * f4 +        \
+   (double) G[cc + k] * f5 + (double) G[cc + k2] * f6 + (double) G[d + k] * f7 + (double) G[d + k2] * f8)
+    const double r0 = RD(g0) * scale, r1 = RD(g1) * scale, r2 = RD(g2) * scale;
+#undef RD
+    out[c] = (float) r0; out[stride + c] = (float) r1; out[2 * stride + c] = (float) r2;
+    s0 += r0; s1 += r1; s2 += r2;
+  }
+  block_sum3(s0, s1, s2);
+  if (threadIdx.x == 0) { partial[3 * blockIdx.x] = s0; partial[3 * blockIdx.x + 1] = s1; partial[3 * blockIdx.x + 2] = s2; }
+}
+
+// particle initialisation (main.c:257-309): ZA/LPT mean removal (2LPT.c:1501-1508), ID, Vel, Pos
+__global__ void __launch_bounds__(256)
+k_ic_particles(size_t nloc, int ns, int p0, const float *__restrict__ za, const float *__restrict__ lpt, size_t stride,
+               double m1x, double m1y, double m1z, double m2x, double m2y, double m2z, double box, int use_cola, double Di,
+               double Di2, double dDdy, double dD2dy, float4 *__restrict__ pA, float4 *__restrict__ pB, float4 *__restrict__ pC,
+               float2 *__restrict__ pE) {
+  const float boxf = (float) box;
+  const double dq = box / (double) ns;
+  for (size_t c = blockIdx.x * (size_t) blockDim.x + threadIdx.x; c < nloc; c += (size_t) gridDim.x * blockDim.x) {
+    const int k = (int) (c % ns);
+    const size_t t = c / ns;
+    const int j = (int) (t % ns), i = (int) (t / ns);
+    const unsigned long long id = ((unsigned long long) ((long long) (i + p0) * ns + j)) * (unsigned long long) ns + (unsigned long long) k;
+    float D[3], D2[3], V[3], X[3];
+    const double m1[3] = {m1x, m1y, m1z}, m2[3] = {m2x, m2y, m2z};
+    const double q[3] = {(i + p0) * dq, j * dq, k * dq};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      D[a] = (float) ((double) za[a * stride + c] - m1[a]);
+      D2[a] = (float) ((double) lpt[a * stride + c] - m2[a]);
+      V[a] = use_cola ? 0.0f : (float) ((double) D[a] * dDdy + (double) D2[a] * dD2dy);
+      float x = (float) (q[a] + (double) D[a] * Di + (double) D2[a] * Di2);
+      while (x >= boxf) x -= boxf;
+      while (x < 0) x += boxf;
+      if (x == boxf) x = 0.0f;
+      X[a] = x;
+    }
+    pA[c] = make_float4(X[0], X[1], X[2], __uint_as_float((unsigned) (id & 0xffffffffull)));
+    pB[c] = make_float4(V[0], V[1], V[2], __uint_as_float((unsigned) (id >> 32)));
+    pC[c] = make_float4(D[0], D[1], D[2], D2[0]);
+    pE[c] = make_float2(D2[1], D2[2]);
+  }
+}
+
+// ------------------------------------------------------------------ host orchestration
+
+template <typename T>
+static void ic_generate_t(Ctx &c, const mgp_ic_config *ic) {
+  typedef typename Cpx<T>::type C;
+  const int N = c.N, ns = c.cfg.nsample;
+  const KL L = layout_of(c);
+  const size_t nloc = (size_t) c.npl * ns * ns;
+  REQUIRE(nloc <= c.cap, MGP_ERR_BUFFER, "mgp_ic_generate: particle capacity too small");
+  const size_t mmax = (size_t) 3 * (N / 2) * (N / 2) + 1;
+  REQUIRE(ic->power_by_k2 != nullptr && ic->n_power >= mmax, MGP_ERR_INVALID,
+          "mgp_ic_generate: power_by_k2 must hold 3 (Nmesh/2)^2 + 1 entries");
+
+  // scratch: delta_k lives in mgarray_one when the model has one, else in a temporary grid
+  void *tmp = nullptr;
+  C *dk = (C *) c.grid[MGP_GRID_MG_ONE];
+  if (!dk) { CK(cudaMalloc(&tmp, c.grid_bytes())); dk = (C *) tmp; }
+  void *save4 = c.grid[MGP_GRID_MG_ONE];
+  c.grid[MGP_GRID_MG_ONE] = dk;           // so that the FFT helpers can address it by id
+
+  std::vector<unsigned> seeds;
+  if (ic->seedtable) seeds.assign(ic->seedtable, ic->seedtable + (size_t) N * N);
+  else make_seedtable(ic->seed, N, seeds);
+  unsigned *d_seed = nullptr; double *d_pow = nullptr;
+  CK(cudaMalloc(&d_seed, seeds.size() * sizeof(unsigned)));
+  CK(cudaMalloc(&d_pow, mmax * sizeof(double)));
+  CK(cudaMemcpyAsync(d_seed, seeds.data(), seeds.size() * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
+  CK(cudaMemcpyAsync(d_pow, ic->power_by_k2, mmax * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+
+  C *f[3] = {(C *) c.grid[1], (C *) c.grid[2], (C *) c.grid[3]};
+  T *fr[3] = {(T *) c.grid[1], (T *) c.grid[2], (T *) c.grid[3]};
+  T *S = (T *) c.grid[0];
+  const unsigned gk = grid_for(L.total, 256), gr = grid_for(c.grid_vals, 256);
+
+  CK(cudaMemsetAsync(dk, 0, c.grid_bytes(), c.stream));
+  k_ic_delta<T><<<(unsigned) (((size_t) N * N + 127) / 128), 128, 0, c.stream>>>(L, d_seed, d_pow, ns, c.cfg.box, ic->sphere_mode,
+                                                                               ic->amplitude_fixed, ic->inverted, dk);
+  c.launches++;
+  // second-order source from the six gradients
+  for (int pass = 0; pass < 2; pass++) {
+    if (pass == 0) k_ic_kernel<T, 1><<<gk, 256, 0, c.stream>>>(L, dk, f[0], f[1], f[2], c.cfg.box, nullptr, 1.0);
+    else k_ic_kernel<T, 2><<<gk, 256, 0, c.stream>>>(L, dk, f[0], f[1], f[2], c.cfg.box, nullptr, 1.0);
+    fft_c2r_forces(c);
+    k_ic_source<T><<<gr, 256, 0, c.stream>>>(S, fr[0], fr[1], fr[2], c.grid_vals, pass);
+    c.launches += 2;
+  }
+  fft_r2c(c, MGP_GRID_DENSITY);           // S_k, unnormalised like the reference's
+
+  // displacement fields at the Lagrangian points: ZA into disp[], 2LPT into the key/perm scratch
+  float *za = c.disp;                      // [3][cap] floats
+  float *lpt = (float *) c.pA2;            // the sort's second buffer set is idle here: 4 cap floats
+  const unsigned gp = grid_for(nloc, 256, 8);
+  reduce_alloc(c, (size_t) gp * 3 + 32);
+  double means[6];
+  const double n3 = (double) N * (double) N * (double) N;
+  for (int order = 1; order <= 2; order++) {
+    if (order == 1) k_ic_kernel<T, 0><<<gk, 256, 0, c.stream>>>(L, dk, f[0], f[1], f[2], c.cfg.box, nullptr, 1.0);
+    else k_ic_kernel<T, 3><<<gk, 256, 0, c.stream>>>(L, (const C *) c.grid[0], f[0], f[1], f[2], c.cfg.box, nullptr, 1.0);
+    fft_c2r_forces(c);
+    halo_fill_forces(c);
+    double *res = c.d_red + (size_t) gp * 3;
+    k_ic_readout<T><<<gp, 256, 0, c.stream>>>(nloc, ns, c.p0, N, c.NZ, c.x0, c.nx, fr[0], fr[1], fr[2],
+                                             order == 1 ? 1.0 : (-3.0 / 7.0) / n3, order == 1 ? za : lpt, c.cap, c.d_red);
+    k_final_reduce<<<1, 256, 0, c.stream>>>(c.d_red, (int) gp, 3, 3, 1.0, res);
+    c.launches += 3;
+    allreduce_sum(c, res, 3);
+    CK(cudaMemcpyAsync(c.h_red, res, 3 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    CK(cudaStreamSynchronize(c.stream));
+    const double tot = (double) ns * (double) ns * (double) ns;
+    for (int a = 0; a < 3; a++) means[3 * (order - 1) + a] = c.h_red[a] / tot;
+  }
+  for (int a = 0; a < 6; a++) c.ic_means[a] = means[a];
+  c.ic_ready = true;
+  c.np = 0;
+
+  if (c.cfg.scale_dependent) {
+    // keep delta1_k and delta2_k = -S_k for the per-step scale-dependent displacement fields
+    REQUIRE(c.sd_delta[0] && c.sd_delta[1], MGP_ERR_STATE, "scale-dependent storage missing");
+    CK(cudaMemcpyAsync(c.sd_delta[0], dk, L.total * sizeof(C), cudaMemcpyDeviceToDevice, c.stream));
+    size_t zero_index = (size_t) -1;
+    if (!L.transposed || L.j0 == 0) zero_index = 0;      // mode (0,0,0) is element 0 of the rank that owns ky = 0
+    k_ic_neg<C><<<gk, 256, 0, c.stream>>>((const C *) c.grid[0], (C *) c.sd_delta[1], L.total, zero_index);
+    c.launches++;
+  }
+  CK(cudaStreamSynchronize(c.stream));
+  c.grid[MGP_GRID_MG_ONE] = save4;
+  if (tmp) CK(cudaFree(tmp));
+  CK(cudaFree(d_seed)); CK(cudaFree(d_pow));
+}
+
+void ic_generate(Ctx &c, const mgp_ic_config *ic) {
+  REQUIRE(ic != nullptr, MGP_ERR_INVALID, "mgp_ic_generate: config is NULL");
+  if (c.gbytes == 4) ic_generate_t<float>(c, ic); else ic_generate_t<double>(c, ic);
+}
+
+void ic_init_particles(Ctx &c, double Di, double Di2, double dDdy, double dD2dy) {
+  REQUIRE(c.ic_ready, MGP_ERR_STATE, "mgp_init_particles: call mgp_ic_generate first");
+  const int ns = c.cfg.nsample;
+  const size_t nloc = (size_t) c.npl * ns * ns;
+  const double *m = c.ic_means;
+  if (nloc)
+    k_ic_particles<<<grid_for(nloc, 256), 256, 0, c.stream>>>(nloc, ns, c.p0, c.disp, (const float *) c.pA2, c.cap, m[0], m[1], m[2],
+                                                            m[3], m[4], m[5], c.cfg.box, c.cfg.use_cola, Di, Di2, dDdy, dD2dy, c.pA,
+                                                            c.pB, c.pC, (float2 *) c.pE);
+  c.launches++;
+  CK(cudaStreamSynchronize(c.stream));
+  c.np = nloc;
+  c.sorted = false;
+  c.drifts_since_sort = 1 << 30;
+  c.have_disp = false;
+  c.ic_ready = false;      // disp[] / pA2 scratch is reused from here on
+}
+
+void ic_seedtable(unsigned seed, int N, unsigned *out) {
+  std::vector<unsigned> t;
+  make_seedtable(seed, N, t);
+  memcpy(out, t.data(), t.size() * sizeof(unsigned));
+}
+
+double ic_ranlxd1_draw(unsigned long seed, long n) {
+  Ranlxd r;
+  ranlxd_set(r, seed);
+  double v = 0;
+  for (long i = 0; i < n; i++) v = ranlxd_uniform(r);
+  return v;
+}
+
+}  // namespace mgp

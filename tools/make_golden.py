@@ -117,9 +117,29 @@ def run_fofr(N=16, box=60.0, nsteps=3):
     print("run_fofr", P0.shape, np.stack(pk).shape)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--ic" not in sys.argv:
     one_step("lcdm", "lcdm")
     one_step("fofr", "lcdm", extra=dict(include_screening=1, fofr0=1e-5, nfofr=1.0))
     one_step("dgp", "dgp", a=0.8, extra=dict(include_screening=1, rcH0_DGP=1.2, Rsmooth_global=1.0))
     kickdrift()
     run_fofr()
+
+
+def ic_fixture(N=16, box=60.0):
+    """Reference displacement_fields() + particle init on seed 5001 (LCDM: plain PowerSpec amplitudes)."""
+    pf = bench.write_paramfile("/tmp/mgp_golden_ic", N, box, "lcdm", 10)
+    r = ref_lib.RefLib("lcdm")
+    with ref_lib._silenced(True):
+        r.init_from_paramfile(pf)
+        h = N // 2
+        m = np.arange(3 * h * h + 1)
+        power = np.array([r.lib.PowerSpec(2 * np.pi / box * np.sqrt(float(v))) for v in m])
+        ic = r.make_ic()
+    P = r.particles().copy()
+    np.savez_compressed(os.path.join(OUT, "ic_lcdm.npz"), N=N, box=box, seed=5001, power_by_k2=power, ZA=ic["ZA"], LPT=ic["LPT"],
+                        Di=ic["Di"], Di2=ic["Di2"], pos=P["Pos"], id=P["ID"])
+    print("ic_lcdm", ic["ZA"].std(0), ic["LPT"].std(0))
+
+
+if __name__ == "__main__" and "--ic" in sys.argv:
+    ic_fixture()
