@@ -31,6 +31,7 @@ sys.path.insert(0, ROOT)
 OMEGA, SIGMA8, Z_INIT, NSTEPS_RUN = 0.267, 0.8, 9.0, 30
 FOFR0, NFOFR, RCH0, RSMOOTH = 1e-5, 1.0, 1.0, 1.0
 # compulsory HBM bytes per particle-step of a maximally fused step
+WEAK_NMESH = {1: 256, 2: 320, 4: 400, 8: 512}
 ALGO_BYTES = {"lcdm": lambda g: 120 + 32 * g, "fofr": lambda g: 120 + 51 * g, "dgp": lambda g: 120 + 51 * g}
 
 
@@ -63,54 +64,6 @@ def amplitude_table(nmesh, box):
     P = 10.0 ** np.interp(lkm, lk, lP, left=-np.inf, right=-np.inf)    # PowerSpec_Tabulated: 0 outside the table
     P[0] = 0.0
     return P
-
-
-def host_ics(nmesh, box, seed, cos):
-    """Gaussian field + 2LPT displacements on the host (numpy) -- used until the particle store is
-    filled; it is data generation, outside every timed region.  Same conventions as 2LPT.c:337-495,
-    1224-1359 (delta = Box^-1.5 sqrt(P (-ln u)), psi_k = i k / k^2 delta, psi2 = -3/7 ...)."""
-    import scipy.fft as sfft
-    N = nmesh
-    rng = np.random.default_rng(seed)
-    amp = amplitude_table(N, box)
-    i = np.arange(N)
-    d = np.where(i >= N // 2, i - N, i).astype(np.int64)
-    dz = np.arange(N // 2 + 1, dtype=np.int64)
-    m = d[:, None, None] ** 2 + d[None, :, None] ** 2 + dz[None, None, :] ** 2
-    white = rng.standard_normal((N, N, N)).astype(np.float64)
-    wk = sfft.rfftn(white, workers=-1) / np.sqrt(float(N) ** 3)      # <|wk|^2> = 1, Hermitian by construction
-    dk = wk * np.sqrt(amp[m]) * box ** -1.5
-    nyq = (np.abs(d)[:, None, None] == N // 2) | (np.abs(d)[None, :, None] == N // 2) | (dz[None, None, :] == N // 2)
-    dk[nyq] = 0.0
-    dk[0, 0, 0] = 0.0
-    kf = 2.0 * np.pi / box
-    kv = (d[:, None, None] * kf, d[None, :, None] * kf, dz[None, None, :] * kf)
-    k2 = (m * kf * kf).astype(np.float64)
-    k2[0, 0, 0] = 1.0
-    psi_k = [1j * kv[a] / k2 * dk for a in range(3)]
-    ZA = [sfft.irfftn(p, s=(N, N, N), workers=-1) * float(N) ** 3 for p in psi_k]
-    # 2LPT source: sum_{i<j} psi_ii psi_jj - psi_ij^2
-    g = {}
-    for a in range(3):
-        for b in range(a, 3):
-            g[(a, b)] = sfft.irfftn(1j * kv[b] * psi_k[a], s=(N, N, N), workers=-1) * float(N) ** 3
-    S = g[(0, 0)] * (g[(1, 1)] + g[(2, 2)]) + g[(1, 1)] * g[(2, 2)] - g[(0, 1)] ** 2 - g[(0, 2)] ** 2 - g[(1, 2)] ** 2
-    del g
-    Sk = sfft.rfftn(S, workers=-1) / float(N) ** 3
-    LPT = [(-3.0 / 7.0) * sfft.irfftn(-1j * kv[a] / k2 * Sk, s=(N, N, N), workers=-1) * float(N) ** 3 for a in range(3)]
-    ZA = np.stack([z.reshape(-1) for z in ZA], 1).astype(np.float32)
-    LPT = np.stack([z.reshape(-1) for z in LPT], 1).astype(np.float32)
-    ZA -= ZA.mean(0, dtype=np.float64).astype(np.float32)
-    LPT -= LPT.mean(0, dtype=np.float64).astype(np.float32)
-    A = 1.0 / (1.0 + Z_INIT)
-    Di, Di2 = cos.growth_D(A), cos.growth_D2(A)
-    q = np.stack(np.meshgrid(i, i, i, indexing="ij"), -1).reshape(-1, 3).astype(np.float64) * (box / N)
-    pos = (q + ZA.astype(np.float64) * Di + LPT.astype(np.float64) * Di2).astype(np.float32)     # main.c:302-304
-    b = np.float32(box)
-    pos = np.where(pos >= b, pos - b, pos)
-    pos = np.where(pos < 0, pos + b, pos)
-    pos[pos == b] = 0
-    return pos.astype(np.float32), np.zeros_like(pos), ZA, LPT
 
 
 # ------------------------------------------------------------------ clocks
@@ -198,10 +151,10 @@ def run_ours(args):
         dist.broadcast_object_list(ids, src=0)
         nccl_id = ids[0]
 
-    N, g = args.nmesh, args.grid_bytes
-    # weak scaling: every GPU owns N^3 / 1 particles of a box that grows along x ... the slab
-    # decomposition needs a cubic mesh, so the mesh side grows with world^(1/3) where that is an
-    # integer multiple, otherwise strong scaling on the fixed mesh is reported.
+    # weak scaling: the mesh side grows so that every GPU keeps ~256^3 = 16.8 M particles and cells
+    # (1: 256, 2: 320, 4: 400, 8: 512; the slab decomposition needs a cubic mesh divisible by the rank count)
+    N = args.nmesh if args.nmesh else WEAK_NMESH.get(world, 256)
+    g = args.grid_bytes
     box = box_for(N)
     model = args.model
     cos = cosmology.LCDM(OMEGA, Z_INIT)
@@ -210,14 +163,10 @@ def run_ours(args):
                 device=local, nccl_id=nccl_id, deposit_mode=args.deposit_mode, sort_particles=args.sort_interval)
     pm.set_pofk(64, 1, 1, 0.03, 2.0)          # paramfiles/additions_compute_pofk.txt
     t0 = time.time()
-    pos, vel, ZA, LPT = host_ics(N, box, 5001, cos)
-    ids = np.arange(N ** 3, dtype=np.uint64)
-    if world > 1:
-        sel = (pos[:, 0].astype(np.float64) * (N / box)).astype(np.int64)
-        mine = (sel >= pm.local_x_start) & (sel < pm.local_x_start + pm.local_nx)
-        pos, vel, ZA, LPT, ids = pos[mine], vel[mine], ZA[mine], LPT[mine], ids[mine]
+    A0 = 1.0 / (1.0 + Z_INIT)
+    pm.ic_generate(amplitude_table(N, box), seed=5001)           # displacement_fields() on the GPU(s)
+    pm.init_particles(cos.growth_D(A0), cos.growth_D2(A0))
     t_ic = time.time() - t0
-    pm.upload_particles(pos, vel, ZA, LPT, ids)
     npart_total = N ** 3
     st = Stepper(pm, cos, model, box)
     stream = torch.cuda.ExternalStream(pm.stream)
@@ -307,14 +256,14 @@ def run_ours(args):
             "phases_ms": {k: round(v, 4) for k, v in phases.items()}}
     line = {"metric": "particle-updates/sec per COLA PM step", "value": value, "unit": "particle-updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 particles, f%d grids/FFTs, f64 weights" % (8 * g), "data": "synthetic",
             "config": {"workload": "%s%s COLA step, Npart=Nmesh=%d^3, Box=%g Mpc/h, P(k) every step, z=9->0 in %d steps "
                                    "(reference configs[1] without SCALEDEPENDENT growth: build MODEL=FOFR_LCDM)"
                                    % (model, " with screening" if model != "lcdm" else "", N, box, NSTEPS_RUN),
                        "nmesh": N, "npart": npart_total, "grid_bytes": g, "deposit_mode": args.deposit_mode, "sort_interval": args.sort_interval,
                        "l2": "inputs larger than L2 (particles %.1f GB, grids %.1f GB each)" % (N ** 3 * 56 / 1e9, N ** 3 * g / 1e9),
-                       "ic_seconds_host": round(t_ic, 1)},
+                       "ic_seconds_gpu": round(t_ic, 2)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "e2e": e2e}
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_reference(args, sample_nmesh=min(N, 128), steps=2, warmup=1)
@@ -390,7 +339,8 @@ def cpu_reference(args, sample_nmesh, steps, warmup):
         return {"value": None, "unit": "particle-updates/s", "cores": 1, "kind": "reference",
                 "sample": "oracle/_ref not built (needs /root/reference at build time)"}
     N = sample_nmesh
-    box = box_for(args.nmesh) * N / args.nmesh
+    nm_full = args.nmesh if args.nmesh else WEAK_NMESH.get(args.gpus, 256)
+    box = box_for(nm_full) * N / nm_full
     wd = tempfile.mkdtemp(prefix="mgp_ref_")
     pf = write_paramfile(wd, N, box, args.model, NSTEPS_RUN)
     drv = ref_lib.RefRun(variant, pf, quiet=True)
@@ -410,14 +360,15 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    N = min(args.nmesh, args.ref_nmesh)
+    nm = args.nmesh if args.nmesh else WEAK_NMESH.get(args.gpus, 256)
+    N = min(nm, args.ref_nmesh)
     cb = cpu_reference(args, sample_nmesh=N, steps=args.steps, warmup=args.warmup)
     line = {"impl": "reference", "metric": "particle-updates/sec per COLA PM step", "value": cb["value"],
             "unit": "particle-updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": cb.get("ms_per_step"), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32 particles, f64 grids/FFTs", "data": "synthetic",
             "config": {"workload": "%s COLA step, reference CPU path, bounded sample Npart=Nmesh=%d^3 of the %d^3 workload"
-                                   % (args.model, N, args.nmesh), "nmesh": N},
+                                   % (args.model, N, nm), "nmesh": N},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -429,7 +380,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--nmesh", type=int, default=256)
+    ap.add_argument("--nmesh", type=int, default=0, help="0: 256 on one GPU, weak-scaled with --gpus")
     ap.add_argument("--ref-nmesh", type=int, default=128)
     ap.add_argument("--model", default="fofr", choices=["fofr", "dgp", "lcdm"])
     ap.add_argument("--grid-bytes", type=int, default=8, choices=[4, 8])

@@ -111,6 +111,11 @@ struct Ctx {
   bool ic_ready = false;
   void *sd_delta[2] = {nullptr, nullptr};    // delta1_k, delta2_k (cdelta_cdm, cdelta_cdm2; vars.h:272-273)
 
+  void *stage = nullptr;      // host <-> device particle staging (two chunks)
+  size_t stage_bytes = 0;
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr;
+
   double *d_red = nullptr;    // device reduction scratch (doubles)
   double *h_red = nullptr;    // pinned host mirror
   size_t red_cap = 0;

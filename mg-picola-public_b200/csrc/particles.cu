@@ -75,7 +75,9 @@ void particles_free(Ctx &c) {
   cudaFree(c.pA); cudaFree(c.pB); cudaFree(c.pC); cudaFree(c.pE); cudaFree(c.disp);
   cudaFree(c.pA2); cudaFree(c.pB2); cudaFree(c.pC2); cudaFree(c.pE2);
   for (int i = 0; i < 2; i++) { cudaFree(c.key[i]); cudaFree(c.perm[i]); }
-  cudaFree(c.row_start); cudaFree(c.cub_temp); cudaFree(c.bucket_start);
+  cudaFree(c.row_start); cudaFree(c.cub_temp); cudaFree(c.bucket_start); cudaFree(c.stage);
+  for (int i = 0; i < 2; i++) if (c.stage_ev[i]) cudaEventDestroy(c.stage_ev[i]);
+  if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
   cudaFree(c.d_red); if (c.h_red) cudaFreeHost(c.h_red);
   cudaFree(c.d_flag); if (c.h_flag) cudaFreeHost(c.h_flag);
 }
@@ -112,34 +114,62 @@ __global__ void k_unpack(size_t n, size_t off, float *pos, float *vel, float *D,
   }
 }
 
-static const size_t kChunk = (size_t) 1 << 24;   // particles per staging chunk
+static const size_t kChunk = (size_t) 1 << 22;   // particles per staging chunk (two chunks in flight)
+
+// Persistent double-buffered staging area: host arrays [n][3] <-> device SoA records.  With pinned
+// host memory every copy is asynchronous, chunk c+1's copy overlaps chunk c's (un)pack kernel and the
+// host blocks once, at the end.
+static float *stage_buffer(Ctx &c, size_t ch) {
+  const size_t need = 2 * ch * (12 * sizeof(float) + sizeof(uint64_t));
+  if (c.stage_bytes < need) {
+    if (c.stage) CK(cudaFree(c.stage));
+    CK(cudaMalloc(&c.stage, need));
+    c.stage_bytes = need;
+    for (int i = 0; i < 2; i++)
+      if (!c.stage_ev[i]) CK(cudaEventCreateWithFlags(&c.stage_ev[i], cudaEventDisableTiming));
+    if (!c.copy_stream) CK(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+  }
+  return (float *) c.stage;
+}
 
 void particles_upload(Ctx &c, uint64_t n, const float *pos, const float *vel, const float *D, const float *D2,
                       const uint64_t *id) {
   REQUIRE(n <= c.cap, MGP_ERR_BUFFER, "mgp_upload_particles: more particles than ceil(NumPart*Buffer); increase Buffer");
-  REQUIRE(pos != nullptr, MGP_ERR_INVALID, "mgp_upload_particles: pos is NULL");
+  REQUIRE(pos != nullptr || n == 0, MGP_ERR_INVALID, "mgp_upload_particles: pos is NULL");
   const size_t ch = n < kChunk ? (n ? n : 1) : kChunk;
-  float *st = nullptr;   // staging: 4 x [ch][3] floats + [ch] u64
-  CK(cudaMalloc(&st, ch * (12 * sizeof(float) + sizeof(uint64_t))));
-  float *s_pos = st, *s_vel = st + 3 * ch, *s_D = st + 6 * ch, *s_D2 = st + 9 * ch;
-  unsigned long long *s_id = (unsigned long long *) (st + 12 * ch);
-  for (size_t off = 0; off < n; off += ch) {
+  float *base = stage_buffer(c, ch);
+  const size_t rec = ch * (12 * sizeof(float) + sizeof(uint64_t));
+  cudaEvent_t packed[2] = {c.stage_ev[0], c.stage_ev[1]};
+  cudaEvent_t copied;
+  CK(cudaEventCreateWithFlags(&copied, cudaEventDisableTiming));
+  CK(cudaStreamSynchronize(c.stream));
+  int it = 0;
+  for (size_t off = 0; off < n; off += ch, it++) {
+    const int b = it & 1;
+    float *st = (float *) ((char *) base + (size_t) b * rec);
+    float *s_pos = st, *s_vel = st + 3 * ch, *s_D = st + 6 * ch, *s_D2 = st + 9 * ch;
+    unsigned long long *s_id = (unsigned long long *) (st + 12 * ch);
     const size_t m = (n - off) < ch ? (n - off) : ch;
-    CK(cudaMemcpyAsync(s_pos, pos + 3 * off, m * 12, cudaMemcpyHostToDevice, c.stream));
-    if (vel) CK(cudaMemcpyAsync(s_vel, vel + 3 * off, m * 12, cudaMemcpyHostToDevice, c.stream));
-    if (D) CK(cudaMemcpyAsync(s_D, D + 3 * off, m * 12, cudaMemcpyHostToDevice, c.stream));
-    if (D2) CK(cudaMemcpyAsync(s_D2, D2 + 3 * off, m * 12, cudaMemcpyHostToDevice, c.stream));
-    if (id) CK(cudaMemcpyAsync(s_id, id + off, m * 8, cudaMemcpyHostToDevice, c.stream));
+    if (it >= 2) CK(cudaStreamWaitEvent(c.copy_stream, packed[b], 0));     // buffer b free again
+    CK(cudaMemcpyAsync(s_pos, pos + 3 * off, m * 12, cudaMemcpyHostToDevice, c.copy_stream));
+    if (vel) CK(cudaMemcpyAsync(s_vel, vel + 3 * off, m * 12, cudaMemcpyHostToDevice, c.copy_stream));
+    if (D) CK(cudaMemcpyAsync(s_D, D + 3 * off, m * 12, cudaMemcpyHostToDevice, c.copy_stream));
+    if (D2) CK(cudaMemcpyAsync(s_D2, D2 + 3 * off, m * 12, cudaMemcpyHostToDevice, c.copy_stream));
+    if (id) CK(cudaMemcpyAsync(s_id, id + off, m * 8, cudaMemcpyHostToDevice, c.copy_stream));
+    CK(cudaEventRecord(copied, c.copy_stream));
+    CK(cudaStreamWaitEvent(c.stream, copied, 0));
     k_pack<<<grid_for(m, 256), 256, 0, c.stream>>>(m, off, s_pos, vel ? s_vel : nullptr, D ? s_D : nullptr,
                                                    D2 ? s_D2 : nullptr, id ? s_id : nullptr, off, c.pA, c.pB, c.pC,
                                                    (float2 *) c.pE);
+    CK(cudaEventRecord(packed[b], c.stream));
     c.launches++;
-    CK(cudaStreamSynchronize(c.stream));
   }
-  CK(cudaFree(st));
+  CK(cudaStreamSynchronize(c.stream));
+  CK(cudaEventDestroy(copied));
   c.np = n;
   c.sorted = false;
   c.drifts_since_sort = 1 << 30;
+  c.np_after_sort = SIZE_MAX;
   c.have_disp = false;
 }
 
@@ -147,24 +177,35 @@ void particles_download(Ctx &c, float *pos, float *vel, float *D, float *D2, uin
   const size_t n = c.np;
   if (!n) return;
   const size_t ch = n < kChunk ? n : kChunk;
-  float *st = nullptr;
-  CK(cudaMalloc(&st, ch * (12 * sizeof(float) + sizeof(uint64_t))));
-  float *s_pos = st, *s_vel = st + 3 * ch, *s_D = st + 6 * ch, *s_D2 = st + 9 * ch;
-  unsigned long long *s_id = (unsigned long long *) (st + 12 * ch);
-  for (size_t off = 0; off < n; off += ch) {
+  float *base = stage_buffer(c, ch);
+  const size_t rec = ch * (12 * sizeof(float) + sizeof(uint64_t));
+  cudaEvent_t drained[2] = {c.stage_ev[0], c.stage_ev[1]};
+  cudaEvent_t unpacked;
+  CK(cudaEventCreateWithFlags(&unpacked, cudaEventDisableTiming));
+  int it = 0;
+  for (size_t off = 0; off < n; off += ch, it++) {
+    const int b = it & 1;
+    float *st = (float *) ((char *) base + (size_t) b * rec);
+    float *s_pos = st, *s_vel = st + 3 * ch, *s_D = st + 6 * ch, *s_D2 = st + 9 * ch;
+    unsigned long long *s_id = (unsigned long long *) (st + 12 * ch);
     const size_t m = (n - off) < ch ? (n - off) : ch;
+    if (it >= 2) CK(cudaStreamWaitEvent(c.stream, drained[b], 0));          // buffer b copied out
     k_unpack<<<grid_for(m, 256), 256, 0, c.stream>>>(m, off, pos ? s_pos : nullptr, vel ? s_vel : nullptr,
                                                      D ? s_D : nullptr, D2 ? s_D2 : nullptr, id ? s_id : nullptr,
                                                      c.pA, c.pB, c.pC, (const float2 *) c.pE);
     c.launches++;
-    if (pos) CK(cudaMemcpyAsync(pos + 3 * off, s_pos, m * 12, cudaMemcpyDeviceToHost, c.stream));
-    if (vel) CK(cudaMemcpyAsync(vel + 3 * off, s_vel, m * 12, cudaMemcpyDeviceToHost, c.stream));
-    if (D) CK(cudaMemcpyAsync(D + 3 * off, s_D, m * 12, cudaMemcpyDeviceToHost, c.stream));
-    if (D2) CK(cudaMemcpyAsync(D2 + 3 * off, s_D2, m * 12, cudaMemcpyDeviceToHost, c.stream));
-    if (id) CK(cudaMemcpyAsync(id + off, s_id, m * 8, cudaMemcpyDeviceToHost, c.stream));
-    CK(cudaStreamSynchronize(c.stream));
+    CK(cudaEventRecord(unpacked, c.stream));
+    CK(cudaStreamWaitEvent(c.copy_stream, unpacked, 0));
+    if (pos) CK(cudaMemcpyAsync(pos + 3 * off, s_pos, m * 12, cudaMemcpyDeviceToHost, c.copy_stream));
+    if (vel) CK(cudaMemcpyAsync(vel + 3 * off, s_vel, m * 12, cudaMemcpyDeviceToHost, c.copy_stream));
+    if (D) CK(cudaMemcpyAsync(D + 3 * off, s_D, m * 12, cudaMemcpyDeviceToHost, c.copy_stream));
+    if (D2) CK(cudaMemcpyAsync(D2 + 3 * off, s_D2, m * 12, cudaMemcpyDeviceToHost, c.copy_stream));
+    if (id) CK(cudaMemcpyAsync(id + off, s_id, m * 8, cudaMemcpyDeviceToHost, c.copy_stream));
+    CK(cudaEventRecord(drained[b], c.copy_stream));
   }
-  CK(cudaFree(st));
+  CK(cudaStreamSynchronize(c.copy_stream));
+  CK(cudaStreamSynchronize(c.stream));
+  CK(cudaEventDestroy(unpacked));
 }
 
 // ------------------------------------------------------------------ cell keys, sort, permute

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--gb", type=int, default=8)
     ap.add_argument("--mode", type=int, default=0)
     ap.add_argument("--out", required=True)
+    ap.add_argument("--ic", action="store_true", help="generate the golden-fixture ICs on the ranks instead of stepping")
     a = ap.parse_args()
     import torch
     import mgpicola_b200 as mgp
@@ -29,6 +30,18 @@ def main():
     import test_gpu_parity as T
     rank, world, local = mdist.init_process_group("nccl")
     torch.cuda.set_device(local)
+    if a.ic:
+        g = dict(np.load(os.path.join(ROOT, "tests", "golden", "ic_lcdm.npz")))
+        N, box = int(g["N"]), float(g["box"])
+        nid = mdist.share_from_rank0(mgp.nccl_unique_id)
+        pm = mgp.PM(N, N, box, grid_bytes=a.gb, rank=rank, nranks=world, device=local, nccl_id=nid)
+        pm.ic_generate(g["power_by_k2"], seed=int(g["seed"]))
+        pm.init_particles(float(g["Di"]), float(g["Di2"]))
+        got = pm.download_particles()
+        np.savez(os.path.join(a.out, "rank%d.npz" % rank), p0=pm.local_p_start, npl=pm.local_np, **got)
+        mdist.barrier()
+        pm.close()
+        return
     N, box, om = a.nmesh, 100.0, 0.267
     pos, vel, D, D2 = T.make_particles(N, box, 77, clustered=True)
     ids = np.arange(N ** 3, dtype=np.uint64)

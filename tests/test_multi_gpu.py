@@ -19,10 +19,10 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-def _run(world, tmp, nmesh, steps, model, gb, mode):
+def _run(world, tmp, nmesh, steps, model, gb, mode, extra=()):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
            "--master-port", "29517", os.path.join(ROOT, "tests", "mgpu_worker.py"), "--nmesh", str(nmesh), "--steps", str(steps),
-           "--model", model, "--gb", str(gb), "--mode", str(mode), "--out", str(tmp)]
+           "--model", model, "--gb", str(gb), "--mode", str(mode), "--out", str(tmp)] + list(extra)
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     return [dict(np.load(os.path.join(tmp, "rank%d.npz" % k))) for k in range(world)]
@@ -81,3 +81,22 @@ def test_slab_decomposed_steps_match_oracle(require_gpu, tmp_path, world, model,
             rel = np.abs(p[good] - pks[it][0][good]) / (np.abs(pks[it][0][good]) + (box / N) ** 3)
             assert rel.max() < (1e-10 if gb == 8 else 1e-4)
         assert int(r["launches"]) > 20
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_distributed_ic_matches_reference(require_gpu, tmp_path, world):
+    """displacement_fields() on P slabs (transposed k-space, distributed FFTs, displacement halos) ==
+    the reference's single-task result (golden fixture), every rank holding its Lagrangian planes."""
+    if _ngpu() < world:
+        pytest.skip("needs %d GPUs" % world)
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "ic_lcdm.npz")))
+    N, box = int(g["N"]), float(g["box"])
+    ranks = _run(world, tmp_path, N, 0, "lcdm", 8, 0, extra=["--ic"])
+    ids = np.concatenate([r["id"] for r in ranks])
+    assert np.array_equal(ids, g["id"])                       # rank order == Lagrangian plane order, exact IDs
+    for nm, key in (("D", "ZA"), ("D2", "LPT")):
+        got = np.concatenate([r[nm] for r in ranks])
+        assert np.abs(got - g[key]).max() < 2e-6 * np.abs(g[key]).max(), nm
+    pos = np.concatenate([r["pos"] for r in ranks])
+    dp = np.abs(pos.astype(np.float64) - g["pos"])
+    assert np.minimum(dp, box - dp).max() < 1e-5 * box / N
