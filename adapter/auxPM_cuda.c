@@ -1,0 +1,359 @@
+/*
+ * auxPM_cuda.c -- the reference-side binding of libmgpicola_cuda.so.
+ *
+ * Compiled INSTEAD OF the reference's auxPM.c (+mg.h), 2LPT.c and compute_pofk.c, together with the
+ * reference's unmodified cosmo.c, power.c, read_param.c, vars.c, timer.c, msg.c, wrappers.c, jbd.c
+ * and a main.c that carries the small patch of adapter/main_c.patch (Kick / Drift particle loops
+ * and the host copy of the particles before Output).  It keeps the reference's function names and
+ * talks to the library through the reference's own globals (vars.h), so main()'s call sites are
+ * untouched.  Everything the reference evaluates per cell or per mode on the host is evaluated here
+ * ONCE per step with the reference's own functions and handed over as numbers:
+ *     coupling_function, mass2_of_a, screening_factor_potential  -> mgp_step_scalars
+ *     PowerSpec, mg_pofk_ratio, mg_sigma8_enhancement            -> mgp_ic_config.power_by_k2
+ *
+ * Particle residency: main.c builds its host array P exactly as before (main.c:257-309, from the
+ * ZA / LPT arrays this file fills from the GPU); the first GetDisplacements() moves P to the GPU,
+ * where it stays.  mgp_adapter_sync_host() brings it back before Output() reads P.
+ */
+#include "vars.h"
+#include "proto.h"
+#include "timer.h"
+#include "mgpicola.h"
+
+#include <limits.h>
+
+static mgp_ctx *g_ctx = NULL;
+static int g_host_is_newer = 1;      /* host P was (re)built: upload before the next force evaluation */
+static size_t g_host_capacity = 0;
+
+static void ck(int rc, const char *where) {
+  if (rc != MGP_OK) {
+    printf("%s: %s\n", where, mgp_last_error());
+    FatalError((char *) where);
+  }
+}
+
+/* ------------------------------------------------------------------ small host utilities that lived in the replaced files */
+
+void set_units(void) {                       /* 2LPT.c:35-42 */
+  UnitTime_in_s = UnitLength_in_cm / UnitVelocity_in_cm_per_s;
+  G = GRAVITY / pow(UnitLength_in_cm, 3) * UnitMass_in_g * pow(UnitTime_in_s, 2);
+  Hubble = HUBBLE * UnitTime_in_s;
+}
+
+#if (MEMORY_MODE || SINGLE_PRECISION)
+float periodic_wrap(float x) {               /* auxPM.c:649-655 */
+  while (x >= (float) Box) x -= (float) Box;
+  while (x < 0) x += (float) Box;
+  if (x == (float) Box) x = 0.0;
+  return x;
+}
+#else
+double periodic_wrap(double x) {
+  while (x >= Box) x -= Box;
+  while (x < 0) x += Box;
+  if (x == Box) x = 0.0;
+  return x;
+}
+#endif
+
+void FatalError(char *errmsg) {              /* auxPM.c:668-673 */
+  printf("Fatal Error: [%s]\n", errmsg);
+  fflush(stdout);
+  MPI_Abort(MPI_COMM_WORLD, 1);
+  exit(1);
+}
+
+size_t my_fwrite(void *ptr, size_t size, size_t nmemb, FILE *stream) {   /* auxPM.c:678-686 */
+  size_t nwritten = fwrite(ptr, size, nmemb, stream);
+  if (nwritten != nmemb) {
+    printf("\nERROR: I/O error (fwrite) on task=%d has occured.\n\n", ThisTask);
+    fflush(stdout);
+    FatalError((char *) "my_fwrite");
+  }
+  return nwritten;
+}
+
+/* particles never travel through MPI any more (the library migrates them over NCCL) */
+void create_MPI_type_for_Particles(MPI_Datatype *t) { *t = MPI_BYTE; }
+
+/* referenced by the ComputeFifthForce dispatcher that user_defined_functions.h compiles into cosmo.o;
+ * the library runs the solvers itself inside mgp_get_displacements */
+void ComputeFifthForce_PotentialScreening(void) {}
+void ComputeFifthForce_DensityScreening(void) {}
+void ComputeFifthForce_TimeDepGeffModels(void) {}
+void ComputeFifthForce_GradientScreening(void) {}
+
+/* ------------------------------------------------------------------ slab layout (2LPT.c:47-176) */
+
+static int model_id(void) {
+  if (!modified_gravity_active) return MGP_MODEL_NONE;
+#if defined(FOFRGRAVITY) || defined(MBETAMODEL)
+  return MGP_MODEL_FOFR;
+#elif defined(DGPGRAVITY)
+  return MGP_MODEL_DGP;
+#elif defined(BRANSDICKE)
+  return MGP_MODEL_GEFF;
+#else
+  return MGP_MODEL_NONE;
+#endif
+}
+
+void initialize_ffts(void) {
+  mgp_config cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.nmesh = Nmesh; cfg.nsample = Nsample; cfg.box = Box; cfg.buffer = Buffer; cfg.omega = Omega;
+  cfg.use_cola = UseCOLA; cfg.model = model_id(); cfg.include_screening = include_screening;
+  cfg.grid_bytes = (int) sizeof(float_kind);
+  cfg.deposit_mode = MGP_DEPOSIT_ATOMIC; cfg.sort_particles = 2;
+  {
+    const char *e = getenv("MGP_DEPOSIT_MODE");
+    if (e) cfg.deposit_mode = atoi(e);
+    e = getenv("MGP_SORT_INTERVAL");
+    if (e) cfg.sort_particles = atoi(e);
+  }
+#ifdef SCALEDEPENDENT
+  cfg.scale_dependent = 1;
+#endif
+  cfg.rank = ThisTask; cfg.nranks = NTask; cfg.device = 0;
+  {
+    const char *e = getenv("MGP_DEVICE");
+    if (e) cfg.device = atoi(e);
+  }
+  static char nccl_id[128];
+  if (NTask > 1) {
+    if (ThisTask == 0) ck(mgp_nccl_unique_id(nccl_id), "mgp_nccl_unique_id");
+    MPI_Bcast(nccl_id, 128, MPI_BYTE, 0, MPI_COMM_WORLD);
+    cfg.nccl_unique_id = nccl_id;
+  }
+  ck(mgp_create(&cfg, &g_ctx), "mgp_create");
+  int lnx, lx0, lnp, lp0;
+  uint64_t np;
+  ck(mgp_get_layout(g_ctx, &lnx, &lx0, &lnp, &lp0, &np), "mgp_get_layout");
+  Local_nx = lnx; Local_x_start = lx0;
+  alloc_slice = Nmesh * (Nmesh / 2 + 1);
+  alloc_local = Local_nx * alloc_slice;
+  last_slice = Local_nx * alloc_slice;
+  Total_size = alloc_local + alloc_slice;
+
+  Local_nx_table = my_malloc(sizeof(int) * NTask);
+  int lnx_i = (int) Local_nx;
+  MPI_Allgather(&lnx_i, 1, MPI_INT, Local_nx_table, 1, MPI_INT, MPI_COMM_WORLD);
+  LeftTask = ThisTask;
+  do { LeftTask--; if (LeftTask < 0) LeftTask = NTask - 1; } while (Local_nx_table[LeftTask] == 0);
+  RightTask = ThisTask;
+  do { RightTask++; if (RightTask >= NTask) RightTask = 0; } while (Local_nx_table[RightTask] == 0);
+  Slab_to_task = my_malloc(sizeof(int) * Nmesh);
+  int block = (Nmesh + NTask - 1) / NTask;
+  for (int i = 0; i < Nmesh; i++) Slab_to_task[i] = i / block < NTask ? i / block : NTask - 1;
+  if (ThisTask == 0) printf("\n[mgpicola-cuda] Local_nx = %d, Local_x_start = %d (library version %d)\n", lnx, lx0, mgp_version());
+}
+
+void initialize_parts(void) {
+  int lnx, lx0, lnp, lp0;
+  uint64_t np;
+  ck(mgp_get_layout(g_ctx, &lnx, &lx0, &lnp, &lp0, &np), "mgp_get_layout");
+  Local_np = lnp; Local_p_start = lp0;
+  NumPart = (unsigned int) (Local_np * Nsample * Nsample);
+  TotNumPart = ((unsigned long long) Nsample) * ((unsigned long long) Nsample) * ((unsigned long long) Nsample);
+  Local_np_table = my_malloc(sizeof(int) * NTask);
+  int lnp_i = (int) Local_np;
+  MPI_Allgather(&lnp_i, 1, MPI_INT, Local_np_table, 1, MPI_INT, MPI_COMM_WORLD);
+  NTaskWithN = 0;
+  for (int i = 0; i < NTask; i++) if (Local_np_table[i] > 0) NTaskWithN++;
+  Part_to_task = my_malloc(sizeof(int) * Nsample);
+  for (int i = 0; i < Nsample; i++) Part_to_task[i] = Slab_to_task[(int) ((double) (i * Nmesh) / (double) Nsample)];
+  g_host_capacity = (size_t) ceil(NumPart * Buffer);
+  if (ThisTask == 0) printf("Total number of particles = %llu\n\n", TotNumPart);
+}
+
+/* ------------------------------------------------------------------ initial conditions (2LPT.c:185-1520) */
+
+void displacement_fields(void) {
+  timer_start(_DisplacementFields);
+  const int h = Nmesh / 2;
+  const size_t nm = (size_t) 3 * h * h + 1;
+  double *power = my_malloc(sizeof(double) * nm);
+  double s8ratio2 = 1.0;
+  if (modified_gravity_active && input_pofk_is_for_lcdm) s8ratio2 = pow(mg_sigma8_enhancement(1.0), 2);   /* 2LPT.c:323-326 */
+  power[0] = 0.0;
+  for (size_t m = 1; m < nm; m++) {
+    const double kmag = 2 * PI / Box * sqrt((double) m);
+    double p = PowerSpec(kmag);                                               /* 2LPT.c:388 */
+    if (modified_gravity_active && input_pofk_is_for_lcdm) {                  /* 2LPT.c:395-406 */
+      p *= mg_pofk_ratio(kmag, 1.0);
+      if (!input_sigma8_is_for_lcdm) p /= s8ratio2;
+    }
+    power[m] = p;
+  }
+  mgp_ic_config ic;
+  memset(&ic, 0, sizeof(ic));
+  ic.seed = (unsigned) Seed; ic.sphere_mode = SphereMode;
+  ic.amplitude_fixed = amplitude_fixed_initial_condition; ic.inverted = inverted_initial_condition;
+  ic.power_by_k2 = power; ic.n_power = nm; ic.seedtable = NULL;
+  ck(mgp_ic_generate(g_ctx, &ic), "mgp_ic_generate");
+  my_free(power);
+#ifndef SCALEDEPENDENT
+  /* main.c:257-309 builds P from ZA / LPT on the host */
+  float *za = my_malloc((size_t) NumPart * 3 * sizeof(float)), *lpt = my_malloc((size_t) NumPart * 3 * sizeof(float));
+  ck(mgp_ic_download(g_ctx, za, lpt), "mgp_ic_download");
+  for (int a = 0; a < 3; a++) {
+    ZA[a] = my_malloc(NumPart * sizeof(float));
+    LPT[a] = my_malloc(NumPart * sizeof(float));
+    for (unsigned int q = 0; q < NumPart; q++) { ZA[a][q] = za[3 * (size_t) q + a]; LPT[a][q] = lpt[3 * (size_t) q + a]; }
+  }
+  my_free(za); my_free(lpt);
+#endif
+  g_host_is_newer = 1;
+  timer_stop(_DisplacementFields);
+}
+
+/* ------------------------------------------------------------------ host <-> device particle copies */
+
+static void upload_host_particles(void) {
+  const size_t n = NumPart;
+  float *pos = my_malloc(n * 12), *vel = my_malloc(n * 12), *d1 = my_malloc(n * 12), *d2 = my_malloc(n * 12);
+  uint64_t *id = my_malloc(n * 8);
+  for (size_t i = 0; i < n; i++) {
+    for (int a = 0; a < 3; a++) {
+      pos[3 * i + a] = P[i].Pos[a]; vel[3 * i + a] = P[i].Vel[a]; d1[3 * i + a] = P[i].D[a]; d2[3 * i + a] = P[i].D2[a];
+    }
+#ifdef PARTICLE_ID
+    id[i] = P[i].ID;
+#else
+    id[i] = ((uint64_t) Local_p_start * Nsample * Nsample) + i;
+#endif
+  }
+  ck(mgp_upload_particles(g_ctx, n, pos, vel, d1, d2, id), "mgp_upload_particles");
+  my_free(pos); my_free(vel); my_free(d1); my_free(d2); my_free(id);
+  g_host_is_newer = 0;
+}
+
+/* called (through the main.c patch) before Output() reads P */
+void mgp_adapter_sync_host(void) {
+  int lnx, lx0, lnp, lp0;
+  uint64_t np;
+  if (g_host_is_newer) return;
+  ck(mgp_get_layout(g_ctx, &lnx, &lx0, &lnp, &lp0, &np), "mgp_get_layout");
+  if (np > g_host_capacity) FatalError((char *) "mgp_adapter_sync_host: more particles than the host buffer holds; increase Buffer");
+  const size_t n = (size_t) np;
+  float *pos = my_malloc(n * 12), *vel = my_malloc(n * 12), *d1 = my_malloc(n * 12), *d2 = my_malloc(n * 12);
+  uint64_t *id = my_malloc(n * 8);
+  ck(mgp_download_particles(g_ctx, pos, vel, d1, d2, id), "mgp_download_particles");
+  for (size_t i = 0; i < n; i++) {
+    for (int a = 0; a < 3; a++) {
+      P[i].Pos[a] = pos[3 * i + a]; P[i].Vel[a] = vel[3 * i + a]; P[i].D[a] = d1[3 * i + a]; P[i].D2[a] = d2[3 * i + a];
+    }
+#ifdef PARTICLE_ID
+    P[i].ID = id[i];
+#endif
+  }
+  NumPart = (unsigned int) n;
+  my_free(pos); my_free(vel); my_free(d1); my_free(d2); my_free(id);
+}
+
+/* ------------------------------------------------------------------ P(k) file (compute_pofk.c:48-64, 239-261) */
+
+#ifdef COMPUTE_POFK
+static double k_of_bin(int i, double kmin, double kmax, int nbins, int bintype) {
+  if (bintype == 0) return (kmin + (kmax - kmin) / (double) nbins * i) * 2.0 * M_PI / Box;
+  return exp(log(kmin) + log(kmax / kmin) / (double) nbins * i) * 2.0 * M_PI / Box;
+}
+
+static void write_pofk_file(double a, const char *label, int nbins, const double *pofk, const double *kmean, const double *nmodes) {
+  /* the sanitised binning parameters, as adjust_pofk_parameters (compute_pofk.c:758-805) leaves them */
+  int bintype = pofk_bintype;
+  double kmin = pofk_kmin * Box / (2.0 * M_PI), kmax = pofk_kmax * Box / (2.0 * M_PI);
+  if (!(bintype == 0 || bintype == 1)) bintype = 0;
+  if (kmax <= kmin) { kmin = bintype == 0 ? 0.0 : 1.0; kmax = (double) Nmesh; }
+  if (kmin < 0.0) kmin = bintype == 0 ? 0.0 : 1.0;
+  if (bintype == 1 && kmin == 0.0) kmin = 1.0;
+  if (kmax > sqrt(3.0) * (double) Nmesh) kmax = (double) Nmesh;
+  const double znow = 1.0 / a - 1.0;
+  if (ThisTask != 0) return;
+  char filename[1000];
+  const int zint = (int) znow, zfrac = (int) ((znow - zint) * 1000);
+  sprintf(filename, "%s/pofk_%s_z%d.%03d_%s.txt", OutputDir, FileBase, zint, zfrac, label);
+  printf("Writing power-spectrum to file: [%s]\n", filename);
+  FILE *fp = fopen(filename, "w");
+  fprintf(fp, "#  k_bin (h/Mpc)        P(k) (Mpc/h)^3     k_mean_bin (h/Mpc)     Delta = k^3P(k)/2pi^2\n");
+  for (int i = 1; i < nbins; i++) {
+    if (nmodes[i] > 0) {
+      const double kb = k_of_bin(i, kmin, kmax, nbins, bintype);
+      fprintf(fp, "%10.5f   %10.5f   %10.5f   %10.5f\n", kb, pofk[i], kmean[i], pofk[i] * kb * kb * kb / 2.0 / M_PI / M_PI);
+    }
+  }
+  fclose(fp);
+}
+#endif
+
+void compute_RSD_powerspectrum(double A, int dDdy_set) {
+  (void) A; (void) dDdy_set;
+  if (ThisTask == 0) printf("[mgpicola-cuda] RSD multipoles are not computed by the CUDA library yet (pofk_compute_rsd_pofk ignored)\n");
+}
+
+/* ------------------------------------------------------------------ the force path (auxPM.c:37-103) */
+
+void GetDisplacements(void) {
+  if (g_host_is_newer) upload_host_particles();
+  mgp_step_scalars s;
+  memset(&s, 0, sizeof(s));
+  s.a = aexp_global;
+  s.geff = 1.0;
+  if (modified_gravity_active) {
+#if defined(FOFRGRAVITY) || defined(MBETAMODEL)
+    /* Phi_crit(a): screening_factor_potential returns |Phi_crit / Phi_N| for deeply screened cells (udf:725-750) */
+    const double big = -1e30;
+    s.phi_crit = include_screening ? screening_factor_potential(aexp_global, big) * fabs(big) : 0.0;
+    s.coupling = coupling_function(aexp_global);                                                   /* mg.h:79 */
+    s.massterm2 = aexp_global * aexp_global * mass2_of_a(aexp_global) / pow((2.0 * PI) * INVERSE_H0_MPCH / Box, 2);   /* mg.h:80 */
+#elif defined(DGPGRAVITY)
+    s.coupling = coupling_function(aexp_global);
+    s.dgp_fac0 = 8.0 / 9.0 * Omega * pow(rcH0_DGP / beta_DGP(aexp_global), 2);                     /* udf:762 */
+    s.rsmooth = Rsmooth_global;
+#elif defined(BRANSDICKE)
+    s.geff = GeffoverG(aexp_global, 0.0);
+#endif
+  }
+#ifdef COMPUTE_POFK
+  s.compute_pofk = pofk_compute_every_step;
+  static int pofk_configured = 0;
+  if (!pofk_configured) {
+    mgp_pofk_config pc = {pofk_nbins, pofk_bintype, pofk_subtract_shotnoise, pofk_kmin, pofk_kmax};
+    ck(mgp_set_pofk_config(g_ctx, &pc), "mgp_set_pofk_config");
+    pofk_configured = 1;
+  }
+#endif
+  timer_start(_PtoMesh);
+  ck(mgp_get_displacements(g_ctx, &s, sumDxyz), "mgp_get_displacements");
+  timer_stop(_PtoMesh);
+#ifdef COMPUTE_POFK
+  if (pofk_compute_every_step) {
+    const int nb = mgp_pofk_nbins(g_ctx);
+    double *p = my_malloc(sizeof(double) * nb), *k = my_malloc(sizeof(double) * nb), *n = my_malloc(sizeof(double) * nb);
+    ck(mgp_get_step_power_spectrum(g_ctx, p, k, n), "mgp_get_step_power_spectrum");
+    write_pofk_file(aexp_global, "CDM", nb, p, k, n);
+    my_free(p); my_free(k); my_free(n);
+  }
+#endif
+  /* main.c frees Disp[] after the kick (main.c:551, 574): hand it something to free */
+  for (int j = 0; j < 3; j++) Disp[j] = my_malloc(sizeof(float));
+  int lnx, lx0, lnp, lp0;
+  uint64_t np;
+  ck(mgp_get_layout(g_ctx, &lnx, &lx0, &lnp, &lp0, &np), "mgp_get_layout");
+  NumPart = (unsigned int) np;                         /* read by main.c:452, 1076 */
+}
+
+/* the particle loops of Kick (main.c:707-739) and Drift (main.c:762-783); the scalar part stays in main.c */
+void mgp_adapter_kick(double A, double dda, double ddDddy, double ddD2ddy) {
+  ck(mgp_kick(g_ctx, A, dda, ddDddy, ddD2ddy, sumDxyz, sumxyz), "mgp_kick");
+}
+
+void mgp_adapter_drift(double dyyy, double deltaD, double deltaD2) {
+  ck(mgp_drift(g_ctx, dyyy, deltaD, deltaD2, sumxyz), "mgp_drift");
+}
+
+void mgp_adapter_finish(void) {
+  if (g_ctx) mgp_destroy(g_ctx);
+  g_ctx = NULL;
+}

@@ -148,6 +148,10 @@ typedef struct mgp_ic_config {
 /* displacement_fields(): delta_k, the six displacement gradients, the 2LPT source, and the ZA / 2LPT
  * displacements read out at the Lagrangian points of this rank's particle planes (13 FFTs) */
 int mgp_ic_generate(mgp_ctx *ctx, const mgp_ic_config *ic);
+/* ZA[3][NumPart] / LPT[3][NumPart] of displacement_fields() (vars.h:265-270) for this rank's Lagrangian
+ * particles, mean-subtracted, as [n][3]; valid between mgp_ic_generate and mgp_init_particles.  For a
+ * driver that keeps main.c's own initialisation loop (main.c:257-309) on the host. */
+int mgp_ic_download(mgp_ctx *ctx, float *za, float *lpt);
 /* main.c:257-309: IDs, D = ZA, D2 = LPT, Vel (0 for COLA), Pos = wrap(q + D Di + D2 Di2) */
 int mgp_init_particles(mgp_ctx *ctx, double Di, double Di2, double dDdy, double dD2dy);
 /* the seed table of 2LPT.c:259-271 (Nmesh*Nmesh unsigned) and the n-th draw of ranlxd1(seed): test hooks

@@ -76,6 +76,7 @@ def load_library(path=None):
     L.mgp_download_disp.argtypes = [C.c_void_p, C.c_void_p]
     L.mgp_upload_disp.argtypes = [C.c_void_p, C.c_void_p]
     L.mgp_ic_generate.argtypes = [C.c_void_p, C.POINTER(IcConfig)]
+    L.mgp_ic_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.mgp_init_particles.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]
     L.mgp_seedtable.argtypes = [C.c_uint, C.c_int, C.c_void_p]
     L.mgp_ranlxd1_draw.argtypes = [C.c_ulong, C.c_long]
@@ -228,6 +229,12 @@ class PM:
         st = None if seedtable is None else np.ascontiguousarray(seedtable, dtype=np.uint32)
         ic = IcConfig(seed, sphere_mode, amplitude_fixed, inverted, pw.ctypes.data, pw.size, None if st is None else st.ctypes.data)
         self._ck(self.L.mgp_ic_generate(self.ctx, C.byref(ic)))
+
+    def ic_download(self):
+        n = self.local_np * self.Ns * self.Ns
+        za, lpt = np.empty((n, 3), np.float32), np.empty((n, 3), np.float32)
+        self._ck(self.L.mgp_ic_download(self.ctx, _ptr(za), _ptr(lpt)))
+        return za, lpt
 
     def init_particles(self, Di, Di2, dDdy=0.0, dD2dy=0.0):
         self._ck(self.L.mgp_init_particles(self.ctx, Di, Di2, dDdy, dD2dy))

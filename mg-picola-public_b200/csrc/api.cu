@@ -296,6 +296,26 @@ int mgp_ic_generate(mgp_ctx *ctx, const mgp_ic_config *ic) {
   API_END
 }
 
+int mgp_ic_download(mgp_ctx *ctx, float *za, float *lpt) {
+  API_BEGIN
+  CTX(ctx);
+  REQUIRE(c.ic_ready, MGP_ERR_STATE, "mgp_ic_download: call mgp_ic_generate first");
+  const size_t n = (size_t) c.npl * c.cfg.nsample * c.cfg.nsample;
+  std::vector<float> tmp(n);
+  for (int f = 0; f < 2; f++) {
+    float *dst = f == 0 ? za : lpt;
+    if (!dst) continue;
+    const float *src = f == 0 ? c.disp : (const float *) c.pA2;
+    for (int a = 0; a < 3; a++) {
+      CK(cudaMemcpyAsync(tmp.data(), src + (size_t) a * c.cap, n * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+      CK(cudaStreamSynchronize(c.stream));
+      const double m = c.ic_means[3 * f + a];
+      for (size_t i = 0; i < n; i++) dst[3 * i + a] = (float) ((double) tmp[i] - m);   // ZA -= sumdis (2LPT.c:1501-1508)
+    }
+  }
+  API_END
+}
+
 int mgp_init_particles(mgp_ctx *ctx, double Di, double Di2, double dDdy, double dD2dy) {
   API_BEGIN
   CTX(ctx);
