@@ -288,8 +288,9 @@ static void deposit_t(Ctx &c, int gid) {
     c.launches++;
     return;
   }
+  static const int agg = getenv("MGP_AGG") ? atoi(getenv("MGP_AGG")) : 1;     // developer knob
   k_deposit_atomic<T><<<grid_for(n, 256), 256, 0, c.stream>>>(n, c.pA, grid, c.N, c.NZ, c.nx, c.x0, single, scale, W,
-                                                              1);
+                                                              agg);
   c.launches++;
 }
 
