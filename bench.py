@@ -273,7 +273,7 @@ def run_ours(args):
 
 # ------------------------------------------------------------------ reference arm (CPU)
 
-def write_paramfile(workdir, nmesh, box, model, nsteps):
+def write_paramfile(workdir, nmesh, box, model, nsteps, lcdm_growth=1, extra=""):
     """Parameter file for the reference build in oracle/_ref (tags: read_param.c:107-445,
     user_defined_functions.h:227-406)."""
     os.makedirs(os.path.join(workdir, "output"), exist_ok=True)
@@ -286,7 +286,7 @@ def write_paramfile(workdir, nmesh, box, model, nsteps):
     mg = {"fofr": "modified_gravity_active 1\nfofr0 %g\nnfofr %g\ninclude_screening 1\n" % (FOFR0, NFOFR),
           "lcdm": "modified_gravity_active 0\nfofr0 %g\nnfofr %g\ninclude_screening 0\n" % (FOFR0, NFOFR),
           "dgp": "modified_gravity_active 1\nrcH0_DGP %g\nRsmooth %g\ninclude_screening 1\n" % (RCH0, RSMOOTH)}[model]
-    txt = mg + """use_lcdm_growth_factors 1
+    txt = mg + extra + """use_lcdm_growth_factors %d
 input_pofk_is_for_lcdm 1
 input_sigma8_is_for_lcdm 1
 inverted_initial_condition 0
@@ -323,7 +323,7 @@ pofk_bintype 1
 pofk_subtract_shotnoise 1
 pofk_kmin 0.03
 pofk_kmax 2.0
-""" % (workdir, workdir, nmesh, nmesh, box, Z_INIT, workdir, OMEGA, SIGMA8)
+""" % (lcdm_growth, workdir, workdir, nmesh, nmesh, box, Z_INIT, workdir, OMEGA, SIGMA8)
     p = os.path.join(workdir, "param.txt")
     open(p, "w").write(txt)
     return p

@@ -57,7 +57,17 @@ enum mgp_grid_id {
   MGP_GRID_FORCE_Y = 2,      /* N12 / FN12 */
   MGP_GRID_FORCE_Z = 3,      /* N13 / FN13 */
   MGP_GRID_MG_ONE = 4,       /* mgarray_one (vars.h:181-186) */
-  MGP_GRID_MG_TWO = 5        /* mgarray_two */
+  MGP_GRID_MG_TWO = 5,       /* mgarray_two */
+  MGP_GRID_SD_DELTA1 = 6,    /* cdelta_cdm  (vars.h:272; scale_dependent only, k-space) */
+  MGP_GRID_SD_DELTA2 = 7     /* cdelta_cdm2 (vars.h:273) */
+};
+
+/* FIELD_* of proto.h:155-158 */
+enum mgp_sd_field {
+  MGP_FIELD_D = 0,           /* D(k, A)                         -> P.D   / P.D2    */
+  MGP_FIELD_DDDY = 1,        /* dD/dy(k, A)                     -> P.dDdy / P.dD2dy */
+  MGP_FIELD_DDDDDY = 2,      /* d^2D/dy^2(k, A)                 -> P.D   / P.D2    (2LPT.c:1821) */
+  MGP_FIELD_DELTAD = 3       /* D(k, AFF) - D(k, A)             -> P.dDdy / P.dD2dy (2LPT.c:1822) */
 };
 
 typedef struct mgp_config {
@@ -159,6 +169,25 @@ int mgp_init_particles(mgp_ctx *ctx, double Di, double Di2, double dDdy, double 
 int mgp_seedtable(unsigned seed, int nmesh, unsigned *out);
 double mgp_ranlxd1_draw(unsigned long seed, long n);
 
+/* ---- scale-dependent growth (-DSCALEDEPENDENT; 2LPT.c:1539-2005) ---- */
+/* assign_displacment_field_to_particles(A, AF, AFF, fieldtype, LPTorder) (2LPT.c:1758): builds
+ * i k / k^2 * growth(|k|) * delta^(order)_k, transforms it back, reads it out at the Lagrangian lattice, removes
+ * the mean and stores it in the particle that was born there (fetched from the birth rank when it has migrated).
+ * growth_by_k2[m], m = |d|^2 in [0, 3 (Nmesh/2)^2], is the factor from_cdisp_store_to_ZA evaluates per mode
+ * WITHOUT its normfactor (2LPT.c:1611-1614): growth_X_scaledependent(k, A), or the difference for
+ * MGP_FIELD_DELTAD, at k = 2 pi sqrt(m) / Box; the -3/7 / Nmesh^3 of order 2 is applied by the library.
+ * The four per-particle fields stay valid until the next mgp_move_particles / mgp_get_displacements.
+ * Before mgp_init_particles the call acts on the Lagrangian particles of this rank (main.c:231-251). */
+int mgp_assign_displacement_field(mgp_ctx *ctx, int fieldtype, int lpt_order, const double *growth_by_k2, size_t n);
+/* both orders in one pass (only D + D2 and dDdy + dD2dy are ever used: main.c:712, 767, 962): the sum goes
+ * to the first-order slot, the second-order slot reads as zero.  6 instead of 12 inverse FFTs per step;
+ * differs from two separate calls by one float rounding. */
+int mgp_assign_displacement_fields_merged(mgp_ctx *ctx, int fieldtype, const double *growth1_by_k2,
+                                          const double *growth2_by_k2, size_t n);
+/* P.dDdy / P.dD2dy as [n][3] (P.D / P.D2 travel with mgp_upload/download_particles); any pointer may be NULL */
+int mgp_download_sd_fields(mgp_ctx *ctx, float *dDdy, float *dD2dy);
+int mgp_upload_sd_fields(mgp_ctx *ctx, const float *dDdy, const float *dD2dy);
+
 /* ---- the per-step force path ---- */
 /* MoveParticles (auxPM.c:108-275): slab ownership + migration; also (re)sorts by cell */
 int mgp_move_particles(mgp_ctx *ctx);
@@ -174,11 +203,12 @@ int mgp_mtoparticles(mgp_ctx *ctx, double sumDxyz[3]);
 int mgp_get_displacements(mgp_ctx *ctx, const mgp_step_scalars *s, double sumDxyz[3]);
 
 /* Kick particle loop (main.c:707-739).  dda = Sphi(...), ddDddy/ddD2ddy = growth_ddDddy(A),
- * growth_ddD2ddy(A) stay on the host.  sumDxyz in (0 on the second kick of an output step,
+ * growth_ddD2ddy(A) stay on the host (ignored when scale_dependent: P.D / P.D2 already hold the weighted fields).  sumDxyz in (0 on the second kick of an output step,
  * main.c:566-569); sumxyz out (mean velocity, / TotNumPart). */
 int mgp_kick(mgp_ctx *ctx, double A, double dda, double ddDddy, double ddD2ddy,
              const double sumDxyz[3], double sumxyz[3]);
-/* Drift particle loop (main.c:762-783).  dyyy = Sq(...), deltaD = growth_D(AFF)-Di, ... */
+/* Drift particle loop (main.c:762-783).  dyyy = Sq(...), deltaD = growth_D(AFF)-Di, ... (deltaD, deltaD2 ignored
+ * when scale_dependent: P.dDdy / P.dD2dy hold the per-particle increments) */
 int mgp_drift(mgp_ctx *ctx, double dyyy, double deltaD, double deltaD2, const double sumxyz[3]);
 
 /* ---- P(k) (compute_pofk.c:71-271) ---- */

@@ -22,7 +22,8 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mgpicola.h")
 
 MODEL_NONE, MODEL_FOFR, MODEL_DGP, MODEL_GEFF = 0, 1, 2, 3
 DEPOSIT_ATOMIC, DEPOSIT_TILE, DEPOSIT_DETERMINISTIC = 0, 1, 2
-GRID_DENSITY, GRID_FORCE_X, GRID_FORCE_Y, GRID_FORCE_Z, GRID_MG_ONE, GRID_MG_TWO = range(6)
+GRID_DENSITY, GRID_FORCE_X, GRID_FORCE_Y, GRID_FORCE_Z, GRID_MG_ONE, GRID_MG_TWO, GRID_SD_DELTA1, GRID_SD_DELTA2 = range(8)
+FIELD_D, FIELD_dDdy, FIELD_ddDddy, FIELD_deltaD = range(4)     # proto.h:155-158
 
 
 class MgpError(RuntimeError):
@@ -82,6 +83,10 @@ def load_library(path=None):
     L.mgp_ranlxd1_draw.argtypes = [C.c_ulong, C.c_long]
     L.mgp_ranlxd1_draw.restype = C.c_double
     L.mgp_move_particles.argtypes = [C.c_void_p]
+    L.mgp_assign_displacement_field.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+    L.mgp_assign_displacement_fields_merged.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
+    L.mgp_download_sd_fields.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mgp_upload_sd_fields.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.mgp_ptomesh.argtypes = [C.c_void_p, C.POINTER(StepScalars)]
     L.mgp_compute_fifth_force.argtypes = [C.c_void_p, C.POINTER(StepScalars)]
     L.mgp_forces.argtypes = [C.c_void_p]
@@ -243,6 +248,36 @@ class PM:
         d = _f32(disp)
         assert d.shape == (self.numpart, 3)
         self._ck(self.L.mgp_upload_disp(self.ctx, _ptr(d)))
+
+    # ---- scale-dependent growth (2LPT.c:1758) ----
+    def assign_displacment_field_to_particles(self, fieldtype, lpt_order, growth_by_k2):
+        """Same name (sic) and meaning as the reference's function; the (A, AF, AFF) dependence has been
+        evaluated by the caller into growth_by_k2[m], m = |d|^2."""
+        g = np.ascontiguousarray(growth_by_k2, dtype=np.float64)
+        self._ck(self.L.mgp_assign_displacement_field(self.ctx, fieldtype, lpt_order, _ptr(g), g.size))
+
+    def assign_displacement_fields_merged(self, fieldtype, growth1_by_k2, growth2_by_k2):
+        g1 = np.ascontiguousarray(growth1_by_k2, dtype=np.float64)
+        g2 = np.ascontiguousarray(growth2_by_k2, dtype=np.float64)
+        assert g1.size == g2.size
+        self._ck(self.L.mgp_assign_displacement_fields_merged(self.ctx, fieldtype, _ptr(g1), _ptr(g2), g1.size))
+
+    def download_sd_fields(self):
+        n = self.numpart
+        a, b = np.empty((n, 3), np.float32), np.empty((n, 3), np.float32)
+        self._ck(self.L.mgp_download_sd_fields(self.ctx, _ptr(a), _ptr(b)))
+        return a, b
+
+    def upload_sd_fields(self, dDdy=None, dD2dy=None):
+        a, b = _f32(dDdy), _f32(dD2dy)
+        self._ck(self.L.mgp_upload_sd_fields(self.ctx, _ptr(a), _ptr(b)))
+
+    def upload_grid_k(self, gid, arr_k):
+        """k-space array [N][N][N/2+1] complex -> the padded slab layout (single rank)."""
+        N = self.N
+        full = np.zeros((self.local_nx + 1, N, N // 2 + 1), self.cdtype)
+        full[: self.local_nx] = arr_k
+        self.upload_grid(gid, full.reshape(-1).view(self.gdtype))
 
     # ---- the reference's per-step functions ----
     @staticmethod

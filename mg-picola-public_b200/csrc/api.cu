@@ -11,7 +11,7 @@ static thread_local std::string g_last_error;
 void set_last_error(const std::string &m) { g_last_error = m; }
 
 static const char *kPhaseNames[PH_COUNT] = {"MoveParticles", "PtoMesh", "FFT", "ComputeFifthForce", "Forces",
-                                            "MtoParticles", "Kick", "Drift", "Pofk", "Sort", "Comm"};
+                                            "MtoParticles", "Kick", "Drift", "Pofk", "Sort", "Comm", "SDField", "SDAssign"};
 
 static bool needs_mg_arrays(const Ctx &c) { return c.cfg.model == MGP_MODEL_FOFR || c.cfg.model == MGP_MODEL_DGP; }
 
@@ -80,6 +80,7 @@ static Ctx *create(const mgp_config *cfg) {
     }
     CK(cudaMalloc(&c.halo_recv, c.plane_bytes()));
     particles_alloc(c);
+    if (cfg->scale_dependent) sd_alloc(c);
     if (c.P > 1) {
       ncclUniqueId id;
       memcpy(&id, cfg->nccl_unique_id, sizeof(id));
@@ -101,6 +102,7 @@ static void destroy(Ctx *cp) {
   cudaStreamSynchronize(c.stream);
   fft_teardown(c);
   particles_free(c);
+  sd_free(c);
   cudaFree(c.grid[0]); cudaFree(c.force_block); cudaFree(c.grid[4]); cudaFree(c.grid[5]); cudaFree(c.halo_recv);
   cudaFree(c.sd_delta[0]); cudaFree(c.sd_delta[1]);
   cudaFree(c.mig_dev); if (c.mig_host) cudaFreeHost(c.mig_host);
@@ -222,6 +224,13 @@ using namespace mgp;
   Ctx &c = *reinterpret_cast<Ctx *>(ctx);                                \
   CK(cudaSetDevice(c.cfg.device));
 
+static void *grid_ptr(Ctx &c, int id) {
+  if (id >= 0 && id < 6) return c.grid[id];
+  if (id == MGP_GRID_SD_DELTA1) return c.sd_delta[0];
+  if (id == MGP_GRID_SD_DELTA2) return c.sd_delta[1];
+  return nullptr;
+}
+
 extern "C" {
 
 const char *mgp_last_error(void) { return g_last_error.c_str(); }
@@ -266,13 +275,23 @@ int mgp_upload_particles(mgp_ctx *ctx, uint64_t n, const float *pos, const float
   API_BEGIN
   CTX(ctx);
   particles_upload(c, n, pos, vel, D, D2, id);
+  if (c.cfg.scale_dependent) {            // P.D / P.D2 live in the per-step field arrays (sd.cu)
+    if (D) sd_copy_field(c, 0, const_cast<float *>(D), false);
+    if (D2) sd_copy_field(c, 1, const_cast<float *>(D2), false);
+  }
   API_END
 }
 
 int mgp_download_particles(mgp_ctx *ctx, float *pos, float *vel, float *D, float *D2, uint64_t *id) {
   API_BEGIN
   CTX(ctx);
-  particles_download(c, pos, vel, D, D2, id);
+  if (c.cfg.scale_dependent) {
+    particles_download(c, pos, vel, nullptr, nullptr, id);
+    if (D) sd_copy_field(c, 0, D, true);
+    if (D2) sd_copy_field(c, 1, D2, true);
+  } else {
+    particles_download(c, pos, vel, D, D2, id);
+  }
   API_END
 }
 
@@ -319,7 +338,8 @@ int mgp_ic_download(mgp_ctx *ctx, float *za, float *lpt) {
 int mgp_init_particles(mgp_ctx *ctx, double Di, double Di2, double dDdy, double dD2dy) {
   API_BEGIN
   CTX(ctx);
-  ic_init_particles(c, Di, Di2, dDdy, dD2dy);
+  if (c.cfg.scale_dependent) sd_init_particles(c);      // main.c:296-300: the fields already carry their growth factors
+  else ic_init_particles(c, Di, Di2, dDdy, dD2dy);
   API_END
 }
 
@@ -402,7 +422,13 @@ int mgp_kick(mgp_ctx *ctx, double A, double dda, double ddDddy, double ddD2ddy, 
   API_BEGIN
   CTX(ctx);
   REQUIRE(sumDxyz && sumxyz, MGP_ERR_INVALID, "mgp_kick: NULL argument");
-  particles_kick(c, A, dda, ddDddy, ddD2ddy, sumDxyz, sumxyz);
+  if (c.cfg.scale_dependent) {
+    PhaseTimer t(c, PH_KICK);
+    REQUIRE(c.have_disp, MGP_ERR_STATE, "mgp_kick: no displacements; call mgp_get_displacements first");
+    sd_kick(c, A, dda, sumDxyz, sumxyz);
+  } else {
+    particles_kick(c, A, dda, ddDddy, ddD2ddy, sumDxyz, sumxyz);
+  }
   API_END
 }
 
@@ -410,8 +436,48 @@ int mgp_drift(mgp_ctx *ctx, double dyyy, double deltaD, double deltaD2, const do
   API_BEGIN
   CTX(ctx);
   REQUIRE(sumxyz != nullptr, MGP_ERR_INVALID, "mgp_drift: NULL argument");
-  particles_drift(c, dyyy, deltaD, deltaD2, sumxyz);
+  if (c.cfg.scale_dependent) {
+    { PhaseTimer t(c, PH_DRIFT); sd_drift(c, dyyy, sumxyz); }
+    particles_after_drift(c);
+  } else {
+    particles_drift(c, dyyy, deltaD, deltaD2, sumxyz);
+  }
   CK(cudaStreamSynchronize(c.stream));
+  API_END
+}
+
+int mgp_assign_displacement_field(mgp_ctx *ctx, int fieldtype, int lpt_order, const double *growth_by_k2, size_t n) {
+  API_BEGIN
+  CTX(ctx);
+  REQUIRE(lpt_order == 1 || lpt_order == 2, MGP_ERR_INVALID, "mgp_assign_displacement_field: LPT order must be 1 or 2");
+  sd_assign(c, fieldtype, lpt_order, growth_by_k2, nullptr, n);
+  CK(cudaStreamSynchronize(c.stream));
+  API_END
+}
+
+int mgp_assign_displacement_fields_merged(mgp_ctx *ctx, int fieldtype, const double *g1, const double *g2, size_t n) {
+  API_BEGIN
+  CTX(ctx);
+  sd_assign(c, fieldtype, 0, g1, g2, n);
+  CK(cudaStreamSynchronize(c.stream));
+  API_END
+}
+
+int mgp_download_sd_fields(mgp_ctx *ctx, float *dDdy, float *dD2dy) {
+  API_BEGIN
+  CTX(ctx);
+  REQUIRE(c.cfg.scale_dependent, MGP_ERR_STATE, "mgp_download_sd_fields: scale_dependent = 0");
+  if (dDdy) sd_copy_field(c, 2, dDdy, true);
+  if (dD2dy) sd_copy_field(c, 3, dD2dy, true);
+  API_END
+}
+
+int mgp_upload_sd_fields(mgp_ctx *ctx, const float *dDdy, const float *dD2dy) {
+  API_BEGIN
+  CTX(ctx);
+  REQUIRE(c.cfg.scale_dependent, MGP_ERR_STATE, "mgp_upload_sd_fields: scale_dependent = 0");
+  if (dDdy) sd_copy_field(c, 2, const_cast<float *>(dDdy), false);
+  if (dD2dy) sd_copy_field(c, 3, const_cast<float *>(dD2dy), false);
   API_END
 }
 
@@ -457,8 +523,8 @@ size_t mgp_grid_local_values(mgp_ctx *ctx) {
 int mgp_download_grid(mgp_ctx *ctx, int grid_id, void *host) {
   API_BEGIN
   CTX(ctx);
-  REQUIRE(grid_id >= 0 && grid_id < 6 && c.grid[grid_id], MGP_ERR_INVALID, "mgp_download_grid: grid not allocated");
-  CK(cudaMemcpyAsync(host, c.grid[grid_id], c.grid_bytes(), cudaMemcpyDeviceToHost, c.stream));
+  REQUIRE(grid_ptr(c, grid_id), MGP_ERR_INVALID, "mgp_download_grid: grid not allocated");
+  CK(cudaMemcpyAsync(host, grid_ptr(c, grid_id), c.grid_bytes(), cudaMemcpyDeviceToHost, c.stream));
   CK(cudaStreamSynchronize(c.stream));
   API_END
 }
@@ -466,9 +532,10 @@ int mgp_download_grid(mgp_ctx *ctx, int grid_id, void *host) {
 int mgp_upload_grid(mgp_ctx *ctx, int grid_id, const void *host) {
   API_BEGIN
   CTX(ctx);
-  REQUIRE(grid_id >= 0 && grid_id < 6 && c.grid[grid_id], MGP_ERR_INVALID, "mgp_upload_grid: grid not allocated");
-  CK(cudaMemcpyAsync(c.grid[grid_id], host, c.grid_bytes(), cudaMemcpyHostToDevice, c.stream));
+  REQUIRE(grid_ptr(c, grid_id), MGP_ERR_INVALID, "mgp_upload_grid: grid not allocated");
+  CK(cudaMemcpyAsync(grid_ptr(c, grid_id), host, c.grid_bytes(), cudaMemcpyHostToDevice, c.stream));
   CK(cudaStreamSynchronize(c.stream));
+  if (grid_id == MGP_GRID_SD_DELTA1 || grid_id == MGP_GRID_SD_DELTA2) c.sd_have_delta = true;
   API_END
 }
 

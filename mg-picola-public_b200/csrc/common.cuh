@@ -53,7 +53,7 @@ void set_last_error(const std::string &m);
   } while (0)
 
 // phases, named after the reference's timer.h sub-categories
-enum Phase { PH_MOVE = 0, PH_PTOMESH, PH_FFT, PH_FIFTH, PH_FORCES, PH_MTOP, PH_KICK, PH_DRIFT, PH_POFK, PH_SORT, PH_COMM, PH_COUNT };
+enum Phase { PH_MOVE = 0, PH_PTOMESH, PH_FFT, PH_FIFTH, PH_FORCES, PH_MTOP, PH_KICK, PH_DRIFT, PH_POFK, PH_SORT, PH_COMM, PH_SDFIELD, PH_SDASSIGN, PH_COUNT };
 
 constexpr int kSMs = 148;   // B200
 
@@ -110,6 +110,21 @@ struct Ctx {
   double ic_means[6] = {0, 0, 0, 0, 0, 0};
   bool ic_ready = false;
   void *sd_delta[2] = {nullptr, nullptr};    // delta1_k, delta2_k (cdelta_cdm, cdelta_cdm2; vars.h:272-273)
+  bool sd_have_delta = false;
+  float *sdf[4] = {nullptr, nullptr, nullptr, nullptr};   // per-particle D, D2, dDdy, dD2dy as [3][cap] (sd.cu)
+  bool sd_zero[4] = {false, false, false, false};         // slot reads as 0 (merged mode)
+  bool sd_set[4] = {false, false, false, false};          // slot assigned for the current particle order
+  bool sd_lagrangian_only = false;                        // particles carry IDs only (before mgp_init_particles)
+  double *sd_gtab[2] = {nullptr, nullptr};                // growth tables over |d|^2 on the device
+  // lattice points owned by other ranks (P > 1): request / response lists, built once per particle order
+  bool sd_req_valid = false;
+  unsigned *sd_cnt_dev = nullptr, *sd_cnt_host = nullptr;
+  std::vector<unsigned> sd_need, sd_serve;                // per rank: what I ask for / what I answer
+  size_t sd_nneed = 0, sd_nserve = 0;
+  unsigned long long *sd_req_id = nullptr, *sd_srv_id = nullptr;
+  uint32_t *sd_req_slot = nullptr;
+  float *sd_resp_out = nullptr, *sd_resp_in = nullptr;
+  size_t sd_req_id_bytes = 0, sd_req_slot_bytes = 0, sd_srv_id_bytes = 0, sd_resp_out_bytes = 0, sd_resp_in_bytes = 0;
 
   void *stage = nullptr;      // host <-> device particle staging (two chunks)
   size_t stage_bytes = 0;
@@ -181,6 +196,7 @@ void particles_sort(Ctx &c);
 void particles_kick(Ctx &c, double A, double dda, double ddD, double ddD2, const double sumD[3], double sumV[3]);
 void particles_drift(Ctx &c, double dyyy, double dD, double dD2, const double sumV[3]);
 void particles_migrate(Ctx &c);
+void particles_after_drift(Ctx &c);
 // deposit.cu
 void deposit_density(Ctx &c, int grid_id);
 void gather_forces(Ctx &c, double sumD[3]);
@@ -211,6 +227,15 @@ void ic_generate(Ctx &c, const mgp_ic_config *ic);
 void ic_init_particles(Ctx &c, double Di, double Di2, double dDdy, double dD2dy);
 void ic_seedtable(unsigned seed, int N, unsigned *out);
 double ic_ranlxd1_draw(unsigned long seed, long n);
+
+// sd.cu (scale-dependent growth)
+void sd_alloc(Ctx &c);
+void sd_free(Ctx &c);
+void sd_assign(Ctx &c, int fieldtype, int order, const double *g1, const double *g2, size_t n);
+void sd_init_particles(Ctx &c);
+void sd_kick(Ctx &c, double A, double dda, const double sumD[3], double sumV[3]);
+void sd_drift(Ctx &c, double dyyy, const double sumV[3]);
+void sd_copy_field(Ctx &c, int slot, float *host, bool to_host);
 
 // reductions: sum `n` doubles' worth of per-block partials living in c.d_red into host values
 void reduce_alloc(Ctx &c, size_t n);

@@ -358,41 +358,45 @@ static void ic_generate_t(Ctx &c, const mgp_ic_config *ic) {
   }
   fft_r2c(c, MGP_GRID_DENSITY);           // S_k, unnormalised like the reference's
 
-  // displacement fields at the Lagrangian points: ZA into disp[], 2LPT into the key/perm scratch
-  float *za = c.disp;                      // [3][cap] floats
-  float *lpt = (float *) c.pA2;            // the sort's second buffer set is idle here: 4 cap floats
-  const unsigned gp = grid_for(nloc, 256, 8);
-  reduce_alloc(c, (size_t) gp * 3 + 32);
-  double means[6];
-  const double n3 = (double) N * (double) N * (double) N;
-  for (int order = 1; order <= 2; order++) {
-    if (order == 1) k_ic_kernel<T, 0><<<gk, 256, 0, c.stream>>>(L, dk, f[0], f[1], f[2], c.cfg.box, nullptr, 1.0);
-    else k_ic_kernel<T, 3><<<gk, 256, 0, c.stream>>>(L, (const C *) c.grid[0], f[0], f[1], f[2], c.cfg.box, nullptr, 1.0);
-    fft_c2r_forces(c);
-    halo_fill_forces(c);
-    double *res = c.d_red + (size_t) gp * 3;
-    k_ic_readout<T><<<gp, 256, 0, c.stream>>>(nloc, ns, c.p0, N, c.NZ, c.x0, c.nx, fr[0], fr[1], fr[2],
-                                             order == 1 ? 1.0 : (-3.0 / 7.0) / n3, order == 1 ? za : lpt, c.cap, c.d_red);
-    k_final_reduce<<<1, 256, 0, c.stream>>>(c.d_red, (int) gp, 3, 3, 1.0, res);
-    c.launches += 3;
-    allreduce_sum(c, res, 3);
-    CK(cudaMemcpyAsync(c.h_red, res, 3 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
-    CK(cudaStreamSynchronize(c.stream));
-    const double tot = (double) ns * (double) ns * (double) ns;
-    for (int a = 0; a < 3; a++) means[3 * (order - 1) + a] = c.h_red[a] / tot;
-  }
-  for (int a = 0; a < 6; a++) c.ic_means[a] = means[a];
-  c.ic_ready = true;
-  c.np = 0;
-
   if (c.cfg.scale_dependent) {
-    // keep delta1_k and delta2_k = -S_k for the per-step scale-dependent displacement fields
+    // -DSCALEDEPENDENT: displacement_fields() returns here (2LPT.c:1361-1374) keeping delta1_k and
+    // delta2_k = -S_k; the displacements are rebuilt from them with k-dependent growth factors (sd.cu)
     REQUIRE(c.sd_delta[0] && c.sd_delta[1], MGP_ERR_STATE, "scale-dependent storage missing");
     CK(cudaMemcpyAsync(c.sd_delta[0], dk, L.total * sizeof(C), cudaMemcpyDeviceToDevice, c.stream));
     size_t zero_index = (size_t) -1;
     if (!L.transposed || L.j0 == 0) zero_index = 0;      // mode (0,0,0) is element 0 of the rank that owns ky = 0
     k_ic_neg<C><<<gk, 256, 0, c.stream>>>((const C *) c.grid[0], (C *) c.sd_delta[1], L.total, zero_index);
     c.launches++;
+    c.sd_have_delta = true;
+    c.np = 0;
+    c.sd_lagrangian_only = false;
+  } else {
+    // displacement fields at the Lagrangian points: ZA into disp[], 2LPT into the key/perm scratch
+    float *za = c.disp;                      // [3][cap] floats
+    float *lpt = (float *) c.pA2;            // the sort's second buffer set is idle here: 4 cap floats
+    const unsigned gp = grid_for(nloc, 256, 8);
+    reduce_alloc(c, (size_t) gp * 3 + 32);
+    double means[6];
+    const double n3 = (double) N * (double) N * (double) N;
+    for (int order = 1; order <= 2; order++) {
+      if (order == 1) k_ic_kernel<T, 0><<<gk, 256, 0, c.stream>>>(L, dk, f[0], f[1], f[2], c.cfg.box, nullptr, 1.0);
+      else k_ic_kernel<T, 3><<<gk, 256, 0, c.stream>>>(L, (const C *) c.grid[0], f[0], f[1], f[2], c.cfg.box, nullptr, 1.0);
+      fft_c2r_forces(c);
+      halo_fill_forces(c);
+      double *res = c.d_red + (size_t) gp * 3;
+      k_ic_readout<T><<<gp, 256, 0, c.stream>>>(nloc, ns, c.p0, N, c.NZ, c.x0, c.nx, fr[0], fr[1], fr[2],
+                                               order == 1 ? 1.0 : (-3.0 / 7.0) / n3, order == 1 ? za : lpt, c.cap, c.d_red);
+      k_final_reduce<<<1, 256, 0, c.stream>>>(c.d_red, (int) gp, 3, 3, 1.0, res);
+      c.launches += 3;
+      allreduce_sum(c, res, 3);
+      CK(cudaMemcpyAsync(c.h_red, res, 3 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+      CK(cudaStreamSynchronize(c.stream));
+      const double tot = (double) ns * (double) ns * (double) ns;
+      for (int a = 0; a < 3; a++) means[3 * (order - 1) + a] = c.h_red[a] / tot;
+    }
+    for (int a = 0; a < 6; a++) c.ic_means[a] = means[a];
+    c.ic_ready = true;
+    c.np = 0;
   }
   CK(cudaStreamSynchronize(c.stream));
   c.grid[MGP_GRID_MG_ONE] = save4;

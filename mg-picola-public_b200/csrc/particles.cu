@@ -171,6 +171,9 @@ void particles_upload(Ctx &c, uint64_t n, const float *pos, const float *vel, co
   c.drifts_since_sort = 1 << 30;
   c.np_after_sort = SIZE_MAX;
   c.have_disp = false;
+  c.sd_req_valid = false;
+  c.sd_lagrangian_only = false;
+  for (int s = 0; s < 4; s++) c.sd_set[s] = false;
 }
 
 void particles_download(Ctx &c, float *pos, float *vel, float *D, float *D2, uint64_t *id) {
@@ -377,6 +380,8 @@ void particles_sort(Ctx &c) {
   c.sorted = true;
   c.drifts_since_sort = 0;
   c.have_disp = false;   // Disp was in the old order
+  c.sd_req_valid = false;                                  // ... and so were the scale-dependent per-particle fields
+  for (int s = 0; s < 4; s++) c.sd_set[s] = false;
 }
 
 // ------------------------------------------------------------------ Kick
@@ -472,6 +477,10 @@ void particles_drift(Ctx &c, double dyyy, double dD, double dD2, const double su
                                                     sumV[2], dyyy, (double) c.cfg.use_cola, dD, dD2, (float) c.cfg.box);
     c.launches++;
   }
+  particles_after_drift(c);
+}
+
+void particles_after_drift(Ctx &c) {
   c.sorted = false;
   if (c.drifts_since_sort < (1 << 30)) c.drifts_since_sort++;
   c.have_disp = false;

@@ -362,3 +362,119 @@ def get_displacements(pos, nmesh, nsample, box, model="none", mg=None, grid_dtyp
     disp, sumD = mtoparticles(pos, N11, N12, N13, N, box)
     out.update(disp=disp, sumDxyz=sumD, density_k=P3D, force_grids=(N11, N12, N13), density=dens)
     return out
+
+
+# ----------------------------------------------------------------------------- scale-dependent growth (2LPT.c:1539-2005)
+
+FIELD_D, FIELD_dDdy, FIELD_ddDddy, FIELD_deltaD = 0, 1, 2, 3      # proto.h:155-158
+
+
+def sd_ivec(nmesh):
+    """Integer wave vector with the IC code's Nyquist convention idx < N/2 ? idx : idx - N (2LPT.c:1589-1605)."""
+    N = nmesh
+    i = np.arange(N)
+    d = np.where(i < N // 2, i, i - N).astype(np.int64)
+    k = np.arange(N // 2 + 1)
+    dz = np.where(k < N // 2, k, k - N).astype(np.int64)
+    return d[:, None, None], d[None, :, None], dz[None, None, :]
+
+
+def sd_k_of_m(nmesh, box):
+    """|k| in h/Mpc for every integer m = |d|^2 in [0, 3 (N/2)^2]: the argument at which the driver evaluates
+    growth_X_scaledependent when it fills the table that crosses the C ABI."""
+    m = np.arange(3 * (nmesh // 2) ** 2 + 1, dtype=np.float64)
+    return 2.0 * PI / box * np.sqrt(m)
+
+
+def sd_field_kspace(delta_k, growth_by_k2, lpt_order, nmesh, box):
+    """from_cdisp_store_to_ZA, the k-space loop (2LPT.c:1584-1630): the three components
+    cdisp_D[a] = (-Im d, Re d) * kvec_a / kmag2 * growth_factor, growth_factor = normfactor * G(|k|)."""
+    N = nmesh
+    d0, d1, d2 = sd_ivec(N)
+    m = d0 * d0 + d1 * d1 + d2 * d2
+    normfactor = 1.0 if lpt_order == 1 else -3.0 / 7.0 / np.float64(N) ** 3
+    g = normfactor * np.asarray(growth_by_k2, dtype=np.float64)[m]
+    kv = [d * 2 * PI / box for d in (d0, d1, d2)]
+    kmag2 = kv[0] * kv[0] + kv[1] * kv[1] + kv[2] * kv[2]
+    out = []
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for a in range(3):
+            re = -delta_k.imag * kv[a] / kmag2 * g
+            im = delta_k.real * kv[a] / kmag2 * g
+            f = re + 1j * im
+            f[0, 0, 0] = 0.0
+            out.append(f)
+    return out
+
+
+def lagrangian_readout(grids, nmesh, nsample):
+    """Trilinear read-out of real grids [N][N][N] at the Lagrangian lattice (2LPT.c:1657-1705), single task.
+    Returns [Nsample^3][len(grids)] doubles in the order coord = (n Ns + m) Ns + p."""
+    N, Ns = nmesh, nsample
+    n = np.arange(Ns)
+    u = (n * N).astype(np.float64) / np.float64(Ns)
+    i = u.astype(np.int64)
+    i[i == N] = N - 1
+    fu = u - i
+    ii = (i + 1) % N                         # x: ghost slice == slice 0 of the single task; y, z wrap (2LPT.c:1679-1680)
+    I, J, K = np.meshgrid(i, i, i, indexing="ij")
+    II, JJ, KK = np.meshgrid(ii, ii, ii, indexing="ij")
+    U, V, W = np.meshgrid(fu, fu, fu, indexing="ij")
+    f1 = (1 - U) * (1 - V) * (1 - W)
+    f2 = (1 - U) * (1 - V) * W
+    f3 = (1 - U) * V * (1 - W)
+    f4 = (1 - U) * V * W
+    f5 = U * (1 - V) * (1 - W)
+    f6 = U * (1 - V) * W
+    f7 = U * V * (1 - W)
+    f8 = U * V * W
+    out = []
+    for G in grids:
+        v = (G[I, J, K] * f1 + G[I, J, KK] * f2 + G[I, JJ, K] * f3 + G[I, JJ, KK] * f4 +
+             G[II, J, K] * f5 + G[II, J, KK] * f6 + G[II, JJ, K] * f7 + G[II, JJ, KK] * f8)
+        out.append(v.reshape(-1))
+    return np.stack(out, axis=1)
+
+
+def sd_displacement_field(delta_k, growth_by_k2, lpt_order, nmesh, nsample, box, grid_dtype=np.float64):
+    """from_cdisp_store_to_ZA (2LPT.c:1539-1735): returns ZA_D[Nsample^3][3] (float_kind), mean removed.
+    assign_displacment_field_to_particles then copies ZA_D[coord_q] into the float particle field."""
+    N = nmesh
+    ck = np.complex64 if grid_dtype == np.float32 else np.complex128
+    comps = [c2r(f.astype(ck).astype(np.complex128), N).astype(grid_dtype).astype(np.float64)
+             for f in sd_field_kspace(delta_k, growth_by_k2, lpt_order, N, box)]
+    za = lagrangian_readout(comps, N, nsample)
+    mean = za.sum(axis=0) / np.float64(nsample) ** 3                     # 2LPT.c:1716-1719
+    za = za.astype(grid_dtype)                                            # ZA_D is float_kind (2LPT.c:1700)
+    return (za.astype(np.float64) - mean[None, :]).astype(grid_dtype)     # 2LPT.c:1724-1728
+
+
+def kick_sd(vel, disp, D, D2, sumDxyz, omega, use_cola, A, dda, tot_numpart=None):
+    """Kick, SCALEDEPENDENT branch (main.c:705-717): P.D / P.D2 hold the ddD-weighted fields; their sum and the
+    product with the int UseCOLA are float arithmetic in C."""
+    disp_new = (disp.astype(np.float64) - np.asarray(sumDxyz, dtype=np.float64)[None, :]).astype(np.float32)
+    dd = (np.float32(use_cola) * (D.astype(np.float32) + D2.astype(np.float32))).astype(np.float32)
+    force = (-1.5 * omega) * disp_new.astype(np.float64) - dd.astype(np.float64) / A
+    vel_new = (vel.astype(np.float64) + force * dda).astype(np.float32)
+    tot = vel.shape[0] if tot_numpart is None else tot_numpart
+    return vel_new, disp_new, vel_new.astype(np.float64).sum(axis=0) / np.float64(tot)
+
+
+def drift_sd(pos, vel, dDdy, dD2dy, sumxyz, box, use_cola, dyyy):
+    """Drift, SCALEDEPENDENT branch (main.c:760-770): P.dDdy / P.dD2dy hold the per-particle increments; the
+    second statement is float arithmetic throughout."""
+    p = (pos.astype(np.float64) + (vel.astype(np.float64) - np.asarray(sumxyz, dtype=np.float64)[None, :]) * dyyy
+         ).astype(np.float32)
+    arg = (p + (np.float32(use_cola) * (dDdy.astype(np.float32) + dD2dy.astype(np.float32))).astype(np.float32)).astype(np.float32)
+    return periodic_wrap(arg, box)
+
+
+def init_particles_sd(D, D2, dDdy, dD2dy, nsample, box, use_cola):
+    """main.c:257-304, SCALEDEPENDENT branch: returns (pos, vel, ids) in Lagrangian order."""
+    Ns = nsample
+    q = np.stack(np.meshgrid(np.arange(Ns), np.arange(Ns), np.arange(Ns), indexing="ij"), -1).reshape(-1, 3)
+    arg = q.astype(np.float64) * (box / np.float64(Ns)) + D.astype(np.float64) + D2.astype(np.float64)
+    pos = periodic_wrap(arg.astype(np.float32), box)
+    vel = np.zeros_like(pos) if use_cola else (dDdy.astype(np.float32) + dD2dy.astype(np.float32)).astype(np.float32)
+    ids = (q[:, 0].astype(np.uint64) * Ns + q[:, 1].astype(np.uint64)) * Ns + q[:, 2].astype(np.uint64)
+    return pos, vel, ids

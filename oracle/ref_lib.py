@@ -89,6 +89,13 @@ class RefLib:
             f.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_uint]
         L.my_fftw_execute.argtypes = [C.c_void_p]
         L.my_fftw_destroy_plan.argtypes = [C.c_void_p]
+        if self.flags["scaledependent"]:
+            for name in ("growth_D_scaledependent", "growth_dDdy_scaledependent", "growth_ddDddy_scaledependent",
+                         "growth_D2_scaledependent", "growth_dD2dy_scaledependent", "growth_ddD2ddy_scaledependent"):
+                f = getattr(L, name)
+                f.restype = C.c_double
+                f.argtypes = [C.c_double, C.c_double]
+            L.assign_displacment_field_to_particles.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]
 
     # ---- globals ----
     def _g(self, name, ctype):
@@ -268,6 +275,69 @@ class RefLib:
         self.set(TotNumPart=n)
         return dict(A=A, Di=Di, Di2=Di2, ZA=ZA, LPT=LPT)
 
+    # ---- SCALEDEPENDENT builds ----
+    SD_FUNCS = {1: ("growth_D_scaledependent", "growth_dDdy_scaledependent", "growth_ddDddy_scaledependent"),
+                2: ("growth_D2_scaledependent", "growth_dD2dy_scaledependent", "growth_ddD2ddy_scaledependent")}
+
+    def sd_growth_table(self, fieldtype, order, A, AFF=None):
+        """What the C adapter hands to mgp_assign_displacement_field: the growth factor from_cdisp_store_to_ZA
+        evaluates per mode (2LPT.c:1611-1614, without normfactor) at every integer m = |d|^2, k = 2 pi sqrt(m) / Box."""
+        from . import pm_oracle
+        kk = pm_oracle.sd_k_of_m(self.N, self.box)
+        fD, fdD, fddD = (getattr(self.lib, n) for n in self.SD_FUNCS[order])
+        out = np.zeros(kk.size)
+        for m in range(1, kk.size):
+            k = float(kk[m])
+            if fieldtype == 0:
+                out[m] = fD(k, A)
+            elif fieldtype == 1:
+                out[m] = fdD(k, A)
+            elif fieldtype == 2:
+                out[m] = fddD(k, A)
+            else:
+                out[m] = fD(k, AFF) - fD(k, A)
+        return out
+
+    def sd_delta(self, order):
+        """cdelta_cdm / cdelta_cdm2 (vars.h:272-273) as complex [N][N][N/2+1]."""
+        N = self.N
+        ptr = C.c_void_p.in_dll(self.lib, "cdelta_cdm" if order == 1 else "cdelta_cdm2").value
+        ck = np.complex64 if self.fk == np.float32 else np.complex128
+        n = N * N * (N // 2 + 1)
+        raw = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_double if self.fk == np.float64 else C.c_float)), shape=(2 * n,))
+        return raw.view(ck).reshape(N, N, N // 2 + 1).copy()
+
+    def sd_assign(self, A, AF, AFF, fieldtype, order):
+        self.lib.assign_displacment_field_to_particles(A, AF, AFF, fieldtype, order)
+
+    def make_ic_sd(self):
+        """displacement_fields() + the particle initialisation of main.c:231-309, SCALEDEPENDENT branch (the
+        loop is inline in main() and restated here; the four assign calls are the reference's own)."""
+        assert self.flags["scaledependent"]
+        L = self.lib
+        Ns, box = self.Ns, self.box
+        init_z = self.get("Init_Redshift", C.c_double)
+        A = 1.0 / (1.0 + init_z)
+        L.displacement_fields()
+        n = Ns ** 3
+        cap = int(np.ceil(n * self.get("Buffer", C.c_double))) + 16
+        P = np.zeros(cap, dtype=self.pdt)
+        P["coord_q"][:n] = np.arange(n, dtype=np.uint32)        # main.c:233-241
+        P["init_cpu_id"][:n] = 0
+        self.P = P
+        C.c_void_p.in_dll(L, "P").value = P.ctypes.data
+        self.set(NumPart=n, TotNumPart=n)
+        for ft in (0, 1):                                       # main.c:246-251
+            for order in (1, 2):
+                L.assign_displacment_field_to_particles(A, A, A, ft, order)
+        from . import pm_oracle
+        use_cola = self.get("UseCOLA", C.c_int)
+        pos, vel, ids = pm_oracle.init_particles_sd(P["D"][:n], P["D2"][:n], P["dDdy"][:n], P["dD2dy"][:n], Ns, box, use_cola)
+        P["Pos"][:n] = pos
+        P["Vel"][:n] = vel
+        P["ID"][:n] = ids
+        return dict(A=A, Di=L.growth_D(A), Di2=L.growth_D2(A))
+
     def get_displacements(self):
         """GetDisplacements() as compiled (MEMORY_MODE: allocates and frees its own grids)."""
         self.lib.GetDisplacements()
@@ -286,15 +356,16 @@ class RefLib:
 class RefRun:
     """Run-level driver: the reference's own set-up, IC generator and GetDisplacements / Kick / Drift
     stepped along main()'s schedule (main.c:394-611, stepDistr = 0; the bookkeeping is inline code in
-    main() and is restated here; non-SCALEDEPENDENT variants).  Output steps are not taken: the
+    main() and is restated here).  Output steps are not taken: the
     schedule is the regular sequence of one output interval."""
 
     def __init__(self, variant, paramfile, quiet=True):
         self.r = RefLib(variant)
         self.quiet = quiet
+        self.sd = self.r.flags["scaledependent"]
         with _silenced(quiet):
             self.r.init_from_paramfile(paramfile)
-            ic = self.r.make_ic()
+            ic = self.r.make_ic_sd() if self.sd else self.r.make_ic()
         L = self.r.lib
         self.A = ic["A"]
         self.AI = self.A
@@ -317,6 +388,10 @@ class RefRun:
         with _silenced(self.quiet):
             r.set(timeStep_global=self.istep, NoutputStart_global=0, aexp_global=A)
             L.GetDisplacements()
+            if self.sd:                                   # main.c:485-503
+                for ft in (3, 2):
+                    for order in (1, 2):
+                        L.assign_displacment_field_to_particles(A, AF, AFF, ft, order)
             L.Kick(self.AI, AF, A, self.Di)
             r.free_disp()
             L.Drift(A, AFF, AF, self.Di, self.Di2)

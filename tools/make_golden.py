@@ -117,7 +117,7 @@ def run_fofr(N=16, box=60.0, nsteps=3):
     print("run_fofr", P0.shape, np.stack(pk).shape)
 
 
-if __name__ == "__main__" and "--ic" not in sys.argv:
+if __name__ == "__main__" and len(sys.argv) == 1:
     one_step("lcdm", "lcdm")
     one_step("fofr", "lcdm", extra=dict(include_screening=1, fofr0=1e-5, nfofr=1.0))
     one_step("dgp", "dgp", a=0.8, extra=dict(include_screening=1, rcH0_DGP=1.2, Rsmooth_global=1.0))
@@ -143,3 +143,74 @@ def ic_fixture(N=16, box=60.0):
 
 if __name__ == "__main__" and "--ic" in sys.argv:
     ic_fixture()
+
+
+def sd_fixture(N=16, box=60.0, nsteps=3):
+    """SCALEDEPENDENT f(R) build (MODEL=FOFR), use_lcdm_growth_factors = 0: the stored delta1_k / delta2_k of the
+    reference's IC generator, the growth tables the adapter would pass, the four per-particle fields at
+    initialisation and in the first step, and the particle state along three full steps."""
+    pf = bench.write_paramfile("/tmp/mgp_golden_sd", N, box, "fofr", 10, lcdm_growth=0)
+    run = ref_lib.RefRun("fofr", pf)
+    r, L = run.r, run.r.lib
+    r.set(**POFK)
+    h = N // 2
+    mm = np.arange(3 * h * h + 1)
+    with ref_lib._silenced(True):
+        power = np.array([L.PowerSpec(2 * np.pi / box * np.sqrt(float(v))) * (L_mg_ratio(L, 2 * np.pi / box * np.sqrt(float(v))) if v else 0.0)
+                          for v in mm])
+    out = dict(N=N, box=box, omega=OMEGA, fofr0=1e-5, nfofr=1.0, seed=5001, power_by_k2=power,
+               delta1=r.sd_delta(1), delta2=r.sd_delta(2), A0=run.A)
+    P0 = run.particles().copy()
+    out.update(id0=P0["ID"], pos0=P0["Pos"], vel0=P0["Vel"], D0=P0["D"], D20=P0["D2"], dDdy0=P0["dDdy"], dD2dy0=P0["dD2dy"])
+    out["G_init"] = np.stack([r.sd_growth_table(ft, o, run.A) for ft in (0, 1) for o in (1, 2)])   # [D1, D2, dD1, dD2]
+    steps, tabs, pk = [], [], []
+    for it in range(nsteps):
+        A, AI, da = run.A, run.AI, run.da
+        AF, AFF = A + 0.5 * da, A + da
+        steps.append([A, AI, AF, AFF, L.Sphi(AI, AF, A), L.Sq(A, AFF, AF)])
+        tabs.append(np.stack([r.sd_growth_table(ft, o, A, AFF) for ft in (3, 2) for o in (1, 2)]))   # [dD1, dD2, ddD1, ddD2]
+        if it == 0:
+            # first step taken apart: GetDisplacements, the four assigns, Kick, Drift
+            with ref_lib._silenced(True):
+                r.set(timeStep_global=0, NoutputStart_global=0, aexp_global=A)
+                ref_lib.tap_reset(r)
+                L.GetDisplacements()
+                taps = [t for t in ref_lib.tap_arrays(r) if len(t) == POFK["pofk_nbins"]]
+                out["disp_s0"] = r.ref_disp()
+                out["sumDxyz_s0"] = r.get3("sumDxyz")
+                for ft in (3, 2):
+                    for o in (1, 2):
+                        L.assign_displacment_field_to_particles(A, AF, AFF, ft, o)
+                Pm = run.particles().copy()
+                out.update(id_s0=Pm["ID"], pos_s0=Pm["Pos"], vel_s0=Pm["Vel"], D_s0=Pm["D"], D2_s0=Pm["D2"], dDdy_s0=Pm["dDdy"], dD2dy_s0=Pm["dD2dy"])
+                L.Kick(AI, AF, A, run.Di)
+                out["vel_k0"] = run.particles()["Vel"].copy()
+                out["sumxyz_k0"] = r.get3("sumxyz")
+                r.free_disp()
+                L.Drift(A, AFF, AF, run.Di, run.Di2)
+                out["pos_d0"] = run.particles()["Pos"].copy()
+            run.A, run.AI = AFF, AF
+            run.Di, run.Di2 = L.growth_D(run.A), L.growth_D2(run.A)
+            run.istep += 1
+        else:
+            ref_lib.tap_reset(r)
+            run.step()
+            taps = [t for t in ref_lib.tap_arrays(r) if len(t) == POFK["pofk_nbins"]]
+        pk.append(np.stack(taps[:3]))
+    P1 = run.particles().copy()
+    out.update(steps=np.array(steps), G_steps=np.stack(tabs), pofk_sums=np.stack(pk), id1=P1["ID"], pos1=P1["Pos"], vel1=P1["Vel"],
+               pofk_cfg=np.array([POFK["pofk_nbins"], POFK["pofk_bintype"], 1, POFK["pofk_kmin"], POFK["pofk_kmax"]]))
+    np.savez_compressed(os.path.join(OUT, "sd_fofr.npz"), **out)
+    print("sd_fofr", {k: getattr(v, "shape", v) for k, v in out.items() if k in ("delta1", "G_steps", "pos1")},
+          "G spread", out["G_init"][0][1:].min(), out["G_init"][0][1:].max())
+
+
+def L_mg_ratio(L, k):
+    import ctypes as C
+    L.mg_pofk_ratio.restype = C.c_double
+    L.mg_pofk_ratio.argtypes = [C.c_double, C.c_double]
+    return L.mg_pofk_ratio(k, 1.0)
+
+
+if __name__ == "__main__" and "--sd" in sys.argv:
+    sd_fixture()
