@@ -33,6 +33,8 @@ FOFR0, NFOFR, RCH0, RSMOOTH = 1e-5, 1.0, 1.0, 1.0
 # compulsory HBM bytes per particle-step of a maximally fused step
 WEAK_NMESH = {1: 256, 2: 320, 4: 400, 8: 512}
 ALGO_BYTES = {"lcdm": lambda g: 120 + 32 * g, "fofr": lambda g: 120 + 51 * g, "dgp": lambda g: 120 + 51 * g}
+# SCALEDEPENDENT add-on (section 8(d)): merged two-order fields 52 g, reference-structured (four fields) 48 + 100 g
+ALGO_BYTES_SD = {"merged": lambda g: 52 * g, "ref": lambda g: 48 + 100 * g}
 
 
 def box_for(nmesh):
@@ -103,9 +105,10 @@ class ClockSampler(threading.Thread):
 class Stepper:
     """Drives the library exactly as main.c's loop does (main.c:394-611)."""
 
-    def __init__(self, pm, cos, model, box):
+    def __init__(self, pm, cos, model, box, sd=None, sd_mode="merged"):
         from mgpicola_b200 import cosmology
         self.pm, self.cos, self.model, self.box = pm, cos, model, box
+        self.sd, self.sd_mode = sd, sd_mode
         self.sched = cosmology.schedule(Z_INIT, [(0.0, NSTEPS_RUN)])
         self.cosmology = cosmology
         self.i = 0
@@ -114,8 +117,10 @@ class Stepper:
         for s in self.sched[:NSTEPS_RUN]:
             A, AI, AF, AFF = s["A"], s["AI"], s["AF"], s["AFF"]
             Di, Di2 = cos.growth_D(A), cos.growth_D2(A)
+            # scale-dependent growth: the tables assign_displacment_field_to_particles needs (main.c:496-501), in call order
+            tabs = [sd.table(ft, o, A, AFF) for ft in (3, 2) for o in (1, 2)] if sd is not None else None
             self.pre.append((self.scalars(A), A, cos.Sphi(AI, AF, A), cos.growth_ddDddy(A), cos.growth_ddD2ddy(A),
-                             cos.Sq(A, AFF, AF), cos.growth_D(AFF) - Di, cos.growth_D2(AFF) - Di2))
+                             cos.Sq(A, AFF, AF), cos.growth_D(AFF) - Di, cos.growth_D2(AFF) - Di2, tabs))
 
     def scalars(self, A):
         if self.model == "fofr":
@@ -125,10 +130,17 @@ class Stepper:
         return self.pm.scalars(a=A, compute_pofk=1)
 
     def step(self):
-        sc, A, dda, ddD, ddD2, dyyy, dD, dD2 = self.pre[self.i % NSTEPS_RUN]   # stay inside the regular (non-output) steps
+        sc, A, dda, ddD, ddD2, dyyy, dD, dD2, tabs = self.pre[self.i % NSTEPS_RUN]   # stay inside the regular (non-output) steps
         self.i += 1
         pm = self.pm
         pm.GetDisplacements(sc)
+        if tabs is not None:
+            if self.sd_mode == "merged":
+                pm.assign_displacement_fields_merged(3, tabs[0], tabs[1])
+                pm.assign_displacement_fields_merged(2, tabs[2], tabs[3])
+            else:
+                for i, (ft, o) in enumerate(((3, 1), (3, 2), (2, 1), (2, 2))):
+                    pm.assign_displacment_field_to_particles(ft, o, tabs[i])
         pm.Kick(A, dda, ddD, ddD2)
         pm.Drift(dyyy, dD, dD2)
 
@@ -159,16 +171,25 @@ def run_ours(args):
     model = args.model
     cos = cosmology.LCDM(OMEGA, Z_INIT)
     model_id = {"lcdm": mgp.MODEL_NONE, "fofr": mgp.MODEL_FOFR, "dgp": mgp.MODEL_DGP}[model]
+    use_sd = args.scale_dependent if args.scale_dependent >= 0 else int(model in ("fofr", "dgp"))
+    sd = cosmology.ScaleDependentGrowth(cos, box, N, model, fofr0=FOFR0, nfofr=NFOFR, rcH0=RCH0) if use_sd else None
     pm = mgp.PM(N, N, box, omega=OMEGA, model=model_id, include_screening=1, grid_bytes=g, rank=rank, nranks=world,
-                device=local, nccl_id=nccl_id, deposit_mode=args.deposit_mode, sort_particles=args.sort_interval)
+                device=local, nccl_id=nccl_id, deposit_mode=args.deposit_mode, sort_particles=args.sort_interval,
+                scale_dependent=use_sd)
     pm.set_pofk(64, 1, 1, 0.03, 2.0)          # paramfiles/additions_compute_pofk.txt
     t0 = time.time()
     A0 = 1.0 / (1.0 + Z_INIT)
-    pm.ic_generate(amplitude_table(N, box), seed=5001)           # displacement_fields() on the GPU(s)
+    power = amplitude_table(N, box)
+    if sd is not None:
+        power = power * sd.pofk_ratio_by_k2()                    # input_pofk_is_for_lcdm = 1 (2LPT.c:396-397)
+    pm.ic_generate(power, seed=5001)                             # displacement_fields() on the GPU(s)
+    if sd is not None:
+        for o in (1, 2):                                         # main.c:246-247 (UseCOLA = 1: Vel = 0, dDdy not needed)
+            pm.assign_displacment_field_to_particles(0, o, sd.table(0, o, A0))
     pm.init_particles(cos.growth_D(A0), cos.growth_D2(A0))
     t_ic = time.time() - t0
     npart_total = N ** 3
-    st = Stepper(pm, cos, model, box)
+    st = Stepper(pm, cos, model, box, sd, args.sd_mode)
     stream = torch.cuda.ExternalStream(pm.stream)
 
     def barrier():
@@ -216,14 +237,16 @@ def run_ours(args):
         got = pm.download_particles()
         hp = {k: torch.from_numpy(got[k].copy()).pin_memory() for k in ("pos", "vel", "D", "D2")}
         hid = torch.from_numpy(got["id"].astype(np.int64)).pin_memory()
+        if use_sd:      # the per-particle displacement fields are rebuilt on the device every step: only Pos, Vel, ID travel
+            hp = {k: hp[k] for k in ("pos", "vel")}
         h2d = sum(t.numel() * t.element_size() for t in hp.values()) + hid.numel() * 8
         d2h = hp["pos"].numel() * 4 * 2
         ne2e = max(2, min(args.steps, 5))
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(ne2e):
-            pm.upload_raw(hp["pos"].data_ptr(), hp["vel"].data_ptr(), hp["D"].data_ptr(), hp["D2"].data_ptr(),
-                          hid.data_ptr(), hid.numel())
+            pm.upload_raw(hp["pos"].data_ptr(), hp["vel"].data_ptr(), hp["D"].data_ptr() if "D" in hp else 0,
+                          hp["D2"].data_ptr() if "D2" in hp else 0, hid.data_ptr(), hid.numel())
             st.step()
             pm.download_raw(hp["pos"].data_ptr(), hp["vel"].data_ptr(), 0, 0, hid.data_ptr())
         torch.cuda.synchronize()
@@ -240,11 +263,11 @@ def run_ours(args):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6550.0))
-    A_min = ALGO_BYTES[model](g)
+    A_min = ALGO_BYTES[model](g) + (ALGO_BYTES_SD[args.sd_mode](g) if use_sd else 0)
     # dominant hand-written kernels: deposit (PtoMesh phase) and gather (MtoParticles phase)
     kern_bytes = {"PtoMesh": (16 + g) * (N ** 3) / max(world, 1),            # Pos(+id) 16 B read, grid g write per cell
                   "MtoParticles": (16 + 3 * g + 12) * (N ** 3) / max(world, 1)}   # Pos 16 R, 3 grids R, Disp 12 W
-    own = {k: phases.get(k, 0.0) for k in ("PtoMesh", "MtoParticles", "Forces", "ComputeFifthForce", "Kick", "Drift", "Sort", "Pofk")}
+    own = {k: phases.get(k, 0.0) for k in ("PtoMesh", "MtoParticles", "Forces", "ComputeFifthForce", "Kick", "Drift", "Sort", "Pofk", "SDField", "SDAssign")}
     dom = max(("PtoMesh", "MtoParticles"), key=lambda k: own.get(k, 0.0))
     ach = kern_bytes[dom] / (own[dom] * 1e-3) / 1e9 if own.get(dom) else None
     roof = {"bound": "hbm", "kernel": {"PtoMesh": ["k_deposit_atomic", "k_deposit_tile", "k_deposit_rowseg"][args.deposit_mode] + " (CIC deposit)",
@@ -258,10 +281,14 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 particles, f%d grids/FFTs, f64 weights" % (8 * g), "data": "synthetic",
-            "config": {"workload": "%s%s COLA step, Npart=Nmesh=%d^3, Box=%g Mpc/h, P(k) every step, z=9->0 in %d steps "
-                                   "(reference configs[1] without SCALEDEPENDENT growth: build MODEL=FOFR_LCDM)"
-                                   % (model, " with screening" if model != "lcdm" else "", N, box, NSTEPS_RUN),
-                       "nmesh": N, "npart": npart_total, "grid_bytes": g, "deposit_mode": args.deposit_mode, "sort_interval": args.sort_interval,
+            "config": {"workload": "%s%s COLA step, Npart=Nmesh=%d^3, Box=%g Mpc/h, P(k) every step, z=9->0 in %d steps, %s"
+                                   % (model, " with screening" if model != "lcdm" else "", N, box, NSTEPS_RUN,
+                                      ("SCALEDEPENDENT growth (reference build MODEL=%s, use_lcdm_growth_factors=0), displacement fields %s"
+                                       % ({"fofr": "FOFR", "dgp": "DGP -DSCALEDEPENDENT"}.get(model, model),
+                                          "merged per field type: D+D2 in one pass, 6 extra c2r/step" if args.sd_mode == "merged"
+                                          else "reference-structured: 4 fields, 12 extra c2r/step")) if use_sd
+                                      else "scale-independent growth (reference build MODEL=FOFR_LCDM / DGP)"),
+                       "nmesh": N, "npart": npart_total, "grid_bytes": g, "scale_dependent": use_sd, "sd_mode": args.sd_mode if use_sd else None, "deposit_mode": args.deposit_mode, "sort_interval": args.sort_interval,
                        "l2": "inputs larger than L2 (particles %.1f GB, grids %.1f GB each)" % (N ** 3 * 56 / 1e9, N ** 3 * g / 1e9),
                        "ic_seconds_gpu": round(t_ic, 2)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "e2e": e2e}
@@ -334,7 +361,11 @@ def cpu_reference(args, sample_nmesh, steps, warmup):
     workload on one host core: its own GetDisplacements / Kick / Drift, wall clock per step."""
     import tempfile
     from oracle import ref_lib
-    variant = "dgp" if args.model == "dgp" else "lcdm"      # 'lcdm' = -DFOFRGRAVITY without SCALEDEPENDENT (MODEL=FOFR_LCDM)
+    use_sd = args.scale_dependent if args.scale_dependent >= 0 else int(args.model in ("fofr", "dgp"))
+    if use_sd:
+        variant = {"fofr": "fofr", "dgp": "dgp_sd", "lcdm": "fofr"}[args.model]     # MODEL=FOFR / DGP -DSCALEDEPENDENT
+    else:
+        variant = "dgp" if args.model == "dgp" else "lcdm"  # 'lcdm' = -DFOFRGRAVITY without SCALEDEPENDENT (MODEL=FOFR_LCDM)
     if not ref_lib.available(variant):
         return {"value": None, "unit": "particle-updates/s", "cores": 1, "kind": "reference",
                 "sample": "oracle/_ref not built (needs /root/reference at build time)"}
@@ -342,7 +373,7 @@ def cpu_reference(args, sample_nmesh, steps, warmup):
     nm_full = args.nmesh if args.nmesh else WEAK_NMESH.get(args.gpus, 256)
     box = box_for(nm_full) * N / nm_full
     wd = tempfile.mkdtemp(prefix="mgp_ref_")
-    pf = write_paramfile(wd, N, box, args.model, NSTEPS_RUN)
+    pf = write_paramfile(wd, N, box, args.model, NSTEPS_RUN, lcdm_growth=0 if use_sd else 1)
     drv = ref_lib.RefRun(variant, pf, quiet=True)
     for _ in range(warmup):
         drv.step()
@@ -353,7 +384,8 @@ def cpu_reference(args, sample_nmesh, steps, warmup):
     return {"value": N ** 3 / dt, "unit": "particle-updates/s", "cores": 1, "kind": "reference",
             "ms_per_step": dt * 1e3,
             "sample": "%d timed + %d warm-up steps of the same %s workload at Npart=Nmesh=%d^3 (Box=%g), unmodified reference "
-                      "sources on serial-MPI / CPU-FFT / mini-GSL stand-ins (no FFTW/MPI/GSL on the box), 1 core" % (steps, warmup, args.model, N, box)}
+                      "sources (variant %s%s) on serial-MPI / CPU-FFT / mini-GSL stand-ins (no FFTW/MPI/GSL on the box), 1 core"
+                      % (steps, warmup, args.model, N, box, variant, ", SCALEDEPENDENT: 12 extra c2r + 4 field assignments per step" if use_sd else "")}
 
 
 def run_reference(args):
@@ -367,8 +399,8 @@ def run_reference(args):
             "unit": "particle-updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": cb.get("ms_per_step"), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32 particles, f64 grids/FFTs", "data": "synthetic",
-            "config": {"workload": "%s COLA step, reference CPU path, bounded sample Npart=Nmesh=%d^3 of the %d^3 workload"
-                                   % (args.model, N, nm), "nmesh": N},
+            "config": {"workload": "%s COLA step, reference CPU path, bounded sample Npart=Nmesh=%d^3 of the %d^3 workload; %s"
+                                   % (args.model, N, nm, cb["sample"]), "nmesh": N},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -386,6 +418,9 @@ def main():
     ap.add_argument("--grid-bytes", type=int, default=8, choices=[4, 8])
     ap.add_argument("--deposit-mode", type=int, default=0, help="0 atomic (warp-aggregated), 1 shared-memory tile, 2 deterministic")
     ap.add_argument("--sort-interval", type=int, default=4, help="re-sort particles by cell every k-th step (0 never)")
+    ap.add_argument("--scale-dependent", type=int, default=-1, help="-1: as the reference build of the model (fofr, dgp: 1; lcdm: 0)")
+    ap.add_argument("--sd-mode", default="merged", choices=["merged", "ref"],
+                    help="merged: D+D2 per field type in one pass; ref: the reference's four separate fields")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

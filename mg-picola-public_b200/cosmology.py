@@ -126,3 +126,127 @@ def dgp_step_scalars(a, omega, rcH0, rsmooth):
     dH = 1.0 / (2.0 * H) * (-3.0 * omega / (a * a * a * a))
     beta = 1.0 + 2.0 * rcH0 * (H + a * dH / 3.0)
     return dict(a=a, coupling=1.0 / (3.0 * beta), dgp_fac0=8.0 / 9.0 * omega * (rcH0 / beta) ** 2, rsmooth=rsmooth)
+
+
+class ScaleDependentGrowth:
+    """Scale-dependent first / second order growth factors: cosmo.c:206-237 (`ode_growth_D` with
+    -DSCALEDEPENDENT), 758-1010 (`calculate_scale_dependent_growth_factor`, `growth_X_scaledependent`).
+
+    The ODE system is integrated for `nk` log-spaced wave numbers between the reference's own limits
+    (cosmo.c:768-770) with a vectorised fixed-step RK4 in x = ln a; D, dD/dy = D' Q/a,
+    ddD/ddy = 1.5 mu Omega a D (and the second-order analogues) are stored on the (x, ln k) grid like the
+    reference's 2-D splines and looked up with cubic splines.  `table(field, order, A, AFF)` is what crosses
+    the C ABI: the growth factor at every integer m = |d|^2, k = 2 pi sqrt(m) / Box.
+
+    model = "fofr": mu = 1 + 2 beta^2 k^2 / (k^2 + a^2 m^2(a)), beta^2 = 1/6 (udf:618-630, 462-470, 490-498) and the
+    Bose-Koyama gamma_2 kernel (udf:848-882); model = "dgp": mu = 1 + 1/(3 beta_DGP) (udf:632-635), gamma_2 of
+    udf:884-888; model = "lcdm": mu = 1."""
+
+    def __init__(self, lcdm, box, nmesh, model="fofr", fofr0=1e-5, nfofr=1.0, rcH0=1.0, nk=400, npts=1000, substeps=4):
+        self.lcdm, self.box, self.N, self.model = lcdm, float(box), int(nmesh), model
+        om = lcdm.omega
+        zini = 200.0
+        xini, xend = np.log(1.0 / (1.0 + zini)), np.log(2.0)
+        kmin = 2.0 * np.pi / box * 0.5                       # cosmo.c:768-769
+        kmax = 2.0 * np.pi / box * nmesh * np.sqrt(3.0) * 2.0
+        self.logk = np.linspace(np.log(kmin), np.log(kmax), nk)
+        k = np.exp(self.logk)
+        self.x = np.linspace(xini, xend, npts)
+
+        def mass2(a):
+            fac = om / a ** 3 + 4.0 * (1.0 - om)
+            fac0 = om + 4.0 * (1.0 - om)
+            return fac0 * (fac / fac0) ** (nfofr + 2.0) / ((1.0 + nfofr) * fofr0)
+
+        def beta_dgp(a):
+            H = lcdm.hubble(a)
+            return 1.0 + 2.0 * rcH0 * (H + a * lcdm.dhubbleda(a) / 3.0)
+
+        def mu_of(a):
+            if model == "fofr":
+                k2 = (k * INVERSE_H0_MPCH) ** 2
+                return 1.0 + 2.0 * (1.0 / 6.0) * k2 / (k2 + a * a * mass2(a))
+            if model == "dgp":
+                return np.full_like(k, 1.0 + 1.0 / (3.0 * beta_dgp(a)))
+            return np.ones_like(k)
+
+        def gamma2_of(a):
+            H = lcdm.hubble(a)
+            if model == "fofr":
+                fac = om / a ** 3 + 4.0 * (1.0 - om)
+                fac0 = om + 4.0 * (1.0 - om)
+
+                def pi_fac(kk):
+                    return (kk * INVERSE_H0_MPCH / a) ** 2 + fac0 * (fac / fac0) ** (nfofr + 2.0) / (1.0 + nfofr) / fofr0
+                g = -(3.0 * (nfofr + 2.0) / (12.0 * (1.0 + nfofr) ** 2)) * (k * INVERSE_H0_MPCH / (a * H)) ** 2 * (om / a ** 3) ** 2 \
+                    * fac0 * (fac / fac0) ** (2.0 * nfofr + 3.0) / fofr0 ** 2
+                return g / (pi_fac(k) * pi_fac(k / np.sqrt(2.0)) ** 2)
+            if model == "dgp":
+                return np.full_like(k, -1.0 / 6.0 / beta_dgp(a) ** 3 * (rcH0 / H) ** 2 * (om / a ** 3) ** 2)
+            return np.zeros_like(k)
+
+        self._mu_of = mu_of
+
+        def rhs(xx, y):
+            a = np.exp(xx)
+            H, dH = lcdm.hubble(a), lcdm.dhubbleda(a)
+            mu = mu_of(a)
+            beta = 1.5 * om * mu / (a ** 3 * H * H)
+            alpha = 2.0 + a * dH / H
+            modfac = 1.0 + 2.0 * (a * a * H) ** 2 * gamma2_of(a) / (1.5 * om * a * mu)
+            return np.stack([y[1], -alpha * y[1] + beta * y[0], y[3], -alpha * y[3] + beta * (y[2] - modfac * y[0] * y[0])])
+
+        y = np.stack([np.ones(nk), np.ones(nk), np.full(nk, -3.0 / 7.0), np.full(nk, -6.0 / 7.0)])
+        store = np.empty((npts, 4, nk))
+        store[0] = y
+        for i in range(1, npts):
+            h = (self.x[i] - self.x[i - 1]) / substeps
+            xx = self.x[i - 1]
+            for _ in range(substeps):
+                k1 = rhs(xx, y)
+                k2_ = rhs(xx + 0.5 * h, y + 0.5 * h * k1)
+                k3 = rhs(xx + 0.5 * h, y + 0.5 * h * k2_)
+                k4 = rhs(xx + h, y + h * k3)
+                y = y + h / 6.0 * (k1 + 2 * k2_ + 2 * k3 + k4)
+                xx += h
+            store[i] = y
+        a = np.exp(self.x)[:, None]
+        Q = lcdm.qfactor(a)
+        mu = np.stack([mu_of(aa) for aa in np.exp(self.x)])
+        D, q, D2, q2 = store[:, 0], store[:, 1], store[:, 2], store[:, 3]
+        self._tab = {("D", 1): D, ("dD", 1): q * Q / a, ("ddD", 1): 1.5 * mu * om * a * D,
+                     ("D", 2): D2, ("dD", 2): q2 * Q / a, ("ddD", 2): 1.5 * mu * om * a * (D2 - D * D)}
+        self._spl = {kk: CubicSpline(self.x, v, axis=0) for kk, v in self._tab.items()}
+        self._norm = {1: self._spl[("D", 1)](0.0), 2: self._spl[("D", 2)](0.0)}     # value at a = 1 per k (cosmo.c:987-1010)
+        h2 = (nmesh // 2) ** 2
+        m = np.arange(3 * h2 + 1, dtype=np.float64)
+        with np.errstate(divide="ignore"):
+            self._logk_m = np.log(2.0 * np.pi / box * np.sqrt(m))
+        self._logk_m[0] = self.logk[0]
+
+    def _column(self, name, order, a):
+        return self._spl[(name, order)](np.log(a)) / self._norm[order]
+
+    def of_k2(self, name, order, a):
+        """growth_<name>_scaledependent(k(m), a) for every integer m = |d|^2 (entry 0 is never used)."""
+        col = self._column(name, order, a)
+        out = CubicSpline(self.logk, col)(np.clip(self._logk_m, self.logk[0], self.logk[-1]))
+        out[0] = 0.0
+        return out
+
+    def table(self, fieldtype, order, A, AFF=None):
+        """The growth factor from_cdisp_store_to_ZA applies (2LPT.c:1611-1614), without its normfactor."""
+        if fieldtype == 0:
+            return self.of_k2("D", order, A)
+        if fieldtype == 1:
+            return self.of_k2("dD", order, A)
+        if fieldtype == 2:
+            return self.of_k2("ddD", order, A)
+        return self.of_k2("D", order, AFF) - self.of_k2("D", order, A)
+
+    def pofk_ratio_by_k2(self):
+        """mg_pofk_ratio(k, 1) = (D(k, 1) / D_LCDM(1))^2 with both unnormalised (cosmo.c:708-714)."""
+        col = self._norm[1] / self.lcdm._n1
+        out = CubicSpline(self.logk, col)(np.clip(self._logk_m, self.logk[0], self.logk[-1])) ** 2
+        out[0] = 0.0
+        return out

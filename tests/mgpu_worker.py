@@ -22,6 +22,8 @@ def main():
     ap.add_argument("--mode", type=int, default=0)
     ap.add_argument("--out", required=True)
     ap.add_argument("--ic", action="store_true", help="generate the golden-fixture ICs on the ranks instead of stepping")
+    ap.add_argument("--sd", action="store_true", help="scale-dependent run of tests/golden/sd_fofr.npz on the ranks")
+    ap.add_argument("--merged", action="store_true")
     a = ap.parse_args()
     import torch
     import mgpicola_b200 as mgp
@@ -39,6 +41,39 @@ def main():
         pm.init_particles(float(g["Di"]), float(g["Di2"]))
         got = pm.download_particles()
         np.savez(os.path.join(a.out, "rank%d.npz" % rank), p0=pm.local_p_start, npl=pm.local_np, **got)
+        mdist.barrier()
+        pm.close()
+        return
+    if a.sd:
+        g = dict(np.load(os.path.join(ROOT, "tests", "golden", "sd_fofr.npz")))
+        N, box, om = int(g["N"]), float(g["box"]), float(g["omega"])
+        nid = mdist.share_from_rank0(mgp.nccl_unique_id)
+        pm = mgp.PM(N, N, box, omega=om, model=mgp.MODEL_FOFR, include_screening=1, grid_bytes=a.gb, scale_dependent=1, buffer=2.5,
+                    rank=rank, nranks=world, device=local, nccl_id=nid)
+        c = g["pofk_cfg"]
+        pm.set_pofk(int(c[0]), int(c[1]), int(c[2]), float(c[3]), float(c[4]))
+        pm.ic_generate(g["power_by_k2"], seed=int(g["seed"]))            # keeps delta1_k / delta2_k, transposed slabs
+        for idx, (ft, order) in enumerate([(0, 1), (0, 2), (1, 1), (1, 2)]):
+            pm.assign_displacment_field_to_particles(ft, order, g["G_init"][idx])
+        pm.init_particles(0.0, 0.0)
+        init = pm.download_particles()
+        pks = []
+        for it, (A, AI, AF, AFF, dda, dyyy) in enumerate(g["steps"]):
+            pc, cc, m2 = po.fofr_scalars(A, om, box, float(g["fofr0"]), float(g["nfofr"]))
+            pm.GetDisplacements(pm.scalars(a=A, phi_crit=pc, coupling=cc, massterm2=m2, compute_pofk=1))
+            pks.append(np.stack(pm.step_power_spectrum()))
+            Tb = g["G_steps"][it]
+            if a.merged:
+                pm.assign_displacement_fields_merged(3, Tb[0], Tb[1])
+                pm.assign_displacement_fields_merged(2, Tb[2], Tb[3])
+            else:
+                for idx, (ft, order) in enumerate([(3, 1), (3, 2), (2, 1), (2, 2)]):
+                    pm.assign_displacment_field_to_particles(ft, order, Tb[idx])
+            pm.Kick(A, dda, 0.0, 0.0)
+            pm.Drift(dyyy, 0.0, 0.0)
+        pm.MoveParticles()
+        got = pm.download_particles(want=("pos", "vel", "id"))
+        np.savez(os.path.join(a.out, "rank%d.npz" % rank), pks=np.stack(pks), id0=init["id"], pos0=init["pos"], **got)
         mdist.barrier()
         pm.close()
         return

@@ -100,3 +100,29 @@ def test_distributed_ic_matches_reference(require_gpu, tmp_path, world):
     pos = np.concatenate([r["pos"] for r in ranks])
     dp = np.abs(pos.astype(np.float64) - g["pos"])
     assert np.minimum(dp, box - dp).max() < 1e-5 * box / N
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("merged", [False, True])
+def test_scale_dependent_run_on_slabs(require_gpu, tmp_path, world, merged):
+    """SCALEDEPENDENT f(R) run on P slabs: distributed delta1_k / delta2_k, per-step displacement fields with the
+    request / response fetch for particles that left their birth slab (2LPT.c:1784-1980) == the reference's
+    single-task run (tests/golden/sd_fofr.npz)."""
+    if _ngpu() < world:
+        pytest.skip("needs %d GPUs" % world)
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "sd_fofr.npz")))
+    N, box = int(g["N"]), float(g["box"])
+    ranks = _run(world, tmp_path, N, 0, "fofr", 8, 0, extra=["--sd"] + (["--merged"] if merged else []))
+    assert np.array_equal(np.concatenate([r["id0"] for r in ranks]), g["id0"])
+    dp = np.abs(np.concatenate([r["pos0"] for r in ranks]).astype(np.float64) - g["pos0"])
+    assert np.minimum(dp, box - dp).max() < 1e-5
+    ids = np.concatenate([r["id"] for r in ranks]).astype(np.int64)
+    assert np.array_equal(np.sort(ids), np.arange(N ** 3))
+    ro = np.argsort(g["id1"])
+    pos = np.concatenate([r["pos"] for r in ranks])
+    vel = np.concatenate([r["vel"] for r in ranks])
+    dp = np.abs(pos.astype(np.float64) - g["pos1"][ro][ids])
+    assert np.minimum(dp, box - dp).max() < 2e-5 * box / N
+    assert np.abs(vel - g["vel1"][ro][ids]).max() < 1e-5 * np.abs(g["vel1"]).max()
+    moved = sum(int(((r["id"].astype(np.int64) // (N * N)) // (N // world) != k).sum()) for k, r in enumerate(ranks))
+    assert moved > 0, "no particle left its birth slab: the remote fetch was not exercised"

@@ -104,6 +104,23 @@ def test_oracle_sd_vs_compiled_reference():
         assert np.array_equal(pos.view(np.uint32), P["Pos"].view(np.uint32))
 
 
+def test_host_sd_growth_tables_match_reference(g):
+    """mgpicola_b200.cosmology.ScaleDependentGrowth (what bench.py uses in place of cosmo.c) against the tables the
+    reference's growth_X_scaledependent produced for the fixture: 1e-7 relative (the reference's own ODE tolerance)."""
+    from mgpicola_b200 import cosmology
+    N, box = int(g["N"]), float(g["box"])
+    sd = cosmology.ScaleDependentGrowth(cosmology.LCDM(float(g["omega"]), 9.0), box, N, "fofr", fofr0=float(g["fofr0"]), nfofr=float(g["nfofr"]))
+    A0 = float(g["A0"])
+    for idx, (ft, o) in enumerate([(0, 1), (0, 2), (1, 1), (1, 2)]):
+        assert np.abs(sd.table(ft, o, A0)[1:] / g["G_init"][idx][1:] - 1).max() < 1e-7
+    for it, (A, AI, AF, AFF, dda, dyyy) in enumerate(g["steps"]):
+        for idx, (ft, o) in enumerate([(3, 1), (3, 2), (2, 1), (2, 2)]):
+            assert np.abs(sd.table(ft, o, A, AFF)[1:] / g["G_steps"][it][idx][1:] - 1).max() < 1e-7
+    # mg_pofk_ratio(k, 1) as folded into the fixture's IC power table
+    t = np.load(os.path.join(G, "input_power_spectrum.npz"))
+    assert np.all(sd.pofk_ratio_by_k2()[1:] >= 1.0) and sd.pofk_ratio_by_k2()[1:].max() < 2.0
+
+
 # ----------------------------------------------------------------------------- GPU: CUDA path vs fixture
 
 def _pm(mgp, g, gb=8, **kw):
