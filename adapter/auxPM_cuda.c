@@ -24,6 +24,7 @@
 
 static mgp_ctx *g_ctx = NULL;
 static int g_host_is_newer = 1;      /* host P was (re)built: upload before the next force evaluation */
+static int g_host_synced = 0;        /* host P mirrors the device order (between mgp_adapter_sync_host and the next force evaluation) */
 static size_t g_host_capacity = 0;
 
 static void ck(int rc, const char *where) {
@@ -227,6 +228,7 @@ static void upload_host_particles(void) {
   ck(mgp_upload_particles(g_ctx, n, pos, vel, d1, d2, id), "mgp_upload_particles");
   my_free(pos); my_free(vel); my_free(d1); my_free(d2); my_free(id);
   g_host_is_newer = 0;
+  g_host_synced = 0;
 }
 
 /* called (through the main.c patch) before Output() reads P */
@@ -250,7 +252,77 @@ void mgp_adapter_sync_host(void) {
   }
   NumPart = (unsigned int) n;
   my_free(pos); my_free(vel); my_free(d1); my_free(d2); my_free(id);
+#ifdef SCALEDEPENDENT
+  {
+    float *f1 = my_malloc(n * 12), *f2 = my_malloc(n * 12);
+    ck(mgp_download_sd_fields(g_ctx, f1, f2), "mgp_download_sd_fields");
+    for (size_t i = 0; i < n; i++)
+      for (int a = 0; a < 3; a++) { P[i].dDdy[a] = f1[3 * i + a]; P[i].dD2dy[a] = f2[3 * i + a]; }
+    my_free(f1); my_free(f2);
+  }
+#endif
+  g_host_synced = 1;
 }
+
+#ifdef SCALEDEPENDENT
+/* ------------------------------------------------------------------ scale-dependent displacement fields (2LPT.c:1539-2005) */
+
+/* growth factor of from_cdisp_store_to_ZA (2LPT.c:1611-1614, without normfactor) at every integer m = |d|^2 */
+static double *sd_growth_table(double A, double AFF, int fieldtype, int LPTorder, size_t *n_out) {
+  const int h = Nmesh / 2;
+  const size_t nm = (size_t) 3 * h * h + 1;
+  double *g = my_malloc(sizeof(double) * nm);
+  double (*fD)(double, double) = LPTorder == 1 ? &growth_D_scaledependent : &growth_D2_scaledependent;
+  double (*fdD)(double, double) = LPTorder == 1 ? &growth_dDdy_scaledependent : &growth_dD2dy_scaledependent;
+  double (*fddD)(double, double) = LPTorder == 1 ? &growth_ddDddy_scaledependent : &growth_ddD2ddy_scaledependent;
+  g[0] = 0.0;
+  for (size_t m = 1; m < nm; m++) {
+    const double kmag = 2 * PI / Box * sqrt((double) m);
+    if (fieldtype == FIELD_D) g[m] = fD(kmag, A);
+    else if (fieldtype == FIELD_dDdy) g[m] = fdD(kmag, A);
+    else if (fieldtype == FIELD_ddDddy) g[m] = fddD(kmag, A);
+    else g[m] = fD(kmag, AFF) - fD(kmag, A);
+  }
+  *n_out = nm;
+  return g;
+}
+
+/* host copy of one of the four per-particle fields, when main.c works on the host array P (initialisation, Output) */
+static void sd_refresh_host(int fieldtype, int LPTorder) {
+  const size_t n = NumPart;
+  float *d1 = my_malloc(n * 12), *d2 = my_malloc(n * 12);
+  const int first_pair = (fieldtype == FIELD_D || fieldtype == FIELD_ddDddy);
+  if (first_pair) ck(mgp_download_particles(g_ctx, NULL, NULL, d1, d2, NULL), "mgp_download_particles");
+  else ck(mgp_download_sd_fields(g_ctx, d1, d2), "mgp_download_sd_fields");
+  for (size_t i = 0; i < n; i++)
+    for (int a = 0; a < 3; a++) {
+      if (first_pair) { if (LPTorder == 1) P[i].D[a] = d1[3 * i + a]; else P[i].D2[a] = d2[3 * i + a]; }
+      else { if (LPTorder == 1) P[i].dDdy[a] = d1[3 * i + a]; else P[i].dD2dy[a] = d2[3 * i + a]; }
+    }
+  my_free(d1); my_free(d2);
+}
+
+void assign_displacment_field_to_particles(double A, double AF, double AFF, int fieldtype, int LPTorder) {
+  (void) AF;
+  size_t nm;
+  /* MGP_SD_MERGED=1: build D + D2 (dDdy + dD2dy) in one pass when the order-2 call arrives; only their sum is ever
+   * used (main.c:712, 767, 962; compute_pofk.c:324).  6 instead of 12 inverse FFTs per step, one float rounding apart. */
+  static int merged = -1;
+  static double *pending = NULL;
+  if (merged < 0) { const char *e = getenv("MGP_SD_MERGED"); merged = e ? atoi(e) : 0; }
+  double *g = sd_growth_table(A, AFF, fieldtype, LPTorder, &nm);
+  if (merged) {
+    if (LPTorder == 1) { if (pending) my_free(pending); pending = g; return; }
+    ck(mgp_assign_displacement_fields_merged(g_ctx, fieldtype, pending, g, nm), "mgp_assign_displacement_fields_merged");
+    my_free(pending); pending = NULL;
+    if (g_host_is_newer || g_host_synced) { sd_refresh_host(fieldtype, 1); sd_refresh_host(fieldtype, 2); }
+  } else {
+    ck(mgp_assign_displacement_field(g_ctx, fieldtype, LPTorder, g, nm), "mgp_assign_displacement_field");
+    if (g_host_is_newer || g_host_synced) sd_refresh_host(fieldtype, LPTorder);
+  }
+  my_free(g);
+}
+#endif
 
 /* ------------------------------------------------------------------ P(k) file (compute_pofk.c:48-64, 239-261) */
 
@@ -287,9 +359,69 @@ static void write_pofk_file(double a, const char *label, int nbins, const double
 }
 #endif
 
-void compute_RSD_powerspectrum(double A, int dDdy_set) {
-  (void) A; (void) dDdy_set;
-  if (ThisTask == 0) printf("[mgpicola-cuda] RSD multipoles are not computed by the CUDA library yet (pofk_compute_rsd_pofk ignored)\n");
+/* compute_pofk.c:403-512 */
+void compute_RSD_powerspectrum(double A, int dDdy_set_in_particles) {
+#ifdef COMPUTE_POFK
+  timer_start(_PofkComputation);
+  if (ThisTask == 0) printf("Computing the RSD power-spectrum...\n");
+  const double scaleBox = (double) Nmesh / Box;
+  const double velfac = (Hubble / A);
+  const double vnorm = velfac / (100.0 * A * hubble(A)) * scaleBox;           /* compute_pofk.c:291-292 */
+  double dDdy = 0.0, dD2dy = 0.0;
+#ifdef SCALEDEPENDENT
+  float *save1 = NULL, *save2 = NULL;
+  if (UseCOLA && !dDdy_set_in_particles) {                                    /* compute_pofk.c:409-428 */
+    int lnx, lx0, lnp, lp0; uint64_t np;
+    ck(mgp_get_layout(g_ctx, &lnx, &lx0, &lnp, &lp0, &np), "mgp_get_layout");
+    save1 = my_malloc((size_t) np * 12); save2 = my_malloc((size_t) np * 12);
+    ck(mgp_download_sd_fields(g_ctx, save1, save2), "mgp_download_sd_fields");
+    const double As = aexp_global;
+    assign_displacment_field_to_particles(As, As, As, FIELD_dDdy, LPT_ORDER_ONE);
+    assign_displacment_field_to_particles(As, As, As, FIELD_dDdy, LPT_ORDER_TWO);
+  }
+#else
+  (void) dDdy_set_in_particles;
+  dDdy = growth_dDdy(A); dD2dy = growth_dD2dy(A);
+#endif
+  static int configured = 0;
+  if (!configured) {
+    mgp_pofk_config pc = {pofk_nbins, pofk_bintype, pofk_subtract_shotnoise, pofk_kmin, pofk_kmax};
+    ck(mgp_set_pofk_config(g_ctx, &pc), "mgp_set_pofk_config");
+    configured = 1;
+  }
+  const int nb = mgp_pofk_nbins(g_ctx);
+  double *oy = my_malloc(sizeof(double) * 5 * nb), *oz = my_malloc(sizeof(double) * 5 * nb);
+  ck(mgp_compute_rsd_power_spectrum(g_ctx, vnorm, dDdy, dD2dy, oy, oz), "mgp_compute_rsd_power_spectrum");
+  if (ThisTask == 0) {                                                       /* compute_pofk.c:453-479 */
+    char filename[1000];
+    const double znow = 1.0 / A - 1.0;
+    const int zint = (int) (znow), zfrac = (int) ((znow - zint) * 1000);
+    sprintf(filename, "%s/pofk_RSD_%s_z%d.%03d.txt", OutputDir, FileBase, zint, zfrac);
+    printf("Writing RSD power-spectrum to file: [%s]\n", filename);
+    FILE *fp = fopen(filename, "w");
+    fprintf(fp, "#  k (h/Mpc)      P0 (Mpc/h)^3      P2 (Mpc/h)^3      P4 (Mpc/h)^3     sigma0     sigma2     sigma4\n");
+    for (int i = 0; i < nb; i++) {
+      if (oy[i] > 0 && oy[nb + i] > 0.0) {
+        const double P0 = (oy[2 * nb + i] + oz[2 * nb + i]) / 2.0, P2 = (oy[3 * nb + i] + oz[3 * nb + i]) / 2.0,
+                     P4 = (oy[4 * nb + i] + oz[4 * nb + i]) / 2.0;
+        fprintf(fp, "%10.5f   %10.5f   %10.5f   %10.5f   %10.5f   %10.5f   %10.5f\n", oy[nb + i], P0, P2, P4,
+                fabs(oy[2 * nb + i] - oz[2 * nb + i]) / sqrt(2.0), fabs(oy[3 * nb + i] - oz[3 * nb + i]) / sqrt(2.0),
+                fabs(oy[4 * nb + i] - oz[4 * nb + i]) / sqrt(2.0));
+      }
+    }
+    fclose(fp);
+  }
+  my_free(oy); my_free(oz);
+#ifdef SCALEDEPENDENT
+  if (save1) {                                                               /* compute_pofk.c:497-508 */
+    ck(mgp_upload_sd_fields(g_ctx, save1, save2), "mgp_upload_sd_fields");
+    my_free(save1); my_free(save2);
+  }
+#endif
+  timer_stop(_PofkComputation);
+#else
+  (void) A; (void) dDdy_set_in_particles;
+#endif
 }
 
 /* ------------------------------------------------------------------ the force path (auxPM.c:37-103) */
@@ -315,6 +447,21 @@ void GetDisplacements(void) {
     s.geff = GeffoverG(aexp_global, 0.0);
 #endif
   }
+#ifdef MASSIVE_NEUTRINOS
+  double *nutab = NULL;
+  if (nu_include_massive_neutrinos) {                                         /* auxPM.c:383-420 */
+    const int h = Nmesh / 2;
+    const size_t nm = (size_t) 3 * h * h + 1;
+    const double nufac_tmp = OmegaNu / Omega * (double) (Nmesh * Nmesh * Nmesh);
+    nutab = my_malloc(sizeof(double) * nm);
+    nutab[0] = 0.0;
+    for (size_t m = 1; m < nm; m++) {
+      const double kmag = 2.0 * PI / Box * sqrt((double) m);
+      nutab[m] = nufac_tmp * get_nu_transfer_function(kmag, aexp_global) / get_cdm_baryon_transfer_function(kmag, 1.0);
+    }
+    s.nu_by_k2 = nutab; s.n_nu = nm; s.nu_cdmfac = (Omega - OmegaNu) / Omega;
+  }
+#endif
 #ifdef COMPUTE_POFK
   s.compute_pofk = pofk_compute_every_step;
   static int pofk_configured = 0;
@@ -325,6 +472,21 @@ void GetDisplacements(void) {
   }
 #endif
   timer_start(_PtoMesh);
+#ifdef COMPUTE_POFK
+  /* the reference bins the RSD multipoles inside PtoMesh, between the CDM P(k) and the neutrino add, except in the
+   * first step of an output interval (auxPM.c:374-380 and appendix B.1 of SURVEY.md: the stale loop counter makes the
+   * test "timeStep_global == 0") */
+  const int rsd_now = (pofk_compute_rsd_pofk == 1) && !(timeStep_global == 0);
+  if (rsd_now) {
+    /* the multipoles need the particles of this step in place but not the force: run the step in two halves */
+    ck(mgp_move_particles(g_ctx), "mgp_move_particles");
+    ck(mgp_ptomesh(g_ctx, &s), "mgp_ptomesh");
+    compute_RSD_powerspectrum(aexp_global, 0);
+    ck(mgp_compute_fifth_force(g_ctx, &s), "mgp_compute_fifth_force");
+    ck(mgp_forces(g_ctx), "mgp_forces");
+    ck(mgp_mtoparticles(g_ctx, sumDxyz), "mgp_mtoparticles");
+  } else
+#endif
   ck(mgp_get_displacements(g_ctx, &s, sumDxyz), "mgp_get_displacements");
   timer_stop(_PtoMesh);
 #ifdef COMPUTE_POFK
@@ -333,8 +495,17 @@ void GetDisplacements(void) {
     double *p = my_malloc(sizeof(double) * nb), *k = my_malloc(sizeof(double) * nb), *n = my_malloc(sizeof(double) * nb);
     ck(mgp_get_step_power_spectrum(g_ctx, p, k, n), "mgp_get_step_power_spectrum");
     write_pofk_file(aexp_global, "CDM", nb, p, k, n);
+#ifdef MASSIVE_NEUTRINOS
+    if (nu_include_massive_neutrinos) {
+      ck(mgp_get_step_power_spectrum_total(g_ctx, p, k, n), "mgp_get_step_power_spectrum_total");
+      write_pofk_file(aexp_global, "total", nb, p, k, n);
+    }
+#endif
     my_free(p); my_free(k); my_free(n);
   }
+#endif
+#ifdef MASSIVE_NEUTRINOS
+  if (nutab) my_free(nutab);
 #endif
   /* main.c frees Disp[] after the kick (main.c:551, 574): hand it something to free */
   for (int j = 0; j < 3; j++) Disp[j] = my_malloc(sizeof(float));

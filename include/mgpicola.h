@@ -113,6 +113,14 @@ typedef struct mgp_step_scalars {
   /* MGP_MODEL_GEFF */
   double geff;               /* GeffoverG(a, 0) */
   int compute_pofk;          /* pofk_compute_every_step: bin P(k) of the CDM density this step */
+  /* MASSIVE_NEUTRINOS (auxPM.c:383-420): after the r2c, P3D = nu_cdmfac * P3D + nu_by_k2[m] * cdelta_cdm for every
+   * mode but (0,0,0), m = |d|^2.  nu_cdmfac = (Omega - OmegaNu) / Omega; nu_by_k2[m] = OmegaNu / Omega * Nmesh^3 *
+   * get_nu_transfer_function(k, a) / get_cdm_baryon_transfer_function(k, 1) at k = 2 pi sqrt(m) / Box.
+   * NULL: no neutrinos.  Needs scale_dependent = 1 (the stored cdelta_cdm).  With compute_pofk the "total" spectrum
+   * is binned after the add (auxPM.c:424-427) and read with mgp_get_step_power_spectrum_total. */
+  const double *nu_by_k2;
+  size_t n_nu;
+  double nu_cdmfac;
 } mgp_step_scalars;
 
 const char *mgp_last_error(void);
@@ -218,6 +226,19 @@ int mgp_pofk_nbins(mgp_ctx *ctx);
 int mgp_compute_power_spectrum(mgp_ctx *ctx, double *pofk, double *kmean, double *nmodes);
 /* result of the in-step binning requested through mgp_step_scalars.compute_pofk */
 int mgp_get_step_power_spectrum(mgp_ctx *ctx, double *pofk, double *kmean, double *nmodes);
+
+/* "total" (CDM + baryons + neutrinos) spectrum of the last step that had nu_by_k2 and compute_pofk set */
+int mgp_get_step_power_spectrum_total(mgp_ctx *ctx, double *pofk, double *kmean, double *nmodes);
+
+/* compute_RSD_powerspectrum (compute_pofk.c:403-512): redshift-space deposits along y and along z (PtoMesh_RSD,
+ * 280-393), two r2c, the P0 / P2 / P4 binning of bin_up_RSD_power_spectrum (518-753).  Uses MGP_GRID_FORCE_X as the
+ * work grid (free between PtoMesh and Forces, and in Output).
+ *   vnorm = (Hubble / A) / (100 A hubble(A)) * Nmesh / Box  (compute_pofk.c:291-292), dDdy / dD2dy = growth_dDdy(A),
+ *   growth_dD2dy(A) (ignored when scale_dependent: P.dDdy / P.dD2dy must then hold FIELD_dDdy, i.e. the caller does
+ *   what compute_pofk.c:409-428 does around the call).
+ * Outputs sized mgp_pofk_nbins(): per line of sight q in {y, z}: n, k (bin centre), P0, P2, P4 as
+ * out_y[0..4][nbins], out_z[0..4][nbins]; the file the reference writes holds their mean and |y - z| / sqrt(2). */
+int mgp_compute_rsd_power_spectrum(mgp_ctx *ctx, double vnorm, double dDdy, double dD2dy, double *out_y, double *out_z);
 
 /* ---- grid access (tests, write_grid_to_file auxPM.c:757-813) ---- */
 /* local slab incl. ghost plane: (Local_nx+1) * Nmesh * 2*(Nmesh/2+1) values of grid_bytes */

@@ -51,7 +51,8 @@ class PofkConfig(C.Structure):
 
 class StepScalars(C.Structure):
     _fields_ = [("a", C.c_double), ("phi_crit", C.c_double), ("coupling", C.c_double), ("massterm2", C.c_double),
-                ("dgp_fac0", C.c_double), ("rsmooth", C.c_double), ("geff", C.c_double), ("compute_pofk", C.c_int)]
+                ("dgp_fac0", C.c_double), ("rsmooth", C.c_double), ("geff", C.c_double), ("compute_pofk", C.c_int),
+                ("nu_by_k2", C.c_void_p), ("n_nu", C.c_size_t), ("nu_cdmfac", C.c_double)]
 
 
 _lib = None
@@ -98,6 +99,8 @@ def load_library(path=None):
     L.mgp_pofk_nbins.argtypes = [C.c_void_p]
     L.mgp_compute_power_spectrum.argtypes = [C.c_void_p, dp, dp, dp]
     L.mgp_get_step_power_spectrum.argtypes = [C.c_void_p, dp, dp, dp]
+    L.mgp_get_step_power_spectrum_total.argtypes = [C.c_void_p, dp, dp, dp]
+    L.mgp_compute_rsd_power_spectrum.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, dp, dp]
     L.mgp_grid_local_values.argtypes = [C.c_void_p]
     L.mgp_grid_local_values.restype = C.c_size_t
     L.mgp_download_grid.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -281,8 +284,14 @@ class PM:
 
     # ---- the reference's per-step functions ----
     @staticmethod
-    def scalars(a=1.0, phi_crit=0.0, coupling=0.0, massterm2=0.0, dgp_fac0=0.0, rsmooth=0.0, geff=1.0, compute_pofk=0):
-        return StepScalars(a, phi_crit, coupling, massterm2, dgp_fac0, rsmooth, geff, compute_pofk)
+    def scalars(a=1.0, phi_crit=0.0, coupling=0.0, massterm2=0.0, dgp_fac0=0.0, rsmooth=0.0, geff=1.0, compute_pofk=0,
+                nu_by_k2=None, nu_cdmfac=1.0):
+        s = StepScalars(a, phi_crit, coupling, massterm2, dgp_fac0, rsmooth, geff, compute_pofk, None, 0, nu_cdmfac)
+        if nu_by_k2 is not None:
+            s._nu = np.ascontiguousarray(nu_by_k2, dtype=np.float64)      # kept alive with the struct
+            s.nu_by_k2 = s._nu.ctypes.data
+            s.n_nu = s._nu.size
+        return s
 
     def MoveParticles(self):
         self._ck(self.L.mgp_move_particles(self.ctx))
@@ -338,6 +347,24 @@ class PM:
 
     def step_power_spectrum(self):
         return self._pofk_out(self.L.mgp_get_step_power_spectrum)
+
+    def step_power_spectrum_total(self):
+        return self._pofk_out(self.L.mgp_get_step_power_spectrum_total)
+
+    def compute_RSD_powerspectrum(self, vnorm, dDdy=0.0, dD2dy=0.0):
+        """compute_RSD_powerspectrum (compute_pofk.c:403): returns dict(k, P0, P2, P4, err0, err2, err4, n, y=..., z=...)
+        with the combination the reference writes to file (465-476)."""
+        nb = self.L.mgp_pofk_nbins(self.ctx)
+        if nb < 0:
+            raise MgpError(nb, "P(k) binning not configured")
+        oy, oz = np.zeros((5, nb)), np.zeros((5, nb))
+        dp = C.POINTER(C.c_double)
+        self._ck(self.L.mgp_compute_rsd_power_spectrum(self.ctx, vnorm, dDdy, dD2dy, oy.ctypes.data_as(dp), oz.ctypes.data_as(dp)))
+        out = dict(y=oy, z=oz, n=oy[0], k=oy[1])
+        for i, nm in ((2, "0"), (3, "2"), (4, "4")):
+            out["P" + nm] = (oy[i] + oz[i]) / 2.0
+            out["err" + nm] = np.abs(oy[i] - oz[i]) / np.sqrt(2.0)
+        return out
 
     # ---- grids ----
     def download_grid(self, gid):

@@ -106,7 +106,7 @@ static void destroy(Ctx *cp) {
   cudaFree(c.grid[0]); cudaFree(c.force_block); cudaFree(c.grid[4]); cudaFree(c.grid[5]); cudaFree(c.halo_recv);
   cudaFree(c.sd_delta[0]); cudaFree(c.sd_delta[1]);
   cudaFree(c.mig_dev); if (c.mig_host) cudaFreeHost(c.mig_host);
-  cudaFree(c.pofk_bins_d); cudaFree(c.pofk_sinc_d); cudaFree(c.pofk_out_d);
+  cudaFree(c.pofk_bins_d); cudaFree(c.pofk_sinc_d); cudaFree(c.pofk_out_d); cudaFree(c.nu_tab_d);
   if (c.pofk_out_h) cudaFreeHost(c.pofk_out_h);
   if (c.comm) ncclCommDestroy(c.comm);
   for (int d = 0; d < 4; d++) { cudaEventDestroy(c.ev[d][0]); cudaEventDestroy(c.ev[d][1]); }
@@ -152,11 +152,31 @@ static void ptomesh(Ctx &c, const mgp_step_scalars *s) {
     fft_r2c(c, MGP_GRID_DENSITY);
   }
   c.step_pofk_valid = false;
+  c.step_pofk_tot_valid = false;
   if (s && s->compute_pofk) {
     const int nb = pofk_effective_nbins(c);
     c.step_pofk.assign(nb, 0.0); c.step_kmean.assign(nb, 0.0); c.step_nmodes.assign(nb, 0.0);
     pofk_bin(c, MGP_GRID_DENSITY, c.step_pofk.data(), c.step_kmean.data(), c.step_nmodes.data());
     c.step_pofk_valid = true;
+  }
+  if (s && s->nu_by_k2) {                                   // MASSIVE_NEUTRINOS (auxPM.c:383-420)
+    { PhaseTimer t(c, PH_PTOMESH); kspace_nu_add(c, s->nu_by_k2, s->n_nu, s->nu_cdmfac); }
+    if (s->compute_pofk) {                                  // "total" P(k) (auxPM.c:424-427)
+      const int nb = pofk_effective_nbins(c);
+      c.step_pofk_tot.assign(nb, 0.0); c.step_kmean_tot.assign(nb, 0.0); c.step_nmodes_tot.assign(nb, 0.0);
+      pofk_bin(c, MGP_GRID_DENSITY, c.step_pofk_tot.data(), c.step_kmean_tot.data(), c.step_nmodes_tot.data());
+      c.step_pofk_tot_valid = true;
+    }
+  }
+}
+
+static void rsd_power_spectrum(Ctx &c, double vnorm, double dDdy, double dD2dy, double *out_y, double *out_z) {
+  REQUIRE(out_y && out_z, MGP_ERR_INVALID, "mgp_compute_rsd_power_spectrum: NULL output");
+  for (int axis = 1; axis <= 2; axis++) {                   // YAXIS then ZAXIS (compute_pofk.c:437-448)
+    deposit_rsd(c, MGP_GRID_FORCE_X, axis, vnorm, dDdy, dD2dy);
+    halo_add_density(c, MGP_GRID_FORCE_X);
+    fft_r2c(c, MGP_GRID_FORCE_X);
+    pofk_bin_rsd(c, MGP_GRID_FORCE_X, axis == 1 ? out_y : out_z);
   }
 }
 
@@ -512,6 +532,24 @@ int mgp_get_step_power_spectrum(mgp_ctx *ctx, double *pofk, double *kmean, doubl
   if (pofk) memcpy(pofk, c.step_pofk.data(), nb * sizeof(double));
   if (kmean) memcpy(kmean, c.step_kmean.data(), nb * sizeof(double));
   if (nmodes) memcpy(nmodes, c.step_nmodes.data(), nb * sizeof(double));
+  API_END
+}
+
+int mgp_get_step_power_spectrum_total(mgp_ctx *ctx, double *pofk, double *kmean, double *nmodes) {
+  API_BEGIN
+  CTX(ctx);
+  REQUIRE(c.step_pofk_tot_valid, MGP_ERR_STATE, "no total-matter P(k) available (set nu_by_k2 and compute_pofk)");
+  const size_t nb = c.step_pofk_tot.size();
+  if (pofk) memcpy(pofk, c.step_pofk_tot.data(), nb * sizeof(double));
+  if (kmean) memcpy(kmean, c.step_kmean_tot.data(), nb * sizeof(double));
+  if (nmodes) memcpy(nmodes, c.step_nmodes_tot.data(), nb * sizeof(double));
+  API_END
+}
+
+int mgp_compute_rsd_power_spectrum(mgp_ctx *ctx, double vnorm, double dDdy, double dD2dy, double *out_y, double *out_z) {
+  API_BEGIN
+  CTX(ctx);
+  rsd_power_spectrum(c, vnorm, dDdy, dD2dy, out_y, out_z);
   API_END
 }
 

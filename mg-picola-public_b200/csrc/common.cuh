@@ -141,6 +141,9 @@ struct Ctx {
   bool pofk_set = false;
   std::vector<double> step_pofk, step_kmean, step_nmodes;
   bool step_pofk_valid = false;
+  std::vector<double> step_pofk_tot, step_kmean_tot, step_nmodes_tot;   // "total" P(k) after the neutrino add
+  bool step_pofk_tot_valid = false;
+  double *nu_tab_d = nullptr;
   int *pofk_bins_d = nullptr;                 // bin index of every integer |d|^2
   double *pofk_sinc_d = nullptr, *pofk_out_d = nullptr, *pofk_out_h = nullptr;
   bool pofk_tables_valid = false;
@@ -200,6 +203,7 @@ void particles_after_drift(Ctx &c);
 // deposit.cu
 void deposit_density(Ctx &c, int grid_id);
 void gather_forces(Ctx &c, double sumD[3]);
+void deposit_rsd(Ctx &c, int grid_id, int axis, double vnorm, double dDdy, double dD2dy);
 // fft.cu
 void fft_setup(Ctx &c);
 void fft_teardown(Ctx &c);
@@ -220,6 +224,8 @@ void real_copy(Ctx &c, int dst_grid, int src_grid, double scale);
 void real_screen_potential(Ctx &c, double phi_crit, bool screening);
 void real_screen_density(Ctx &c, double coupling, double fac0, double stats[3]);
 void pofk_bin(Ctx &c, int grid_id, double *pofk, double *kmean, double *nmodes);
+void pofk_bin_rsd(Ctx &c, int grid_id, double *out5);
+void kspace_nu_add(Ctx &c, const double *nufac_host, size_t n, double cdmfac);
 int pofk_effective_nbins(const Ctx &c);
 
 // ic.cu

@@ -294,6 +294,90 @@ static void deposit_t(Ctx &c, int gid) {
   c.launches++;
 }
 
+// ------------------------------------------------------------------ redshift-space deposit (PtoMesh_RSD, compute_pofk.c:280-393)
+
+// Line of sight = y (axis 1: y and z swap roles) or z (axis 2).  The velocity shift leaves the x-slab of a
+// particle unchanged, which is why the reference skips the x axis (compute_pofk.c:450-451).
+//   V = Vel[axis] + COLA LPT velocity;  Z += V * vnorm;  one periodic wrap;  CIC as PtoMesh
+// SD = 1: the LPT velocity is P.dDdy + P.dD2dy (float add, compute_pofk.c:321); else D dDdy + D2 dD2dy (double).
+template <typename T, int SD>
+__global__ void __launch_bounds__(256)
+k_deposit_rsd(size_t n, const float4 *__restrict__ pA, const float4 *__restrict__ pB, const float4 *__restrict__ pC,
+              const float2 *__restrict__ pE, const float *__restrict__ s1, const float *__restrict__ s2, size_t cap,
+              T *__restrict__ grid, int N, int NZ, int nx, int x0, int single_rank, double scale, double W, int axis,
+              int usecola, double vnorm, double dDdy, double dD2dy) {
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+    const float4 p = pA[i], v = pB[i];
+    const double X = (double) p.x * scale;
+    const double Y = (double) (axis == 1 ? p.z : p.y) * scale;
+    double Z = (double) (axis == 1 ? p.y : p.z) * scale;
+    const float vel = axis == 1 ? v.y : v.z;
+    double V;
+    if (!usecola) {
+      V = (double) vel;
+    } else if (SD) {
+      const float a = s1[(size_t) axis * cap + i], b = s2 ? s2[(size_t) axis * cap + i] : 0.0f;
+      V = (double) __fadd_rn(vel, __fadd_rn(a, b));
+    } else {
+      const float4 d = pC[i];
+      const float2 e = pE[i];
+      const double d1 = (double) (axis == 1 ? d.y : d.z), d2 = (double) (axis == 1 ? e.x : e.y);
+      V = __dadd_rn((double) vel, __dadd_rn(__dmul_rn(d1, dDdy), __dmul_rn(d2, dD2dy)));
+    }
+    V *= vnorm;
+    Z += V;
+    if (Z >= (double) N) Z -= (double) N;
+    if (Z < 0) Z += (double) N;
+    unsigned ix = (unsigned) X, iy = (unsigned) Y, iz = (unsigned) Z;
+    const double dx = X - (double) ix, dz = Z - (double) iz;
+    double dy = Y - (double) iy;
+    const double tx = 1.0 - dx, tz = 1.0 - dz;
+    double ty = 1.0 - dy;
+    dy *= W; ty *= W;
+    const unsigned lx = ix - (unsigned) x0;
+    if (iy >= (unsigned) N) iy = 0;
+    if (iz >= (unsigned) N) iz = 0;
+    unsigned lx1 = lx + 1;
+    if (single_rank && lx1 == (unsigned) nx) lx1 = 0;
+    const unsigned iy1 = (iy + 1 == (unsigned) N) ? 0 : iy + 1, iz1 = (iz + 1 == (unsigned) N) ? 0 : iz + 1;
+    const size_t rz = (size_t) 2 * NZ;
+    T *r00 = grid + ((size_t) lx * N + iy) * rz, *r01 = grid + ((size_t) lx * N + iy1) * rz;
+    T *r10 = grid + ((size_t) lx1 * N + iy) * rz, *r11 = grid + ((size_t) lx1 * N + iy1) * rz;
+    atomicAdd(r00 + iz, (T) (tx * ty * tz)); atomicAdd(r00 + iz1, (T) (tx * ty * dz));
+    atomicAdd(r01 + iz, (T) (tx * dy * tz)); atomicAdd(r01 + iz1, (T) (tx * dy * dz));
+    atomicAdd(r10 + iz, (T) (dx * ty * tz)); atomicAdd(r10 + iz1, (T) (dx * ty * dz));
+    atomicAdd(r11 + iz, (T) (dx * dy * tz)); atomicAdd(r11 + iz1, (T) (dx * dy * dz));
+  }
+}
+
+template <typename T>
+static void deposit_rsd_t(Ctx &c, int gid, int axis, double vnorm, double dDdy, double dD2dy) {
+  T *grid = (T *) c.grid[gid];
+  const double scale = (double) c.N / c.cfg.box;
+  const double r = (double) c.N / (double) c.cfg.nsample;
+  const double W = r * r * r;
+  k_fill<T><<<grid_for(c.grid_vals, 256), 256, 0, c.stream>>>(grid, c.grid_vals, (T) -1.0);
+  c.launches++;
+  if (!c.np) return;
+  const unsigned g = grid_for(c.np, 256);
+  if (c.cfg.scale_dependent)
+    k_deposit_rsd<T, 1><<<g, 256, 0, c.stream>>>(c.np, c.pA, c.pB, nullptr, nullptr, c.sdf[2], c.sd_zero[3] ? nullptr : c.sdf[3], c.cap,
+                                                grid, c.N, c.NZ, c.nx, c.x0, c.P == 1, scale, W, axis, c.cfg.use_cola, vnorm, dDdy, dD2dy);
+  else
+    k_deposit_rsd<T, 0><<<g, 256, 0, c.stream>>>(c.np, c.pA, c.pB, c.pC, (const float2 *) c.pE, nullptr, nullptr, c.cap, grid, c.N,
+                                                c.NZ, c.nx, c.x0, c.P == 1, scale, W, axis, c.cfg.use_cola, vnorm, dDdy, dD2dy);
+  c.launches++;
+}
+
+void deposit_rsd(Ctx &c, int grid_id, int axis, double vnorm, double dDdy, double dD2dy) {
+  PhaseTimer t(c, PH_PTOMESH);
+  REQUIRE(axis == 1 || axis == 2, MGP_ERR_INVALID, "redshift-space line of sight must be y (1) or z (2)");
+  if (c.cfg.scale_dependent && c.cfg.use_cola)
+    REQUIRE(c.sd_set[2] && c.sd_set[3], MGP_ERR_STATE, "RSD P(k) (scale-dependent): assign FIELD_dDdy first");
+  if (c.gbytes == 4) deposit_rsd_t<float>(c, grid_id, axis, vnorm, dDdy, dD2dy);
+  else deposit_rsd_t<double>(c, grid_id, axis, vnorm, dDdy, dD2dy);
+}
+
 void deposit_density(Ctx &c, int grid_id) {
   if (c.gbytes == 4) deposit_t<float>(c, grid_id); else deposit_t<double>(c, grid_id);
 }

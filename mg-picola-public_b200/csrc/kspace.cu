@@ -194,6 +194,43 @@ void real_screen_density(Ctx &c, double coupling, double fac0, double stats[3]) 
   }
 }
 
+// ------------------------------------------------------------------ massive neutrinos (auxPM.c:383-420)
+
+// P3D = cdmfac * P3D + nufac(|k|) * cdelta_cdm for every mode but (0,0,0); nufac[m], m = |d|^2, is
+// OmegaNu/Omega * Nmesh^3 * T_nu(k, a) / T_cb(k, 1) filled by the driver from its CAMB splines
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_nu_add(KL L, typename Cpx<T>::type *__restrict__ p3d, const typename Cpx<T>::type *__restrict__ d1,
+         const double *__restrict__ nufac, double cdmfac) {
+  typedef typename Cpx<T>::type C;
+  const int N = L.N;
+  KLOOP(e, L) {
+    int i, j, k;
+    kl_decode(L, e, i, j, k);
+    if (i == 0 && j == 0 && k == 0) continue;
+    const int d0 = i > N / 2 ? N - i : i, d1i = j > N / 2 ? N - j : j;
+    const double nf = nufac[(long long) d0 * d0 + (long long) d1i * d1i + (long long) k * k];
+    C v = p3d[e];
+    const C w = d1[e];
+    v.x = (T) (cdmfac * (double) v.x + nf * (double) w.x);
+    v.y = (T) (cdmfac * (double) v.y + nf * (double) w.y);
+    p3d[e] = v;
+  }
+}
+
+void kspace_nu_add(Ctx &c, const double *nufac_host, size_t n, double cdmfac) {
+  const size_t mmax = (size_t) 3 * (c.N / 2) * (c.N / 2) + 1;
+  REQUIRE(nufac_host != nullptr && n >= mmax, MGP_ERR_INVALID, "neutrino table must hold 3 (Nmesh/2)^2 + 1 entries");
+  REQUIRE(c.sd_delta[0] && c.sd_have_delta, MGP_ERR_STATE, "massive neutrinos need the stored delta_cdm(k) (scale_dependent = 1 and mgp_ic_generate)");
+  if (!c.nu_tab_d) CK(cudaMalloc(&c.nu_tab_d, mmax * sizeof(double)));
+  CK(cudaMemcpyAsync(c.nu_tab_d, nufac_host, mmax * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+  const KL L = layout_of(c);
+  const unsigned g = grid_for(L.total, 256);
+  if (c.gbytes == 4) k_nu_add<float><<<g, 256, 0, c.stream>>>(L, (float2 *) c.grid[0], (const float2 *) c.sd_delta[0], c.nu_tab_d, cdmfac);
+  else k_nu_add<double><<<g, 256, 0, c.stream>>>(L, (double2 *) c.grid[0], (const double2 *) c.sd_delta[0], c.nu_tab_d, cdmfac);
+  c.launches++;
+}
+
 // ------------------------------------------------------------------ P(k)
 
 // The reference's parameter sanitiser (compute_pofk.c:758-805), in integer-k units.
@@ -223,12 +260,14 @@ static int bin_index(double kmag, double kmin, double kmax, int nbins, int binty
   return (int) (log(kmag / kmin) / log(kmax / kmin) * nbins + 0.5);
 }
 
-template <typename T>
+// RSD = 1 adds the mu^2 and mu^4 moments of bin_up_RSD_power_spectrum (compute_pofk.c:518-753), mu^2 = kz^2 / k^2
+template <typename T, int RSD>
 __global__ void __launch_bounds__(256)
 k_pofk(KL L, const typename Cpx<T>::type *__restrict__ dk, const int *__restrict__ bin_of_m,
        const double *__restrict__ sinc, int nbins, double norm, double *__restrict__ out) {
-  extern __shared__ double sb[];     // [3][nbins]: sum P, sum k, sum n
-  for (int b = threadIdx.x; b < 3 * nbins; b += blockDim.x) sb[b] = 0.0;
+  extern __shared__ double sb[];     // [3 (+2)][nbins]: sum P, sum k, sum n (, sum P mu^2, sum P mu^4)
+  constexpr int NS = RSD ? 5 : 3;
+  for (int b = threadIdx.x; b < NS * nbins; b += blockDim.x) sb[b] = 0.0;
   __syncthreads();
   typedef typename Cpx<T>::type C;
   const int N = L.N;
@@ -250,19 +289,24 @@ k_pofk(KL L, const typename Cpx<T>::type *__restrict__ dk, const int *__restrict
       atomicAdd(&sb[nk], w * p);
       atomicAdd(&sb[nbins + nk], w * kmag);
       atomicAdd(&sb[2 * nbins + nk], w);
+      if (RSD) {
+        // mu2 = d[2]*d[2]/kmag/kmag; the (0,0,0) mode has mu2 = 0 (compute_pofk.c:601-602)
+        const double mu2 = m == 0 ? 0.0 : (double) ((long long) d2 * d2) / kmag / kmag;
+        atomicAdd(&sb[3 * nbins + nk], w * p * mu2);
+        atomicAdd(&sb[4 * nbins + nk], w * p * mu2 * mu2);
+      }
     }
   }
   __syncthreads();
-  for (int b = threadIdx.x; b < 3 * nbins; b += blockDim.x)
+  for (int b = threadIdx.x; b < NS * nbins; b += blockDim.x)
     if (sb[b] != 0.0) atomicAdd(&out[b], sb[b]);
 }
 
-void pofk_bin(Ctx &c, int gid, double *pofk, double *kmean, double *nmodes) {
-  PhaseTimer t(c, PH_POFK);
+// raw per-bin sums [ns][nbins] (ns = 3, or 5 with the RSD moments) in c.pofk_out_h, all-reduced over the ranks
+static void pofk_sums(Ctx &c, int gid, bool rsd, int &nbins, int &bintype, int &shot, double &kmin, double &kmax) {
   REQUIRE(c.pofk_set, MGP_ERR_STATE, "P(k) requested but mgp_set_pofk_config was never called");
-  int nbins, bintype, shot; double kmin, kmax;
   adjust_pofk(c, nbins, bintype, shot, kmin, kmax);
-  REQUIRE((size_t) 3 * nbins * sizeof(double) <= 200 * 1024, MGP_ERR_INVALID, "pofk_nbins too large");
+  REQUIRE((size_t) 5 * nbins * sizeof(double) <= 200 * 1024, MGP_ERR_INVALID, "pofk_nbins too large");
   const int N = c.N, h = N / 2;
   const size_t mmax = (size_t) 3 * h * h + 1;
   // bin-of-|d|^2 and sinc tables live on the device until the binning parameters change
@@ -276,8 +320,8 @@ void pofk_bin(Ctx &c, int gid, double *pofk, double *kmean, double *nmodes) {
     if (c.pofk_bins_d) { CK(cudaFree(c.pofk_bins_d)); CK(cudaFree(c.pofk_sinc_d)); CK(cudaFree(c.pofk_out_d)); CK(cudaFreeHost(c.pofk_out_h)); }
     CK(cudaMalloc(&c.pofk_bins_d, mmax * sizeof(int)));
     CK(cudaMalloc(&c.pofk_sinc_d, (h + 1) * sizeof(double)));
-    CK(cudaMalloc(&c.pofk_out_d, (size_t) 3 * nbins * sizeof(double)));
-    CK(cudaMallocHost(&c.pofk_out_h, (size_t) 3 * nbins * sizeof(double)));
+    CK(cudaMalloc(&c.pofk_out_d, (size_t) 5 * nbins * sizeof(double)));
+    CK(cudaMallocHost(&c.pofk_out_h, (size_t) 5 * nbins * sizeof(double)));
     CK(cudaMemcpyAsync(c.pofk_bins_d, bins.data(), mmax * sizeof(int), cudaMemcpyHostToDevice, c.stream));
     CK(cudaMemcpyAsync(c.pofk_sinc_d, sinc.data(), (h + 1) * sizeof(double), cudaMemcpyHostToDevice, c.stream));
     CK(cudaStreamSynchronize(c.stream));
@@ -285,24 +329,32 @@ void pofk_bin(Ctx &c, int gid, double *pofk, double *kmean, double *nmodes) {
     c.pofk_tab_nbins = nbins; c.pofk_tab_bintype = bintype; c.pofk_tab_kmin = kmin; c.pofk_tab_kmax = kmax;
   }
   int *d_bins = c.pofk_bins_d; double *d_sinc = c.pofk_sinc_d, *d_out = c.pofk_out_d;
-  CK(cudaMemsetAsync(d_out, 0, (size_t) 3 * nbins * sizeof(double), c.stream));
+  const int ns = rsd ? 5 : 3;
+  CK(cudaMemsetAsync(d_out, 0, (size_t) ns * nbins * sizeof(double), c.stream));
   const KL L = layout_of(c);
   const double n3 = (double) N * (double) N * (double) N;
   const double norm = 1.0 / (n3 * n3);                      // 1/pow(Nmesh,6)
-  const size_t sm = (size_t) 3 * nbins * sizeof(double);
+  const size_t sm = (size_t) ns * nbins * sizeof(double);
   const unsigned g = grid_for(L.total, 256, 4);
-  if (c.gbytes == 4) {
-    CK(cudaFuncSetAttribute(k_pofk<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
-    k_pofk<float><<<g, 256, sm, c.stream>>>(L, (const float2 *) c.grid[gid], d_bins, d_sinc, nbins, norm, d_out);
-  } else {
-    CK(cudaFuncSetAttribute(k_pofk<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
-    k_pofk<double><<<g, 256, sm, c.stream>>>(L, (const double2 *) c.grid[gid], d_bins, d_sinc, nbins, norm, d_out);
-  }
+#define LAUNCH_POFK(T, C2, R)                                                                                         \
+  do {                                                                                                                \
+    CK(cudaFuncSetAttribute(k_pofk<T, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));                    \
+    k_pofk<T, R><<<g, 256, sm, c.stream>>>(L, (const C2 *) c.grid[gid], d_bins, d_sinc, nbins, norm, d_out);          \
+  } while (0)
+  if (c.gbytes == 4) { if (rsd) LAUNCH_POFK(float, float2, 1); else LAUNCH_POFK(float, float2, 0); }
+  else { if (rsd) LAUNCH_POFK(double, double2, 1); else LAUNCH_POFK(double, double2, 0); }
+#undef LAUNCH_POFK
   c.launches++;
-  allreduce_sum(c, d_out, 3 * nbins);
-  double *hout = c.pofk_out_h;
-  CK(cudaMemcpyAsync(hout, d_out, (size_t) 3 * nbins * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+  allreduce_sum(c, d_out, ns * nbins);
+  CK(cudaMemcpyAsync(c.pofk_out_h, d_out, (size_t) ns * nbins * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
   CK(cudaStreamSynchronize(c.stream));
+}
+
+void pofk_bin(Ctx &c, int gid, double *pofk, double *kmean, double *nmodes) {
+  PhaseTimer t(c, PH_POFK);
+  int nbins, bintype, shot; double kmin, kmax;
+  pofk_sums(c, gid, false, nbins, bintype, shot, kmin, kmax);
+  const double *hout = c.pofk_out_h;
   // normalise and subtract shot noise (compute_pofk.c:230-236)
   const double box3 = pow(c.cfg.box, 3);
   const double shotv = pow(c.cfg.box / (double) c.cfg.nsample, 3);
@@ -317,6 +369,30 @@ void pofk_bin(Ctx &c, int gid, double *pofk, double *kmean, double *nmodes) {
     if (pofk) pofk[b] = p;
     if (kmean) kmean[b] = km;
     if (nmodes) nmodes[b] = nb;
+  }
+}
+
+// bin_up_RSD_power_spectrum (compute_pofk.c:518-753): out[0..4][nbins] = n, k (bin centre, k_from_index), P0, P2, P4
+void pofk_bin_rsd(Ctx &c, int gid, double *out) {
+  PhaseTimer t(c, PH_POFK);
+  int nbins, bintype, shot; double kmin, kmax;
+  pofk_sums(c, gid, true, nbins, bintype, shot, kmin, kmax);
+  const double *h = c.pofk_out_h;
+  const double box3 = pow(c.cfg.box, 3);
+  const double shotv = pow(c.cfg.box / (double) c.cfg.nsample, 3);
+  for (int b = 0; b < nbins; b++) {
+    const double nb = h[2 * nbins + b];
+    double p0 = 0, p2 = 0, p4 = 0, kb = 0;
+    if (nb > 0) {
+      p0 = (h[b] / nb) * box3; p2 = (h[3 * nbins + b] / nb) * box3; p4 = (h[4 * nbins + b] / nb) * box3;
+      p4 = 9.0 * (35.0 * p4 - 30.0 * p2 + 3.0 * p0) / 8.0;     // powers of mu -> Legendre combinations, in this order (708-710)
+      p2 = 5.0 * (3.0 * p2 - 1.0 * p0) / 2.0;
+      if (shot) { p0 -= shotv; p2 -= shotv; p4 -= shotv; }      // all three, as the reference does (712-716)
+      const double kk = bintype == 0 ? kmin + (kmax - kmin) / (double) nbins * b
+                                     : exp(log(kmin) + log(kmax / kmin) / (double) nbins * b);   // k_from_index (50-64)
+      kb = kk * 2.0 * M_PI / c.cfg.box;
+    }
+    out[b] = nb; out[nbins + b] = kb; out[2 * nbins + b] = p0; out[3 * nbins + b] = p2; out[4 * nbins + b] = p4;
   }
 }
 

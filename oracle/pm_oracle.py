@@ -478,3 +478,135 @@ def init_particles_sd(D, D2, dDdy, dD2dy, nsample, box, use_cola):
     vel = np.zeros_like(pos) if use_cola else (dDdy.astype(np.float32) + dD2dy.astype(np.float32)).astype(np.float32)
     ids = (q[:, 0].astype(np.uint64) * Ns + q[:, 1].astype(np.uint64)) * Ns + q[:, 2].astype(np.uint64)
     return pos, vel, ids
+
+
+# ----------------------------------------------------------------------------- massive neutrinos (auxPM.c:383-420)
+
+def nu_add(P3D, cdelta_cdm, nufac_by_k2, cdmfac, nmesh):
+    """P3D = cdmfac * P3D + nufac(|k|) * cdelta_cdm for all modes but (0,0,0); nufac_by_k2[m] at m = |d|^2 is
+    OmegaNu / Omega * Nmesh^3 * T_nu(k, a) / T_cb(k, 1) (auxPM.c:394, 407)."""
+    RK = _rk(nmesh).astype(np.int64)
+    nf = np.asarray(nufac_by_k2, dtype=np.float64)[RK]
+    out = cdmfac * P3D + nf * cdelta_cdm
+    out[0, 0, 0] = P3D[0, 0, 0]
+    return out
+
+
+# ----------------------------------------------------------------------------- redshift-space multipoles (compute_pofk.c:280-753)
+
+def ptomesh_rsd_deposit(pos, V, axis, vnorm, nmesh, nsample, box, grid_dtype=np.float64):
+    """PtoMesh_RSD (compute_pofk.c:280-393), single task.  V = the line-of-sight velocity per particle as the
+    reference forms it (double): Vel[axis] (+ the COLA LPT velocity).  axis 1 = y (y and z swap roles), 2 = z."""
+    N = nmesh
+    nzp = 2 * (N // 2 + 1)
+    scale = np.float64(N) / np.float64(box)
+    wpar = (np.float64(N) / np.float64(nsample)) ** 3
+    X = pos[:, 0].astype(np.float64) * scale
+    if axis == 1:
+        Y = pos[:, 2].astype(np.float64) * scale
+        Z = pos[:, 1].astype(np.float64) * scale
+    else:
+        Y = pos[:, 1].astype(np.float64) * scale
+        Z = pos[:, 2].astype(np.float64) * scale
+    Z = Z + np.asarray(V, dtype=np.float64) * vnorm
+    Z = np.where(Z >= N, Z - N, Z)
+    Z = np.where(Z < 0, Z + N, Z)
+    IX, IY, IZ = X.astype(np.uint32).astype(np.int64), Y.astype(np.uint32).astype(np.int64), Z.astype(np.uint32).astype(np.int64)
+    DX, DY, DZ = X - IX, Y - IY, Z - IZ
+    TX, TY, TZ = 1.0 - DX, 1.0 - DY, 1.0 - DZ
+    DY = DY * wpar
+    TY = TY * wpar
+    IY[IY >= N] = 0
+    IZ[IZ >= N] = 0
+    IXn, IYn, IZn = IX + 1, IY + 1, IZ + 1
+    IYn[IYn >= N] = 0
+    IZn[IZn >= N] = 0
+    size = (N + 1) * N * nzp
+    grid = np.zeros(size, dtype=np.float64)
+    for ix, wx in ((IX, TX), (IXn, DX)):
+        for iy, wy in ((IY, TY), (IYn, DY)):
+            for iz, wz in ((IZ, TZ), (IZn, DZ)):
+                grid += np.bincount((ix * N + iy) * nzp + iz, weights=wx * wy * wz, minlength=size)
+    grid = (grid - 1.0).astype(grid_dtype).reshape(N + 1, N, nzp)
+    grid[0] += (grid[N] + grid_dtype(1.0)).astype(grid_dtype)
+    return np.ascontiguousarray(grid[:N])
+
+
+def bin_up_rsd_sums(dens_k, nmesh, box, nbins, bintype, subtract_shotnoise, kmin_hmpc, kmax_hmpc):
+    """The five per-bin sums of bin_up_RSD_power_spectrum before normalisation (compute_pofk.c:568-690):
+    returns (pofk0, pofk2, pofk4, n, k) arrays and the adjusted (nbins, bintype, shot, kmin, kmax)."""
+    N = nmesh
+    nbins, bintype, shot, kmin, kmax = adjust_pofk_parameters(N, box, nbins, bintype, subtract_shotnoise, kmin_hmpc, kmax_hmpc)
+    i = np.arange(N)
+    dxy = np.where(i > N // 2, N - i, i)
+    dz = np.arange(N // 2 + 1)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        gxy = np.where(dxy == 0, 1.0, np.sin((PI * dxy) / float(N)) / ((PI * dxy) / float(N)))
+        gz = np.where(dz == 0, 1.0, np.sin((PI * dz) / float(N)) / ((PI * dz) / float(N)))
+    gz[N // 2] = 2.0 / PI
+    m = (dxy[:, None, None] ** 2 + dxy[None, :, None] ** 2 + dz[None, None, :] ** 2).astype(np.float64)
+    kmag = np.sqrt(m)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        mu2 = (dz[None, None, :] ** 2).astype(np.float64) / kmag / kmag
+    mu2[0, 0, 0] = 0.0
+    nk = pofk_bin_index(kmag, kmin, kmax, nbins, bintype)
+    corr = 1.0 / (gxy[:, None, None] * gxy[None, :, None] * gz[None, None, :]) ** 4.0 * (1.0 / np.float64(N) ** 6)
+    p = (dens_k.real * dens_k.real + dens_k.imag * dens_k.imag) * corr
+    w = np.full(N // 2 + 1, 2.0)
+    w[0] = 1.0
+    w[N // 2] = 1.0
+    w = np.broadcast_to(w[None, None, :], p.shape)
+    ok = (nk >= 0) & (nk < nbins)
+    mu2 = np.broadcast_to(mu2, p.shape)
+
+    def acc(v):
+        return np.bincount(nk[ok], weights=v[ok], minlength=nbins)
+    return (acc(w * p), acc(w * p * mu2), acc(w * p * mu2 * mu2), acc(w), acc(w * kmag)), (nbins, bintype, shot, kmin, kmax)
+
+
+def rsd_multipoles(sums, cfg, box, nsample):
+    """Normalisation, Legendre combinations, shot noise on all three, bin-centre k (compute_pofk.c:699-725)."""
+    p0s, p2s, p4s, n, ks = sums
+    nbins, bintype, shot, kmin, kmax = cfg
+    good = n > 0
+    P0, P2, P4, k = np.zeros(nbins), np.zeros(nbins), np.zeros(nbins), np.zeros(nbins)
+    b3 = box ** 3
+    p0 = p0s[good] / n[good] * b3
+    p2 = p2s[good] / n[good] * b3
+    p4 = p4s[good] / n[good] * b3
+    p4 = 9.0 * (35.0 * p4 - 30.0 * p2 + 3.0 * p0) / 8.0
+    p2 = 5.0 * (3.0 * p2 - 1.0 * p0) / 2.0
+    if shot:
+        sn = (box / float(nsample)) ** 3
+        p0, p2, p4 = p0 - sn, p2 - sn, p4 - sn
+    idx = np.arange(nbins)[good]
+    if bintype == 0:
+        kk = kmin + (kmax - kmin) / float(nbins) * idx
+    else:
+        kk = np.exp(np.log(kmin) + np.log(kmax / kmin) / float(nbins) * idx)
+    P0[good], P2[good], P4[good], k[good] = p0, p2, p4, kk * 2.0 * np.pi / box
+    return n, k, P0, P2, P4
+
+
+def compute_rsd_powerspectrum(pos, Vy, Vz, vnorm, nmesh, nsample, box, pofk, grid_dtype=np.float64):
+    """compute_RSD_powerspectrum (compute_pofk.c:403-512): lines of sight y then z.  Returns the two per-axis
+    results (n, k, P0, P2, P4) and the raw sums."""
+    out = {}
+    for name, axis, V in (("y", 1, Vy), ("z", 2, Vz)):
+        dens = ptomesh_rsd_deposit(pos, V, axis, vnorm, nmesh, nsample, box, grid_dtype)
+        dk = r2c(dens, nmesh)
+        sums, cfg = bin_up_rsd_sums(dk, nmesh, box, **pofk)
+        out[name] = rsd_multipoles(sums, cfg, box, nsample)
+        out[name + "_sums"] = sums
+    return out
+
+
+def rsd_velocity(vel, D, D2, axis, use_cola, dDdy, dD2dy, scale_dependent=False):
+    """The line-of-sight velocity of PtoMesh_RSD (compute_pofk.c:320-327): SCALEDEPENDENT: D, D2 are P.dDdy, P.dD2dy
+    and the sum is float arithmetic; else Vel + (D dDdy + D2 dD2dy) in double."""
+    v = vel[:, axis]
+    if not use_cola:
+        return v.astype(np.float64)
+    if scale_dependent:
+        return (v + (D[:, axis] + D2[:, axis]).astype(np.float32)).astype(np.float32).astype(np.float64)
+    return v.astype(np.float64) + (D[:, axis].astype(np.float64) * dDdy + D2[:, axis].astype(np.float64) * dD2dy)

@@ -77,3 +77,45 @@ def test_driver_with_cuda_library_matches_cpu_reference(require_gpu, tmp_path, v
     dp = np.minimum(dp, box - dp)
     assert dp.max() < tolx * box / N
     assert np.abs(vc[oc] - vg[og]).max() < tolx * np.abs(vc).max() * 10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant,merged", [("fofr", 0), ("fofr", 1), ("dgp_sd", 0)])
+def test_scale_dependent_driver_matches_cpu_reference(require_gpu, tmp_path, variant, merged):
+    """SCALEDEPENDENT builds (MODEL=FOFR, DGP -DSCALEDEPENDENT) with use_lcdm_growth_factors = 0 and RSD multipoles
+    every step: the driver's own assign_displacment_field_to_particles / compute_RSD_powerspectrum call sites,
+    served by the CUDA library, against the unmodified CPU reference."""
+    import bench
+    N, box, nsteps = 32, 100.0, 5
+    model = "fofr" if variant == "fofr" else "dgp"
+    runs = {}
+    for kind in ("cpu", "gpu"):
+        wd = str(tmp_path / kind)
+        pf = bench.write_paramfile(wd, N, box, model, nsteps, lcdm_growth=0)
+        open(pf, "w").write(open(pf).read().replace("pofk_compute_rsd_pofk 0", "pofk_compute_rsd_pofk 1"))
+        env = dict(os.environ, MGP_SD_MERGED=str(merged))
+        r = subprocess.run([_exe(kind, variant), pf], capture_output=True, text=True, cwd=wd, timeout=900, env=env)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        runs[kind] = wd
+    out_c, out_g = os.path.join(runs["cpu"], "output"), os.path.join(runs["gpu"], "output")
+    shot = (box / N) ** 3
+    for suffix, ncol in (("_CDM.txt", 4), (".txt", 7)):
+        fc = sorted(f for f in os.listdir(out_c) if f.startswith("pofk_") and f.endswith(suffix) and (ncol == 4 or "RSD" in f))
+        fg = sorted(f for f in os.listdir(out_g) if f.startswith("pofk_") and f.endswith(suffix) and (ncol == 4 or "RSD" in f))
+        assert fc == fg and len(fc) >= nsteps - 1
+        for f in fc:
+            a = np.loadtxt(os.path.join(out_c, f), comments="#").reshape(-1, ncol)
+            b = np.loadtxt(os.path.join(out_g, f), comments="#").reshape(-1, ncol)
+            assert a.shape == b.shape and np.array_equal(a[:, 0], b[:, 0])
+            for col in range(1, 4):          # P(k) [, k_mean, Delta] or P0, P2, P4: print resolution + 1e-6 relative
+                assert np.all(np.abs(a[:, col] - b[:, col]) <= 2e-5 + 1e-6 * (np.abs(a[:, col]) + shot)), (f, col)
+    snap = [f for f in os.listdir(out_c) if f.startswith("bench_z0p000")]
+    assert snap
+    pc, vc, ic = read_gadget(os.path.join(out_c, snap[0]))
+    pg, vg, ig = read_gadget(os.path.join(out_g, snap[0]))
+    oc, og = np.argsort(ic), np.argsort(ig)
+    assert np.array_equal(ic[oc], ig[og])
+    dp = np.abs(pc[oc].astype(np.float64) - pg[og])
+    dp = np.minimum(dp, box - dp)
+    assert dp.max() < 3e-5 * box / N
+    assert np.abs(vc[oc] - vg[og]).max() < 3e-4 * np.abs(vc).max()

@@ -214,3 +214,85 @@ def L_mg_ratio(L, k):
 
 if __name__ == "__main__" and "--sd" in sys.argv:
     sd_fixture()
+
+
+def nu_paramfile(wd, N, box):
+    """fofrnu (MODEL=FOFRNU) parameter file on the reference's bundled CAMB data (camb_data/example_data_nu0.2)."""
+    src = "/root/reference/camb_data/example_data_nu0.2"
+    lines = open(os.path.join(src, "picola_transfer_info_nu0.2.txt")).read().split("\n")
+    lines[0] = "%s 50" % src                       # the file ships with the author's absolute path
+    os.makedirs(wd, exist_ok=True)
+    open(os.path.join(wd, "info.txt"), "w").write("\n".join(lines))
+    extra = "nu_FilenameTransferInfofile %s/info.txt\nnu_include_massive_neutrinos 1\nnu_SumMassNuEV 0.2\n" % wd
+    pf = bench.write_paramfile(wd, N, box, "fofr", 10, lcdm_growth=0, extra=extra)
+    txt = open(pf).read().replace("Omega 0.267", "Omega 0.3175").replace("HubbleParam 0.71", "HubbleParam 0.671")
+    open(pf, "w").write(txt)
+    return pf
+
+
+def nu_fixture(N=16, box=200.0):
+    """MASSIVE_NEUTRINOS: the reference's PtoMesh on its own ICs after two steps, with the neutrino add
+    (auxPM.c:383-420) and both in-step spectra ("CDM" before, "total" after the add)."""
+    import ctypes as C
+    pf = nu_paramfile("/tmp/mgp_golden_nu", N, box)
+    run = ref_lib.RefRun("fofrnu", pf)
+    r, L = run.r, run.r.lib
+    r.set(**POFK)
+    run.step()
+    run.step()
+    A = run.A
+    for nm in ("get_nu_transfer_function", "get_cdm_baryon_transfer_function"):
+        f = getattr(L, nm)
+        f.restype = C.c_double
+        f.argtypes = [C.c_double, C.c_double]
+    omega, omega_nu = C.c_double.in_dll(L, "Omega").value, C.c_double.in_dll(L, "OmegaNu").value
+    kk = po.sd_k_of_m(N, box)
+    tab = np.zeros(kk.size)
+    for m in range(1, kk.size):
+        tab[m] = omega_nu / omega * float(N * N * N) * L.get_nu_transfer_function(float(kk[m]), A) / L.get_cdm_baryon_transfer_function(float(kk[m]), 1.0)
+    P = run.particles().copy()
+    with ref_lib._silenced(True):
+        r.set(aexp_global=A, timeStep_global=1, NoutputStart_global=0, allocate_mg_arrays=1)
+        r.alloc_step_grids(mg=True)
+        ref_lib.tap_reset(r)
+        L.PtoMesh()
+    taps = [t for t in ref_lib.tap_arrays(r) if len(t) == POFK["pofk_nbins"]]
+    assert len(taps) == 6
+    np.savez_compressed(os.path.join(OUT, "step_nu.npz"), N=N, box=box, a=A, omega=omega, omega_nu=omega_nu, pos=P["Pos"],
+                        cdelta_cdm=r.sd_delta(1), nu_by_k2=tab, cdmfac=(omega - omega_nu) / omega, density_k=r.grid_k("density").copy(),
+                        pofk_cdm=np.stack(taps[:3]), pofk_total=np.stack(taps[3:]),
+                        pofk_cfg=np.array([POFK["pofk_nbins"], POFK["pofk_bintype"], 1, POFK["pofk_kmin"], POFK["pofk_kmax"]]))
+    print("step_nu", omega_nu, tab[1:4], np.abs(taps[3] / np.maximum(taps[0], 1e-300) - 1).max())
+
+
+def rsd_fixture(N=16, box=60.0):
+    """compute_RSD_powerspectrum (compute_pofk.c:403) on the reference's own particles after three f(R) steps:
+    the ten per-bin sums (P0, P2, P4, n, k for the y and the z line of sight)."""
+    import ctypes as C
+    pf = bench.write_paramfile("/tmp/mgp_golden_rsd", N, box, "fofr", 10)
+    run = ref_lib.RefRun("lcdm", pf)
+    r, L = run.r, run.r.lib
+    r.set(**POFK)
+    for _ in range(3):
+        run.step()
+    A = run.A
+    P = run.particles().copy()
+    L.compute_RSD_powerspectrum.argtypes = [C.c_double, C.c_int]
+    ref_lib.tap_reset(r)
+    with ref_lib._silenced(True):
+        L.compute_RSD_powerspectrum(A, 1)
+    taps = ref_lib.tap_arrays(r)
+    assert len(taps) == 10
+    hub = C.c_double.in_dll(L, "Hubble").value
+    vnorm = (hub / A) / (100.0 * A * L.hubble(A)) * N / box                 # compute_pofk.c:291-292
+    np.savez_compressed(os.path.join(OUT, "rsd_lcdm.npz"), N=N, box=box, a=A, omega=OMEGA, pos=P["Pos"], vel=P["Vel"], D=P["D"], D2=P["D2"],
+                        id=P["ID"], vnorm=vnorm, dDdy=L.growth_dDdy(A), dD2dy=L.growth_dD2dy(A), sums_y=np.stack(taps[:5]),
+                        sums_z=np.stack(taps[5:]),
+                        pofk_cfg=np.array([POFK["pofk_nbins"], POFK["pofk_bintype"], 1, POFK["pofk_kmin"], POFK["pofk_kmax"]]))
+    print("rsd_lcdm", vnorm, taps[0][:4])
+
+
+if __name__ == "__main__" and "--nu" in sys.argv:
+    nu_fixture()
+if __name__ == "__main__" and "--rsd" in sys.argv:
+    rsd_fixture()
