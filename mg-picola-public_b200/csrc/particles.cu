@@ -314,9 +314,9 @@ k_permute_all(size_t n, const uint32_t *__restrict__ src_of, const float4 *__res
               float4 *__restrict__ oB, float4 *__restrict__ oC, float2 *__restrict__ oE) {
   for (size_t d = blockIdx.x * (size_t) blockDim.x + threadIdx.x; d < n; d += (size_t) gridDim.x * blockDim.x) {
     const uint32_t i = src_of[d];
-    const float4 a = iA[i], b = iB[i], cc = iC[i];
-    const float2 e = iE[i];
-    oA[d] = a; oB[d] = b; oC[d] = cc; oE[d] = e;
+    const float4 a = iA[i], b = iB[i];
+    oA[d] = a; oB[d] = b;
+    if (iC) { const float4 cc = iC[i]; const float2 e = iE[i]; oC[d] = cc; oE[d] = e; }   // unused when scale_dependent
   }
 }
 
@@ -338,8 +338,9 @@ static void bucket_sort(Ctx &c) {
   size_t tb = c.cub_temp_bytes;
   CK(cub::DeviceScan::ExclusiveSum(c.cub_temp, tb, c.bucket_start, c.bucket_start, (int64_t) (c.nbuckets + 2), c.stream));
   k_bucket_invert<<<grid_for(n, 256), 256, 0, c.stream>>>(n, c.key[0], c.perm[0], c.bucket_start, c.perm[1]);
-  k_permute_all<<<grid_for(n, 256), 256, 0, c.stream>>>(n, c.perm[1], c.pA, c.pB, c.pC, (const float2 *) c.pE, c.pA2, c.pB2,
-                                                      c.pC2, (float2 *) c.pE2);
+  // scale_dependent: P.D / P.D2 are per-step temporaries kept in the sd field arrays, pC / pE are unused
+  k_permute_all<<<grid_for(n, 256), 256, 0, c.stream>>>(n, c.perm[1], c.pA, c.pB, c.cfg.scale_dependent ? nullptr : c.pC,
+                                                      (const float2 *) c.pE, c.pA2, c.pB2, c.pC2, (float2 *) c.pE2);
   std::swap(c.pA, c.pA2); std::swap(c.pB, c.pB2); std::swap(c.pC, c.pC2); std::swap(c.pE, c.pE2);
   k_rows_from_buckets<<<grid_for((size_t) nrows + 1, 256), 256, 0, c.stream>>>(nrows, nbz, c.bucket_start, c.row_start);
   c.launches += 4 + 2;   // + CUB's scan (2 launches)

@@ -47,33 +47,35 @@ k_sd_field(KL L, const typename Cpx<T>::type *__restrict__ d1, const double *__r
            typename Cpx<T>::type *__restrict__ o2, double box) {
   typedef typename Cpx<T>::type C;
   const int N = L.N, h = N / 2;
-  const double PI = 3.14159265358979323846;
+  const double twopi_over_box = 2 * 3.14159265358979323846 / box;
   KLOOP(e, L) {
     int i, j, k;
     kl_decode(L, e, i, j, k);
     const int c0 = i < h ? i : i - N, c1 = j < h ? j : j - N, c2 = k < h ? k : k - N;
-    const double kv[3] = {c0 * 2 * PI / box, c1 * 2 * PI / box, c2 * 2 * PI / box};
-    const double kmag2 = kv[0] * kv[0] + kv[1] * kv[1] + kv[2] * kv[2];
+    const long long m = (long long) c0 * c0 + (long long) c1 * c1 + (long long) c2 * c2;
     C out[3];
-    if (!(kmag2 > 0.0)) {
+    if (m == 0) {
       out[0].x = out[0].y = out[1].x = out[1].y = out[2].x = out[2].y = (T) 0;
     } else {
-      const long long m = (long long) c0 * c0 + (long long) c1 * c1 + (long long) c2 * c2;
+      // kvec_a / kmag2 = d_a / (|d|^2 * 2 pi / Box): one division per mode instead of the reference's nine
+      // (the quotient differs from kvec[a] / kmag2 of 2LPT.c:1620 in the last bit of a double)
+      const double inv = 1.0 / ((double) m * twopi_over_box);
+      const double kq[3] = {(double) c0 * inv, (double) c1 * inv, (double) c2 * inv};
       const C s = d1[e];
       const double ga = norm1 * g1[m];
       if (d2 == nullptr) {
 #pragma unroll
         for (int a = 0; a < 3; a++) {
-          out[a].x = (T) (-(double) s.y * kv[a] / kmag2 * ga);
-          out[a].y = (T) ((double) s.x * kv[a] / kmag2 * ga);
+          out[a].x = (T) (-(double) s.y * kq[a] * ga);
+          out[a].y = (T) ((double) s.x * kq[a] * ga);
         }
       } else {
         const C t = d2[e];
         const double gb = norm2 * g2[m];
 #pragma unroll
         for (int a = 0; a < 3; a++) {
-          out[a].x = (T) (-(double) s.y * kv[a] / kmag2 * ga + -(double) t.y * kv[a] / kmag2 * gb);
-          out[a].y = (T) ((double) s.x * kv[a] / kmag2 * ga + (double) t.x * kv[a] / kmag2 * gb);
+          out[a].x = (T) (-(double) s.y * kq[a] * ga + -(double) t.y * kq[a] * gb);
+          out[a].y = (T) ((double) s.x * kq[a] * ga + (double) t.x * kq[a] * gb);
         }
       }
     }
@@ -151,14 +153,15 @@ __device__ __forceinline__ float sd_value(double dis, double mean) {
 }
 
 // every particle whose birth plane is local interpolates for itself
-template <typename T>
+// ID32: Nsample^3 < 2^32, the high word of every ID (kept in pB.w) is zero and pB need not be read
+template <typename T, int ID32>
 __global__ void __launch_bounds__(256)
 k_sd_assign(size_t np, const float4 *__restrict__ pA, const float4 *__restrict__ pB, int ns, int p0, int npl, int N,
             int NZ, int x0, int nx, const T *__restrict__ g0, const T *__restrict__ g1, const T *__restrict__ g2,
             double m0, double m1, double m2, float *__restrict__ out, size_t cap) {
   const unsigned long long ns2 = (unsigned long long) ns * ns;
   for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < np; i += (size_t) gridDim.x * blockDim.x) {
-    const unsigned long long id = particle_id(pA[i], pB[i]);
+    const unsigned long long id = ID32 ? (unsigned long long) __float_as_uint(pA[i].w) : particle_id(pA[i], pB[i]);
     const long long n = (long long) (id / ns2);
     if (n < p0 || n >= p0 + npl) continue;             // born on another rank: answered by k_sd_serve there
     const unsigned rem = (unsigned) (id - (unsigned long long) n * ns2);
@@ -383,9 +386,13 @@ static void sd_assign_t(Ctx &c, int fieldtype, int order, const double *g1, cons
   float *out = c.sdf[slot];
   {
     PhaseTimer t(c, PH_SDASSIGN);
-    if (c.np)
-      k_sd_assign<T><<<grid_for(c.np, 256), 256, 0, c.stream>>>(c.np, c.pA, c.pB, ns, c.p0, c.npl, N, c.NZ, c.x0, c.nx, fr[0],
-                                                               fr[1], fr[2], mean[0], mean[1], mean[2], out, c.cap);
+    const bool id32 = (double) ns * ns * ns < 4294967296.0;
+    if (c.np && id32)
+      k_sd_assign<T, 1><<<grid_for(c.np, 256), 256, 0, c.stream>>>(c.np, c.pA, c.pB, ns, c.p0, c.npl, N, c.NZ, c.x0, c.nx, fr[0],
+                                                                  fr[1], fr[2], mean[0], mean[1], mean[2], out, c.cap);
+    else if (c.np)
+      k_sd_assign<T, 0><<<grid_for(c.np, 256), 256, 0, c.stream>>>(c.np, c.pA, c.pB, ns, c.p0, c.npl, N, c.NZ, c.x0, c.nx, fr[0],
+                                                                  fr[1], fr[2], mean[0], mean[1], mean[2], out, c.cap);
     c.launches++;
   }
   if (c.P > 1) {

@@ -19,7 +19,13 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag, launches, rep = sys.argv[1], sys.argv[2], sys.argv[3]
 nsteps = int(sys.argv[4]) if len(sys.argv) > 4 else 6
-peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+try:
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    peak_src = "measured HBM copy bandwidth %.0f GB/s (MEASURED_PEAKS.json)" % peak
+except Exception:
+    peak = 6650.0        # /opt/skills/guides/B200_PROFILING.md: fallback when the driver's file is absent
+    peak_src = "FALLBACK HBM copy bandwidth 6650 GB/s of B200_PROFILING.md (MEASURED_PEAKS.json absent in this container)"
+cmdline = os.environ.get("MGP_PROFILE_CMD", "python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline")
 
 
 def short(name):
@@ -39,7 +45,7 @@ for r in csv.DictReader(lines):
 # the last `per` launches = whole steps at the end of the run (the bench's phase-timing steps)
 names = [n for _, n, _ in rows]
 # one step = distance between consecutive k_drift launches
-drifts = [i for i, n in enumerate(names) if n == "k_drift"]
+drifts = [i for i, n in enumerate(names) if n in ("k_drift", "k_drift_sd")]
 per = drifts[-1] - drifts[-2] if len(drifts) > 1 else len(rows)
 last = rows[drifts[-2] + 1: drifts[-1] + 1] if len(drifts) > 1 else rows
 agg = collections.OrderedDict()
@@ -50,7 +56,7 @@ for _, n, v in last:
 tot = sum(v for _, v in agg.values())
 with open(os.path.join(ROOT, "profiles", tag + "_launches.md"), "w") as f:
     f.write("# %s: launch list of one COLA step (`ncu --metrics gpu__time_duration.sum --clock-control none`)\n\n" % tag)
-    f.write("Command: `python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline` (f(R) + screening, 256^3, double grids), "
+    f.write("Command: `" + cmdline + "` (f(R) + screening, 256^3, double grids), "
             "%d launches captured in the whole run, %d in the step shown (a step without a re-sort unless the sort kernels appear). "
             "ncu serialises launches and runs them cold-cache: compare SHARES with bench.py's phases, not absolutes.\n\n" % (len(rows), per))
     f.write("| kernel | launches | device time (us) | share |\n|---|---:|---:|---:|\n")
@@ -113,8 +119,7 @@ traffic = {}
 with open(os.path.join(ROOT, "profiles", tag + "_kernels.md"), "w") as f:
     f.write("# %s: `ncu --set full --clock-control none --import-source on` capture of the hand-written kernels\n\n" % tag)
     f.write("Same bench command, one step after one warm-up step; one row per kernel (mean over the captured launches). "
-            "`GB/s` = (DRAM read + write) / duration; `of peak` = against the measured HBM copy bandwidth %.0f GB/s "
-            "(MEASURED_PEAKS.json).  The `.ncu-rep` itself stays in gpurun_out/ (scratch).\n\n" % peak)
+            "`GB/s` = (DRAM read + write) / duration; `of peak` = against the " + peak_src + ".  The `.ncu-rep` itself stays in gpurun_out/ (scratch).\n\n")
     f.write("| kernel | n | us | DRAM rd MB | DRAM wr MB | GB/s | of peak | ncu dram % | regs | warps active % | issue active % | L1 hit % | L2 hit % | grid x block | top stalls (warps per issue) |\n")
     f.write("|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---|---|\n")
     for n, ds in seen.items():
