@@ -207,11 +207,16 @@ def run_ours(args):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
+    dbg = []
     for _ in range(args.steps):
+        t_dbg = time.perf_counter()
         st.step()
+        dbg.append(time.perf_counter() - t_dbg)
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
+    if os.environ.get("MGP_BENCH_DEBUG") and rank == 0:
+        sys.stderr.write("host ms per timed step: " + " ".join("%.2f" % (v * 1e3) for v in dbg) + " | device total %.2f\n" % ms)
     launches = pm.launch_count()
     clocks = sampler.result() if rank == 0 else None
     if world > 1:

@@ -239,10 +239,13 @@ k_sd_scatter(size_t nreq, const uint32_t *__restrict__ req_slot, const float *__
   }
 }
 
-static void sd_grow(void **p, size_t *have, size_t need) {
+// cudaFree of a buffer NCCL has used costs up to hundreds of ms (peer mappings are torn down), so the request /
+// response buffers start at `floor_bytes` (1/8 of the particle capacity) and double when they have to grow
+static void sd_grow(void **p, size_t *have, size_t need, size_t floor_bytes) {
   if (*have >= need && *p) return;
   if (*p) CK(cudaFree(*p));
-  size_t n = need + need / 4 + 1024;
+  size_t n = 2 * need + 1024;
+  if (n < floor_bytes) n = floor_bytes;
   CK(cudaMalloc(p, n));
   *have = n;
 }
@@ -274,11 +277,12 @@ static void sd_build_requests(Ctx &c) {
     nneed += c.sd_need[q]; nserve += c.sd_serve[q];
   }
   c.sd_nneed = nneed; c.sd_nserve = nserve;
-  sd_grow((void **) &c.sd_req_id, &c.sd_req_id_bytes, nneed * sizeof(unsigned long long));
-  sd_grow((void **) &c.sd_req_slot, &c.sd_req_slot_bytes, nneed * sizeof(uint32_t));
-  sd_grow((void **) &c.sd_srv_id, &c.sd_srv_id_bytes, nserve * sizeof(unsigned long long));
-  sd_grow((void **) &c.sd_resp_out, &c.sd_resp_out_bytes, nserve * 3 * sizeof(float));
-  sd_grow((void **) &c.sd_resp_in, &c.sd_resp_in_bytes, nneed * 3 * sizeof(float));
+  const size_t fl = c.cap / 8 + 1024;
+  sd_grow((void **) &c.sd_req_id, &c.sd_req_id_bytes, nneed * sizeof(unsigned long long), fl * sizeof(unsigned long long));
+  sd_grow((void **) &c.sd_req_slot, &c.sd_req_slot_bytes, nneed * sizeof(uint32_t), fl * sizeof(uint32_t));
+  sd_grow((void **) &c.sd_srv_id, &c.sd_srv_id_bytes, nserve * sizeof(unsigned long long), fl * sizeof(unsigned long long));
+  sd_grow((void **) &c.sd_resp_out, &c.sd_resp_out_bytes, nserve * 3 * sizeof(float), fl * 3 * sizeof(float));
+  sd_grow((void **) &c.sd_resp_in, &c.sd_resp_in_bytes, nneed * 3 * sizeof(float), fl * 3 * sizeof(float));
   std::vector<unsigned> off(P, 0);
   for (int q = 1; q < P; q++) off[q] = off[q - 1] + c.sd_need[q - 1];
   CK(cudaMemcpyAsync(d_off, off.data(), P * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
