@@ -78,6 +78,13 @@ struct Ctx {
   cufftHandle plan2d_r2c = 0, plan2d_c2r = 0, plan1d_x = 0;
   int ny_loc = 0, y0 = 0;     // k-space y-slab of this rank
   void *tbuf_a = nullptr, *tbuf_b = nullptr;   // transpose pack / unpack buffers
+  // peer-memory transposes (P > 1): every rank maps every other rank's tbuf_a and flag array (cudaIpc) and the
+  // transpose kernel stores straight into the owner's buffer over NVLink; barriers are flag exchanges in peer memory
+  bool p2p = false;
+  void *peer_tbuf[16] = {nullptr};
+  uint32_t *sync_flags = nullptr;              // [P] epoch counters, written by the peers
+  uint32_t *peer_flags[16] = {nullptr};
+  uint32_t sync_epoch = 0;
   void *fft_work = nullptr;                    // cuFFT work area shared by all plans
 
   // particles (SoA of 16-byte records; see DESIGN.md "data layout")

@@ -26,6 +26,124 @@ static size_t make_plan_many(cufftHandle *plan, int rank, lli *n, lli *inembed, 
   return ws;
 }
 
+// ------------------------------------------------------------------ peer-memory plumbing (P > 1)
+
+struct PeerPtrs { void *p[16]; };
+
+static void p2p_teardown(Ctx &c) {
+  for (int r = 0; r < 16; r++) {
+    if (r != c.rank && c.peer_tbuf[r]) cudaIpcCloseMemHandle(c.peer_tbuf[r]);
+    if (r != c.rank && c.peer_flags[r]) cudaIpcCloseMemHandle(c.peer_flags[r]);
+    c.peer_tbuf[r] = nullptr; c.peer_flags[r] = nullptr;
+  }
+  cudaFree(c.sync_flags); c.sync_flags = nullptr;
+  c.p2p = false;
+}
+
+// Maps every peer's transpose buffer and flag array into this process (cudaIpc over NVLink / NVSwitch).  All ranks
+// agree on the outcome: if any mapping fails (no peer access, MGP_P2P=0) everybody keeps the NCCL all-to-all.
+static void p2p_setup(Ctx &c) {
+  const int P = c.P;
+  const char *env = getenv("MGP_P2P");
+  int ok = (P <= 16) && !(env && atoi(env) == 0);
+  struct Handles { cudaIpcMemHandle_t buf, flags; };
+  static_assert(sizeof(Handles) == 128, "cudaIpcMemHandle_t is 64 bytes");
+  CK(cudaMalloc(&c.sync_flags, 16 * sizeof(uint32_t)));
+  CK(cudaMemset(c.sync_flags, 0, 16 * sizeof(uint32_t)));
+  Handles mine;
+  memset(&mine, 0, sizeof(mine));
+  if (ok && cudaIpcGetMemHandle(&mine.buf, c.tbuf_a) != cudaSuccess) ok = 0;
+  if (ok && cudaIpcGetMemHandle(&mine.flags, c.sync_flags) != cudaSuccess) ok = 0;
+  cudaGetLastError();
+  Handles *d_all = nullptr;
+  CK(cudaMalloc(&d_all, (size_t) (P + 1) * sizeof(Handles)));
+  CK(cudaMemcpy(d_all + P, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+  CKNCCL(ncclAllGather(d_all + P, d_all, sizeof(Handles), ncclChar, c.comm, c.stream));
+  std::vector<Handles> all(P);
+  CK(cudaMemcpyAsync(all.data(), d_all, (size_t) P * sizeof(Handles), cudaMemcpyDeviceToHost, c.stream));
+  CK(cudaStreamSynchronize(c.stream));
+  for (int r = 0; r < P && ok; r++) {
+    if (r == c.rank) { c.peer_tbuf[r] = c.tbuf_a; c.peer_flags[r] = c.sync_flags; continue; }
+    void *a = nullptr, *b = nullptr;
+    if (cudaIpcOpenMemHandle(&a, all[r].buf, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+        cudaIpcOpenMemHandle(&b, all[r].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
+    c.peer_tbuf[r] = a; c.peer_flags[r] = (uint32_t *) b;
+  }
+  cudaGetLastError();
+  int *d_ok = (int *) d_all;
+  CK(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
+  CKNCCL(ncclAllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, c.comm, c.stream));
+  CK(cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+  CK(cudaStreamSynchronize(c.stream));
+  CK(cudaFree(d_all));
+  c.p2p = ok != 0;
+  if (!c.p2p) { for (int r = 0; r < 16; r++) if (r == c.rank) { c.peer_tbuf[r] = nullptr; c.peer_flags[r] = nullptr; } }
+}
+
+// Barrier over peer memory: thread r stores the epoch into rank r's flag array (slot = my rank) and then waits
+// until rank r has stored it into mine.  Everything this rank wrote to peer memory in earlier kernels of the stream
+// is ordered before the signal by the system-scope release.
+__global__ void k_p2p_barrier(PeerPtrs flags, uint32_t *mine, int P, int me, uint32_t epoch) {
+  const int r = threadIdx.x;
+  if (r < P) {
+    __threadfence_system();
+    uint32_t *dst = (uint32_t *) flags.p[r] + me;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(epoch) : "memory");
+    uint32_t v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine + r) : "memory");
+    } while ((int32_t) (v - epoch) < 0);
+  }
+}
+
+static void p2p_barrier(Ctx &c) {
+  PeerPtrs f;
+  for (int r = 0; r < 16; r++) f.p[r] = c.peer_flags[r];
+  c.sync_epoch++;
+  k_p2p_barrier<<<1, 32, 0, c.stream>>>(f, c.sync_flags, c.P, c.rank, c.sync_epoch);
+  c.launches++;
+}
+
+// forward transpose, fused with the exchange: in = [nx][N (ky)][NZ] on this rank; the element (x, ky, kz) goes to the
+// rank that owns ky, into its buffer laid out [nyl][NZ][N (kx)].  32 x 32 (x, kz) tiles through shared memory: reads
+// are 512-byte runs along kz, the peer stores 512-byte runs along kx.
+template <typename C>
+__global__ void k_transpose_fwd_p2p(const C *__restrict__ in, PeerPtrs out, int nxb, int x0, int N, int NZ, int nyl) {
+  __shared__ C tile[32][33];
+  const int j = blockIdx.z, r = j / nyl, jl = j - r * nyl;
+  C *dst = (C *) out.p[r];
+  const int xb = blockIdx.x * 32, kb = blockIdx.y * 32;
+  for (int q = threadIdx.y; q < 32; q += blockDim.y) {
+    const int x = xb + q, k = kb + threadIdx.x;
+    if (x < nxb && k < NZ) tile[q][threadIdx.x] = in[((size_t) x * N + j) * NZ + k];
+  }
+  __syncthreads();
+  for (int q = threadIdx.y; q < 32; q += blockDim.y) {
+    const int k = kb + q, x = xb + threadIdx.x;
+    if (x < nxb && k < NZ) dst[((size_t) jl * NZ + k) * N + x0 + x] = tile[threadIdx.x][q];
+  }
+}
+
+// backward: in = [nyl][NZ][N (x)] on this rank; (ky, kz, x) goes to the owner of x, laid out [nxb][N (ky)][NZ]
+template <typename C>
+__global__ void k_transpose_bwd_p2p(const C *__restrict__ in, PeerPtrs out, int nxb, int y0, int N, int NZ, int nyl) {
+  __shared__ C tile[32][33];
+  const int jl = blockIdx.z;
+  const int xb = blockIdx.x * 32, kb = blockIdx.y * 32;
+  for (int q = threadIdx.y; q < 32; q += blockDim.y) {
+    const int k = kb + q, x = xb + threadIdx.x;
+    if (x < N && k < NZ) tile[q][threadIdx.x] = in[((size_t) jl * NZ + k) * N + x];
+  }
+  __syncthreads();
+  for (int q = threadIdx.y; q < 32; q += blockDim.y) {
+    const int x = xb + q, k = kb + threadIdx.x;
+    if (x < N && k < NZ) {
+      const int s = x / nxb, xl = x - s * nxb;
+      ((C *) out.p[s])[((size_t) xl * N + (y0 + jl)) * NZ + k] = tile[threadIdx.x][q];
+    }
+  }
+}
+
 void fft_setup(Ctx &c) {
   const int N = c.N, NZ = c.NZ;
   const bool f32 = c.gbytes == 4;
@@ -55,6 +173,7 @@ void fft_setup(Ctx &c) {
     ws = w > ws ? w : ws;
     CK(cudaMalloc(&c.tbuf_a, c.grid_bytes()));
     CK(cudaMalloc(&c.tbuf_b, c.grid_bytes()));
+    p2p_setup(c);
   }
   if (ws) CK(cudaMalloc(&c.fft_work, ws));     // shared cuFFT work area
   cufftHandle all[7] = {c.plan_r2c, c.plan_c2r, c.plan_c2r3, c.plan2d_r2c, c.plan2d_c2r, c.plan1d_x, c.plan_r2c_oop};
@@ -64,6 +183,7 @@ void fft_setup(Ctx &c) {
 }
 
 void fft_teardown(Ctx &c) {
+  p2p_teardown(c);
   cufftHandle all[7] = {c.plan_r2c, c.plan_c2r, c.plan_c2r3, c.plan2d_r2c, c.plan2d_c2r, c.plan1d_x, c.plan_r2c_oop};
   for (cufftHandle h : all)
     if (h) cufftDestroy(h);
@@ -155,6 +275,21 @@ static void dist_r2c(Ctx &c, void *g) {
   const int N = c.N, NZ = c.NZ, nxb = c.nx, nyl = c.ny_loc;
   if (sizeof(R) == 4) CKFFT(cufftExecR2C(c.plan2d_r2c, (cufftReal *) g, (cufftComplex *) g));
   else CKFFT(cufftExecD2Z(c.plan2d_r2c, (cufftDoubleReal *) g, (cufftDoubleComplex *) g));
+  if (c.p2p) {
+    PeerPtrs pp;
+    for (int r = 0; r < 16; r++) pp.p[r] = c.peer_tbuf[r];
+    {
+      PhaseTimer t(c, PH_COMM);
+      p2p_barrier(c);                       // every rank has finished reading its transpose buffer
+      dim3 gr((nxb + 31) / 32, (NZ + 31) / 32, N), bl(32, 8);
+      k_transpose_fwd_p2p<C><<<gr, bl, 0, c.stream>>>((const C *) g, pp, nxb, c.x0, N, NZ, nyl);
+      p2p_barrier(c);                       // every rank's stores have landed
+    }
+    if (sizeof(R) == 4) CKFFT(cufftExecC2C(c.plan1d_x, (cufftComplex *) c.tbuf_a, (cufftComplex *) g, CUFFT_FORWARD));
+    else CKFFT(cufftExecZ2Z(c.plan1d_x, (cufftDoubleComplex *) c.tbuf_a, (cufftDoubleComplex *) g, CUFFT_FORWARD));
+    c.launches += 3;
+    return;
+  }
   const size_t tot = (size_t) nxb * N * NZ;
   k_pack_fwd<C><<<grid_for(tot, 256), 256, 0, c.stream>>>((const C *) g, (C *) c.tbuf_a, nxb, N, NZ, nyl);
   all_to_all(c, c.tbuf_a, c.tbuf_b, (size_t) nxb * nyl * NZ * sizeof(C));
@@ -170,6 +305,21 @@ static void dist_c2r(Ctx &c, void *g) {
   const int N = c.N, NZ = c.NZ, nxb = c.nx, nyl = c.ny_loc;
   if (sizeof(R) == 4) CKFFT(cufftExecC2C(c.plan1d_x, (cufftComplex *) g, (cufftComplex *) g, CUFFT_INVERSE));
   else CKFFT(cufftExecZ2Z(c.plan1d_x, (cufftDoubleComplex *) g, (cufftDoubleComplex *) g, CUFFT_INVERSE));
+  if (c.p2p) {
+    PeerPtrs pp;
+    for (int r = 0; r < 16; r++) pp.p[r] = c.peer_tbuf[r];
+    {
+      PhaseTimer t(c, PH_COMM);
+      p2p_barrier(c);
+      dim3 gr2((N + 31) / 32, (NZ + 31) / 32, nyl), bl2(32, 8);
+      k_transpose_bwd_p2p<C><<<gr2, bl2, 0, c.stream>>>((const C *) g, pp, nxb, c.y0, N, NZ, nyl);
+      p2p_barrier(c);
+    }
+    if (sizeof(R) == 4) CKFFT(cufftExecC2R(c.plan2d_c2r, (cufftComplex *) c.tbuf_a, (cufftReal *) g));
+    else CKFFT(cufftExecZ2D(c.plan2d_c2r, (cufftDoubleComplex *) c.tbuf_a, (cufftDoubleReal *) g));
+    c.launches += 3;
+    return;
+  }
   dim3 gr((N + 31) / 32, (NZ + 31) / 32, nyl), bl(32, 8);
   k_pack_bwd<C><<<gr, bl, 0, c.stream>>>((const C *) g, (C *) c.tbuf_a, nxb, N, NZ, nyl);
   all_to_all(c, c.tbuf_a, c.tbuf_b, (size_t) nxb * nyl * NZ * sizeof(C));
