@@ -27,6 +27,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's banner ("NCCL version ...", printed when NCCL_DEBUG is set) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 OMEGA, SIGMA8, Z_INIT, NSTEPS_RUN = 0.267, 0.8, 9.0, 30
 FOFR0, NFOFR, RCH0, RSMOOTH = 1e-5, 1.0, 1.0, 1.0

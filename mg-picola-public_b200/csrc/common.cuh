@@ -85,6 +85,8 @@ struct Ctx {
   uint32_t *sync_flags = nullptr;              // [P] epoch counters, written by the peers
   uint32_t *peer_flags[16] = {nullptr};
   uint32_t sync_epoch = 0;
+  cudaStream_t comm_stream = nullptr;          // high-priority stream the transposes of a batched transform run on
+  cudaEvent_t ev_fft[3] = {nullptr, nullptr, nullptr}, ev_tr[3] = {nullptr, nullptr, nullptr};
   void *fft_work = nullptr;                    // cuFFT work area shared by all plans
 
   // particles (SoA of 16-byte records; see DESIGN.md "data layout")

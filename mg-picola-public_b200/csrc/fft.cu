@@ -96,11 +96,11 @@ __global__ void k_p2p_barrier(PeerPtrs flags, uint32_t *mine, int P, int me, uin
   }
 }
 
-static void p2p_barrier(Ctx &c) {
+static void p2p_barrier(Ctx &c, cudaStream_t st = nullptr) {
   PeerPtrs f;
   for (int r = 0; r < 16; r++) f.p[r] = c.peer_flags[r];
   c.sync_epoch++;
-  k_p2p_barrier<<<1, 32, 0, c.stream>>>(f, c.sync_flags, c.P, c.rank, c.sync_epoch);
+  k_p2p_barrier<<<1, 32, 0, st ? st : c.stream>>>(f, c.sync_flags, c.P, c.rank, c.sync_epoch);
   c.launches++;
 }
 
@@ -171,9 +171,18 @@ void fft_setup(Ctx &c) {
     lli n1[1] = {N};
     w = make_plan_many(&c.plan1d_x, 1, n1, n1, 1, N, n1, 1, N, f32 ? CUFFT_C2C : CUFFT_Z2Z, c.ny_loc * NZ, c.stream);
     ws = w > ws ? w : ws;
-    CK(cudaMalloc(&c.tbuf_a, c.grid_bytes()));
+    CK(cudaMalloc(&c.tbuf_a, 3 * c.grid_bytes()));     // three slots: the batched c2r pipelines its three transposes
     CK(cudaMalloc(&c.tbuf_b, c.grid_bytes()));
     p2p_setup(c);
+    if (c.p2p) {
+      int lo = 0, hi = 0;
+      CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CK(cudaStreamCreateWithPriority(&c.comm_stream, cudaStreamNonBlocking, hi));
+      for (int a = 0; a < 3; a++) {
+        CK(cudaEventCreateWithFlags(&c.ev_fft[a], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c.ev_tr[a], cudaEventDisableTiming));
+      }
+    }
   }
   if (ws) CK(cudaMalloc(&c.fft_work, ws));     // shared cuFFT work area
   cufftHandle all[7] = {c.plan_r2c, c.plan_c2r, c.plan_c2r3, c.plan2d_r2c, c.plan2d_c2r, c.plan1d_x, c.plan_r2c_oop};
@@ -184,6 +193,8 @@ void fft_setup(Ctx &c) {
 
 void fft_teardown(Ctx &c) {
   p2p_teardown(c);
+  for (int a = 0; a < 3; a++) { if (c.ev_fft[a]) cudaEventDestroy(c.ev_fft[a]); if (c.ev_tr[a]) cudaEventDestroy(c.ev_tr[a]); }
+  if (c.comm_stream) cudaStreamDestroy(c.comm_stream);
   cufftHandle all[7] = {c.plan_r2c, c.plan_c2r, c.plan_c2r3, c.plan2d_r2c, c.plan2d_c2r, c.plan1d_x, c.plan_r2c_oop};
   for (cufftHandle h : all)
     if (h) cufftDestroy(h);
@@ -330,6 +341,41 @@ static void dist_c2r(Ctx &c, void *g) {
   c.launches += 5;
 }
 
+// The three inverse transforms of a vector field (Forces, the displacement fields) as one pipeline: the x-FFTs run on
+// the compute stream while the peer-memory transposes of the previous component run on the communication stream, and
+// the 2-D c2r of a component starts as soon as all ranks have delivered it (one flag barrier per component):
+//   compute: [x-FFT 0][x-FFT 1][x-FFT 2]          [2-D c2r 0][2-D c2r 1][2-D c2r 2]
+//   comm   :          [B][T 0][B]   [T 1][B]   [T 2][B]
+template <typename R, typename C>
+static void dist_c2r3(Ctx &c) {
+  const int N = c.N, NZ = c.NZ, nxb = c.nx, nyl = c.ny_loc;
+  const size_t gb = c.grid_bytes();
+  cudaStream_t S = c.stream, T = c.comm_stream;
+  for (int a = 0; a < 3; a++) {
+    void *g = c.grid[MGP_GRID_FORCE_X + a];
+    if (sizeof(R) == 4) CKFFT(cufftExecC2C(c.plan1d_x, (cufftComplex *) g, (cufftComplex *) g, CUFFT_INVERSE));
+    else CKFFT(cufftExecZ2Z(c.plan1d_x, (cufftDoubleComplex *) g, (cufftDoubleComplex *) g, CUFFT_INVERSE));
+    CK(cudaEventRecord(c.ev_fft[a], S));
+  }
+  dim3 gr((N + 31) / 32, (NZ + 31) / 32, nyl), bl(32, 8);
+  for (int a = 0; a < 3; a++) {
+    CK(cudaStreamWaitEvent(T, c.ev_fft[a], 0));
+    if (a == 0) p2p_barrier(c, T);          // every rank is done with all three slots of its transpose buffer
+    PeerPtrs pp;
+    for (int r = 0; r < 16; r++) pp.p[r] = c.peer_tbuf[r] ? (char *) c.peer_tbuf[r] + (size_t) a * gb : nullptr;
+    k_transpose_bwd_p2p<C><<<gr, bl, 0, T>>>((const C *) c.grid[MGP_GRID_FORCE_X + a], pp, nxb, c.y0, N, NZ, nyl);
+    p2p_barrier(c, T);                      // component a has landed everywhere
+    CK(cudaEventRecord(c.ev_tr[a], T));
+  }
+  for (int a = 0; a < 3; a++) {
+    CK(cudaStreamWaitEvent(S, c.ev_tr[a], 0));
+    void *src = (char *) c.tbuf_a + (size_t) a * gb, *g = c.grid[MGP_GRID_FORCE_X + a];
+    if (sizeof(R) == 4) CKFFT(cufftExecC2R(c.plan2d_c2r, (cufftComplex *) src, (cufftReal *) g));
+    else CKFFT(cufftExecZ2D(c.plan2d_c2r, (cufftDoubleComplex *) src, (cufftDoubleReal *) g));
+  }
+  c.launches += 9 + 3;
+}
+
 // ------------------------------------------------------------------ public (module) entry points
 
 void fft_r2c(Ctx &c, int gid) {
@@ -366,6 +412,11 @@ void fft_c2r(Ctx &c, int gid) {
 }
 
 void fft_c2r_forces(Ctx &c) {
+  if (c.P > 1 && c.p2p) {
+    PhaseTimer t(c, PH_FFT);
+    if (c.gbytes == 4) dist_c2r3<float, float2>(c); else dist_c2r3<double, double2>(c);
+    return;
+  }
   if (c.P > 1) {
     for (int a = 0; a < 3; a++) fft_c2r(c, MGP_GRID_FORCE_X + a);
     return;
