@@ -67,12 +67,20 @@ static Ctx *create(const mgp_config *cfg) {
     CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
     for (int d = 0; d < 4; d++) { CK(cudaEventCreate(&c.ev[d][0])); CK(cudaEventCreate(&c.ev[d][1])); }
 
-    CK(cudaMalloc(&c.grid[0], c.grid_bytes()));
     CK(cudaMalloc(&c.force_block, 3 * c.grid_bytes()));
     for (int a = 0; a < 3; a++) c.grid[1 + a] = (char *) c.force_block + (size_t) a * c.grid_bytes();
-    if (needs_mg_arrays(c)) {
-      CK(cudaMalloc(&c.grid[4], c.grid_bytes()));
-      CK(cudaMalloc(&c.grid[5], c.grid_bytes()));
+    if (cfg->scale_dependent) {
+      // density, mgarray_one, mgarray_two contiguous: the second target of the batched inverse transform (sd.cu)
+      CK(cudaMalloc(&c.aux_block, 3 * c.grid_bytes()));
+      c.grid[0] = c.aux_block;
+      c.grid[4] = (char *) c.aux_block + c.grid_bytes();
+      c.grid[5] = (char *) c.aux_block + 2 * c.grid_bytes();
+    } else {
+      CK(cudaMalloc(&c.grid[0], c.grid_bytes()));
+      if (needs_mg_arrays(c)) {
+        CK(cudaMalloc(&c.grid[4], c.grid_bytes()));
+        CK(cudaMalloc(&c.grid[5], c.grid_bytes()));
+      }
     }
     if (cfg->scale_dependent) {
       CK(cudaMalloc(&c.sd_delta[0], c.grid_bytes()));
@@ -103,7 +111,9 @@ static void destroy(Ctx *cp) {
   fft_teardown(c);
   particles_free(c);
   sd_free(c);
-  cudaFree(c.grid[0]); cudaFree(c.force_block); cudaFree(c.grid[4]); cudaFree(c.grid[5]); cudaFree(c.halo_recv);
+  if (c.aux_block) cudaFree(c.aux_block);
+  else { cudaFree(c.grid[0]); cudaFree(c.grid[4]); cudaFree(c.grid[5]); }
+  cudaFree(c.force_block); cudaFree(c.halo_recv);
   cudaFree(c.sd_delta[0]); cudaFree(c.sd_delta[1]);
   cudaFree(c.mig_dev); if (c.mig_host) cudaFreeHost(c.mig_host);
   cudaFree(c.pofk_bins_d); cudaFree(c.pofk_sinc_d); cudaFree(c.pofk_out_d); cudaFree(c.nu_tab_d);
@@ -127,6 +137,7 @@ static void ensure_order(Ctx &c) {
 }
 
 static void move_particles(Ctx &c) {
+  if (c.cfg.scale_dependent) sd_drop(c);
   {
     PhaseTimer t(c, PH_MOVE);
     if (c.P > 1) particles_migrate(c);
@@ -136,6 +147,7 @@ static void move_particles(Ctx &c) {
 }
 
 static void ptomesh(Ctx &c, const mgp_step_scalars *s) {
+  if (c.cfg.scale_dependent) sd_drop(c);
   ensure_order(c);
   if (needs_mg_arrays(c) && c.P == 1) {
     // CopyDensityArray (mg.h:381) without the copy: deposit straight into mgarray_two and transform
@@ -151,6 +163,7 @@ static void ptomesh(Ctx &c, const mgp_step_scalars *s) {
     }
     fft_r2c(c, MGP_GRID_DENSITY);
   }
+  c.density_live = true;
   c.step_pofk_valid = false;
   c.step_pofk_tot_valid = false;
   if (s && s->compute_pofk) {
@@ -172,6 +185,7 @@ static void ptomesh(Ctx &c, const mgp_step_scalars *s) {
 
 static void rsd_power_spectrum(Ctx &c, double vnorm, double dDdy, double dD2dy, double *out_y, double *out_z) {
   REQUIRE(out_y && out_z, MGP_ERR_INVALID, "mgp_compute_rsd_power_spectrum: NULL output");
+  if (c.cfg.scale_dependent) { sd_evict_block(c, 0); sd_materialise(c, 1); }   // work grid = force grid X; V needs P.dDdy
   for (int axis = 1; axis <= 2; axis++) {                   // YAXIS then ZAXIS (compute_pofk.c:437-448)
     deposit_rsd(c, MGP_GRID_FORCE_X, axis, vnorm, dDdy, dD2dy);
     halo_add_density(c, MGP_GRID_FORCE_X);
@@ -218,8 +232,10 @@ static void compute_fifth_force(Ctx &c, const mgp_step_scalars *s) {
 
 static void forces(Ctx &c) {
   { PhaseTimer t(c, PH_FORCES); kspace_forces(c, needs_mg_arrays(c)); }
+  c.density_live = false;                  // P3D and mgarray_two are consumed
   fft_c2r_forces(c);
   halo_fill_forces(c);
+  c.forces_live = true;
 }
 
 }  // namespace mgp
@@ -331,6 +347,8 @@ int mgp_download_disp(mgp_ctx *ctx, float *disp) {
 int mgp_ic_generate(mgp_ctx *ctx, const mgp_ic_config *ic) {
   API_BEGIN
   CTX(ctx);
+  if (c.cfg.scale_dependent) sd_drop(c);
+  c.density_live = false; c.forces_live = false;
   ic_generate(c, ic);
   API_END
 }
@@ -358,7 +376,7 @@ int mgp_ic_download(mgp_ctx *ctx, float *za, float *lpt) {
 int mgp_init_particles(mgp_ctx *ctx, double Di, double Di2, double dDdy, double dD2dy) {
   API_BEGIN
   CTX(ctx);
-  if (c.cfg.scale_dependent) sd_init_particles(c);      // main.c:296-300: the fields already carry their growth factors
+  if (c.cfg.scale_dependent) { sd_materialise(c, 0); sd_materialise(c, 1); sd_init_particles(c); }      // main.c:296-300: the fields already carry their growth factors
   else ic_init_particles(c, Di, Di2, dDdy, dD2dy);
   API_END
 }
@@ -423,6 +441,7 @@ int mgp_mtoparticles(mgp_ctx *ctx, double sumDxyz[3]) {
   CTX(ctx);
   REQUIRE(sumDxyz != nullptr, MGP_ERR_INVALID, "mgp_mtoparticles: sumDxyz is NULL");
   gather_forces(c, sumDxyz);
+  c.forces_live = false;
   API_END
 }
 
@@ -435,6 +454,7 @@ int mgp_get_displacements(mgp_ctx *ctx, const mgp_step_scalars *s, double sumDxy
   compute_fifth_force(c, s);
   forces(c);
   gather_forces(c, sumDxyz);
+  c.forces_live = false;
   API_END
 }
 

@@ -125,6 +125,13 @@ struct Ctx {
   bool sd_set[4] = {false, false, false, false};          // slot assigned for the current particle order
   bool sd_lagrangian_only = false;                        // particles carry IDs only (before mgp_init_particles)
   double *sd_gtab[2] = {nullptr, nullptr};                // growth tables over |d|^2 on the device
+  // merged fields stay in the grids they were transformed in and are read by Kick / Drift directly:
+  // sd_res[pair] = block (0: force grids 1-3, 1: grids 0, 4, 5) holding the field of pair 0 (D + D2) / 1 (dDdy + dD2dy)
+  void *aux_block = nullptr;                              // grids 0, 4, 5 as one allocation (second batched c2r target)
+  int sd_res[2] = {-1, -1};
+  bool density_live = false;                              // grid 0 (and 4, 5) hold this step's density / MG fields (PtoMesh .. Forces)
+  bool forces_live = false;                               // grids 1-3 hold the force components (Forces .. MtoParticles)
+  double sd_res_mean[2][3] = {{0, 0, 0}, {0, 0, 0}};
   // lattice points owned by other ranks (P > 1): request / response lists, built once per particle order
   bool sd_req_valid = false;
   unsigned *sd_cnt_dev = nullptr, *sd_cnt_host = nullptr;
@@ -220,6 +227,9 @@ void fft_r2c(Ctx &c, int grid_id);
 void fft_c2r(Ctx &c, int grid_id);
 void fft_r2c_to(Ctx &c, int src_grid, int dst_grid);
 void fft_c2r_forces(Ctx &c);
+void fft_c2r_block(Ctx &c, int block);      // block 0: grids 1, 2, 3; block 1: grids 0, 4, 5 (scale_dependent only)
+void halo_fill_block(Ctx &c, int block);
+inline int block_grid(int block, int a) { return block == 0 ? 1 + a : (a == 0 ? 0 : 3 + a); }
 void halo_add_density(Ctx &c, int grid_id);
 void halo_fill_forces(Ctx &c);
 // kspace.cu
@@ -251,6 +261,9 @@ void sd_init_particles(Ctx &c);
 void sd_kick(Ctx &c, double A, double dda, const double sumD[3], double sumV[3]);
 void sd_drift(Ctx &c, double dyyy, const double sumV[3]);
 void sd_copy_field(Ctx &c, int slot, float *host, bool to_host);
+void sd_materialise(Ctx &c, int pair);      // resident merged field -> the per-particle arrays
+void sd_drop(Ctx &c);                        // a new force evaluation starts: the four fields are dead
+void sd_evict_block(Ctx &c, int block);      // about to overwrite a grid block: save a live resident field first
 
 // reductions: sum `n` doubles' worth of per-block partials living in c.d_red into host values
 void reduce_alloc(Ctx &c, size_t n);

@@ -347,12 +347,12 @@ static void dist_c2r(Ctx &c, void *g) {
 //   compute: [x-FFT 0][x-FFT 1][x-FFT 2]          [2-D c2r 0][2-D c2r 1][2-D c2r 2]
 //   comm   :          [B][T 0][B]   [T 1][B]   [T 2][B]
 template <typename R, typename C>
-static void dist_c2r3(Ctx &c) {
+static void dist_c2r3(Ctx &c, int block) {
   const int N = c.N, NZ = c.NZ, nxb = c.nx, nyl = c.ny_loc;
   const size_t gb = c.grid_bytes();
   cudaStream_t S = c.stream, T = c.comm_stream;
   for (int a = 0; a < 3; a++) {
-    void *g = c.grid[MGP_GRID_FORCE_X + a];
+    void *g = c.grid[block_grid(block, a)];
     if (sizeof(R) == 4) CKFFT(cufftExecC2C(c.plan1d_x, (cufftComplex *) g, (cufftComplex *) g, CUFFT_INVERSE));
     else CKFFT(cufftExecZ2Z(c.plan1d_x, (cufftDoubleComplex *) g, (cufftDoubleComplex *) g, CUFFT_INVERSE));
     CK(cudaEventRecord(c.ev_fft[a], S));
@@ -363,13 +363,13 @@ static void dist_c2r3(Ctx &c) {
     if (a == 0) p2p_barrier(c, T);          // every rank is done with all three slots of its transpose buffer
     PeerPtrs pp;
     for (int r = 0; r < 16; r++) pp.p[r] = c.peer_tbuf[r] ? (char *) c.peer_tbuf[r] + (size_t) a * gb : nullptr;
-    k_transpose_bwd_p2p<C><<<gr, bl, 0, T>>>((const C *) c.grid[MGP_GRID_FORCE_X + a], pp, nxb, c.y0, N, NZ, nyl);
+    k_transpose_bwd_p2p<C><<<gr, bl, 0, T>>>((const C *) c.grid[block_grid(block, a)], pp, nxb, c.y0, N, NZ, nyl);
     p2p_barrier(c, T);                      // component a has landed everywhere
     CK(cudaEventRecord(c.ev_tr[a], T));
   }
   for (int a = 0; a < 3; a++) {
     CK(cudaStreamWaitEvent(S, c.ev_tr[a], 0));
-    void *src = (char *) c.tbuf_a + (size_t) a * gb, *g = c.grid[MGP_GRID_FORCE_X + a];
+    void *src = (char *) c.tbuf_a + (size_t) a * gb, *g = c.grid[block_grid(block, a)];
     if (sizeof(R) == 4) CKFFT(cufftExecC2R(c.plan2d_c2r, (cufftComplex *) src, (cufftReal *) g));
     else CKFFT(cufftExecZ2D(c.plan2d_c2r, (cufftDoubleComplex *) src, (cufftDoubleReal *) g));
   }
@@ -411,18 +411,21 @@ void fft_c2r(Ctx &c, int gid) {
   c.launches += 3;
 }
 
-void fft_c2r_forces(Ctx &c) {
+void fft_c2r_forces(Ctx &c) { fft_c2r_block(c, 0); }
+
+void fft_c2r_block(Ctx &c, int block) {
+  REQUIRE(block == 0 || (block == 1 && c.aux_block), MGP_ERR_STATE, "batched c2r: block not allocated");
   if (c.P > 1 && c.p2p) {
     PhaseTimer t(c, PH_FFT);
-    if (c.gbytes == 4) dist_c2r3<float, float2>(c); else dist_c2r3<double, double2>(c);
+    if (c.gbytes == 4) dist_c2r3<float, float2>(c, block); else dist_c2r3<double, double2>(c, block);
     return;
   }
   if (c.P > 1) {
-    for (int a = 0; a < 3; a++) fft_c2r(c, MGP_GRID_FORCE_X + a);
+    for (int a = 0; a < 3; a++) fft_c2r(c, block_grid(block, a));
     return;
   }
   PhaseTimer t(c, PH_FFT);
-  void *g = c.force_block;
+  void *g = block == 0 ? c.force_block : c.aux_block;
   if (c.gbytes == 4) CKFFT(cufftExecC2R(c.plan_c2r3, (cufftComplex *) g, (cufftReal *) g));
   else CKFFT(cufftExecZ2D(c.plan_c2r3, (cufftDoubleComplex *) g, (cufftDoubleReal *) g));
   c.launches += 9;
@@ -449,11 +452,13 @@ void halo_add_density(Ctx &c, int gid) {
   c.launches++;
 }
 
-void halo_fill_forces(Ctx &c) {
+void halo_fill_forces(Ctx &c) { halo_fill_block(c, 0); }
+
+void halo_fill_block(Ctx &c, int block) {
   const size_t pb = c.plane_bytes();
   if (c.P == 1) {
     for (int a = 0; a < 3; a++) {
-      char *g = (char *) c.grid[MGP_GRID_FORCE_X + a];
+      char *g = (char *) c.grid[block_grid(block, a)];
       CK(cudaMemcpyAsync(g + (size_t) c.nx * pb, g, pb, cudaMemcpyDeviceToDevice, c.stream));
     }
     return;
@@ -461,7 +466,7 @@ void halo_fill_forces(Ctx &c) {
   PhaseTimer t(c, PH_COMM);
   CKNCCL(ncclGroupStart());
   for (int a = 0; a < 3; a++) {
-    char *g = (char *) c.grid[MGP_GRID_FORCE_X + a];
+    char *g = (char *) c.grid[block_grid(block, a)];
     CKNCCL(ncclSend(g, pb, ncclChar, c.left, c.comm, c.stream));
     CKNCCL(ncclRecv(g + (size_t) c.nx * pb, pb, ncclChar, c.right, c.comm, c.stream));
   }

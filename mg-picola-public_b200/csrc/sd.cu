@@ -35,6 +35,10 @@
 
 namespace mgp {
 
+#ifndef MGP_SD_BLOCKS
+#define MGP_SD_BLOCKS 6        // resident CTAs per SM the fused Kick / Drift kernels are compiled for (register cap 40)
+#endif
+
 // ------------------------------------------------------------------ k-space
 
 // (2LPT.c:1584-1630)  out_a = ( -Im(d) * kvec_a / kmag2 * g , Re(d) * kvec_a / kmag2 * g ),  g = norm * G[m]
@@ -350,8 +354,20 @@ static void sd_assign_t(Ctx &c, int fieldtype, int order, const double *g1, cons
   CK(cudaMemcpyAsync(c.sd_gtab[0], g1, mmax * sizeof(double), cudaMemcpyHostToDevice, c.stream));
   if (merged) CK(cudaMemcpyAsync(c.sd_gtab[1], g2, mmax * sizeof(double), cudaMemcpyHostToDevice, c.stream));
 
-  C *f[3] = {(C *) c.grid[1], (C *) c.grid[2], (C *) c.grid[3]};
-  const T *fr[3] = {(const T *) c.grid[1], (const T *) c.grid[2], (const T *) c.grid[3]};
+  // destination slot (2LPT.c:1817-1827): D / ddDddy -> D (order 1) or D2 (order 2); dDdy / deltaD -> dDdy or dD2dy
+  const int pair = (fieldtype == MGP_FIELD_D || fieldtype == MGP_FIELD_DDDDDY) ? 0 : 2;
+  const int slot = pair + ((merged || order == 1) ? 0 : 1);
+  // merged fields stay resident in their grid block until Kick (pair 0, force grids) / Drift (pair 1, grids 0, 4, 5)
+  // read them; separate orders share the force grids and go to the per-particle arrays at once
+  static const bool lazy_env = !(getenv("MGP_SD_LAZY") && atoi(getenv("MGP_SD_LAZY")) == 0);
+  REQUIRE(!c.forces_live, MGP_ERR_STATE, "scale-dependent fields: the force grids are in use (call mgp_mtoparticles first)");
+  // pair 1 would live in grids 0, 4, 5: not while they hold this step's density (RSD multipoles inside PtoMesh)
+  const bool lazy = merged && lazy_env && c.aux_block != nullptr && !c.sd_lagrangian_only && !(pair == 2 && c.density_live);
+  const int block = (lazy && pair == 2) ? 1 : 0;
+  c.sd_res[pair / 2] = -1;                                      // the old field of this pair is dead
+  sd_evict_block(c, block);
+  C *f[3]; const T *fr[3];
+  for (int a = 0; a < 3; a++) { f[a] = (C *) c.grid[block_grid(block, a)]; fr[a] = (const T *) c.grid[block_grid(block, a)]; }
   {
     PhaseTimer t(c, PH_SDFIELD);
     const C *src1 = (const C *) c.sd_delta[(merged || order == 1) ? 0 : 1];
@@ -361,8 +377,8 @@ static void sd_assign_t(Ctx &c, int fieldtype, int order, const double *g1, cons
                                                                f[0], f[1], f[2], c.cfg.box);
     c.launches++;
   }
-  fft_c2r_forces(c);
-  halo_fill_forces(c);                                          // 2LPT.c:1638-1639
+  fft_c2r_block(c, block);
+  halo_fill_block(c, block);                                    // 2LPT.c:1638-1639
 
   const size_t nloc = (size_t) c.npl * ns * ns;
   double mean[3] = {0, 0, 0};
@@ -384,11 +400,8 @@ static void sd_assign_t(Ctx &c, int fieldtype, int order, const double *g1, cons
     for (int a = 0; a < 3; a++) mean[a] = c.h_red[a] / tot;     // sumdis_D /= TotNumPart (2LPT.c:1716-1719)
   }
 
-  // destination slot (2LPT.c:1817-1827): D / ddDddy -> D (order 1) or D2 (order 2); dDdy / deltaD -> dDdy or dD2dy
-  const int pair = (fieldtype == MGP_FIELD_D || fieldtype == MGP_FIELD_DDDDDY) ? 0 : 2;
-  const int slot = pair + ((merged || order == 1) ? 0 : 1);
   float *out = c.sdf[slot];
-  {
+  if (!lazy) {
     PhaseTimer t(c, PH_SDASSIGN);
     const bool id32 = (double) ns * ns * ns < 4294967296.0;
     if (c.np && id32)
@@ -428,6 +441,43 @@ static void sd_assign_t(Ctx &c, int fieldtype, int order, const double *g1, cons
   if (merged) c.sd_zero[slot + 1] = true;                        // the second-order slot reads as 0
   c.sd_set[slot] = true;
   if (merged) c.sd_set[slot + 1] = true;
+  if (lazy) {
+    c.sd_res[pair / 2] = block;
+    for (int a = 0; a < 3; a++) c.sd_res_mean[pair / 2][a] = mean[a];
+  }
+}
+
+// resident merged field -> the per-particle array of its first-order slot (the remote-born entries are there already)
+template <typename T>
+static void sd_materialise_t(Ctx &c, int pr) {
+  const int block = c.sd_res[pr], ns = c.cfg.nsample;
+  const T *fr[3];
+  for (int a = 0; a < 3; a++) fr[a] = (const T *) c.grid[block_grid(block, a)];
+  const double *m = c.sd_res_mean[pr];
+  PhaseTimer t(c, PH_SDASSIGN);
+  const bool id32 = (double) ns * ns * ns < 4294967296.0;
+  if (c.np && id32)
+    k_sd_assign<T, 1><<<grid_for(c.np, 256), 256, 0, c.stream>>>(c.np, c.pA, c.pB, ns, c.p0, c.npl, c.N, c.NZ, c.x0, c.nx, fr[0], fr[1],
+                                                                fr[2], m[0], m[1], m[2], c.sdf[2 * pr], c.cap);
+  else if (c.np)
+    k_sd_assign<T, 0><<<grid_for(c.np, 256), 256, 0, c.stream>>>(c.np, c.pA, c.pB, ns, c.p0, c.npl, c.N, c.NZ, c.x0, c.nx, fr[0], fr[1],
+                                                                fr[2], m[0], m[1], m[2], c.sdf[2 * pr], c.cap);
+  c.launches++;
+  c.sd_res[pr] = -1;
+}
+
+void sd_materialise(Ctx &c, int pr) {
+  if (pr < 0 || pr > 1 || c.sd_res[pr] < 0) return;
+  if (c.gbytes == 4) sd_materialise_t<float>(c, pr); else sd_materialise_t<double>(c, pr);
+}
+
+void sd_evict_block(Ctx &c, int block) {
+  for (int pr = 0; pr < 2; pr++) if (c.sd_res[pr] == block) sd_materialise(c, pr);
+}
+
+void sd_drop(Ctx &c) {
+  c.sd_res[0] = c.sd_res[1] = -1;
+  for (int s = 0; s < 4; s++) c.sd_set[s] = false;
 }
 
 void sd_assign(Ctx &c, int fieldtype, int order, const double *g1, const double *g2, size_t n) {
@@ -502,11 +552,14 @@ k_kick_sd(size_t n, float4 *__restrict__ pB, const float *__restrict__ D, const 
   for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
     float4 v = pB[i];
     float vel[3] = {v.x, v.y, v.z};
+    const float dsp[3] = {disp[i], disp[cap + i], disp[2 * cap + i]};      // all loads before the first store
+    const float d1[3] = {D[i], D[cap + i], D[2 * cap + i]};
+    const float d2[3] = {D2 ? D2[i] : 0.0f, D2 ? D2[cap + i] : 0.0f, D2 ? D2[2 * cap + i] : 0.0f};
 #pragma unroll
     for (int ax = 0; ax < 3; ax++) {
-      const float g = (float) __dsub_rn((double) disp[ax * cap + i], sD[ax]);
+      const float g = (float) __dsub_rn((double) dsp[ax], sD[ax]);
       disp[ax * cap + i] = g;
-      const float dd = __fmul_rn(usecola, __fadd_rn(D[ax * cap + i], D2 ? D2[ax * cap + i] : 0.0f));
+      const float dd = __fmul_rn(usecola, __fadd_rn(d1[ax], d2[ax]));
       const double f = __dsub_rn(__dmul_rn(m15omega, (double) g), __ddiv_rn((double) dd, A));
       vel[ax] = (float) __dadd_rn((double) vel[ax], __dmul_rn(f, dda));
       s[ax] += (double) vel[ax];
@@ -518,12 +571,114 @@ k_kick_sd(size_t n, float4 *__restrict__ pB, const float *__restrict__ D, const 
   if (threadIdx.x == 0) { partial[3 * blockIdx.x] = s[0]; partial[3 * blockIdx.x + 1] = s[1]; partial[3 * blockIdx.x + 2] = s[2]; }
 }
 
+// per-particle value of a resident merged field: interpolated at the Lagrangian point of the particle's ID when that
+// point is on this rank, else the value its birth rank sent (already scattered into `remote`)
+struct SdRes {
+  const void *g0, *g1, *g2;
+  const float *remote;
+  double m0, m1, m2;
+  int ns, p0, npl, N, NZ, x0, nx;
+};
+
+template <typename T, int ID32>
+__device__ __forceinline__ void sd_resident_value(const SdRes &R, unsigned idlo, unsigned idhi, size_t i, size_t cap, float D[3]) {
+  const unsigned long long ns2 = (unsigned long long) R.ns * R.ns;
+  const unsigned long long id = ID32 ? (unsigned long long) idlo : (((unsigned long long) idhi << 32) | idlo);
+  const long long n = (long long) (id / ns2);
+  if (n < R.p0 || n >= R.p0 + R.npl) {
+    D[0] = R.remote[i]; D[1] = R.remote[cap + i]; D[2] = R.remote[2 * cap + i];
+    return;
+  }
+  const unsigned rem = (unsigned) (id - (unsigned long long) n * ns2);
+  double r[3];
+  sd_interp<T>(n, (int) (rem / R.ns), (int) (rem % R.ns), R.ns, R.N, R.NZ, R.x0, R.nx, (const T *) R.g0, (const T *) R.g1,
+               (const T *) R.g2, r);
+  D[0] = sd_value<T>(r[0], R.m0); D[1] = sd_value<T>(r[1], R.m1); D[2] = sd_value<T>(r[2], R.m2);
+}
+
+static SdRes sd_res_of(const Ctx &c, int pr) {
+  SdRes R;
+  const int block = c.sd_res[pr];
+  R.g0 = c.grid[block_grid(block, 0)]; R.g1 = c.grid[block_grid(block, 1)]; R.g2 = c.grid[block_grid(block, 2)];
+  R.remote = c.sdf[2 * pr];
+  R.m0 = c.sd_res_mean[pr][0]; R.m1 = c.sd_res_mean[pr][1]; R.m2 = c.sd_res_mean[pr][2];
+  R.ns = c.cfg.nsample; R.p0 = c.p0; R.npl = c.npl; R.N = c.N; R.NZ = c.NZ; R.x0 = c.x0; R.nx = c.nx;
+  return R;
+}
+
+// Kick with the D + D2 field read straight from the grids it was transformed in (no per-particle copy)
+template <typename T, int ID32>
+__global__ void __launch_bounds__(256, MGP_SD_BLOCKS)
+k_kick_sd_fused(size_t n, const float4 *__restrict__ pA, float4 *__restrict__ pB, SdRes R, float *__restrict__ disp, size_t cap,
+                double sDx, double sDy, double sDz, double m15omega, float usecola, double A, double dda,
+                double *__restrict__ partial) {
+  double s[3] = {0, 0, 0};
+  const double sD[3] = {sDx, sDy, sDz};
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+    float4 v = pB[i];
+    const unsigned idlo = __float_as_uint(pA[i].w);
+    const float dsp[3] = {disp[i], disp[cap + i], disp[2 * cap + i]};      // all loads before the first store
+    float D[3];
+    sd_resident_value<T, ID32>(R, idlo, __float_as_uint(v.w), i, cap, D);
+    float vel[3] = {v.x, v.y, v.z};
+#pragma unroll
+    for (int ax = 0; ax < 3; ax++) {
+      const float g = (float) __dsub_rn((double) dsp[ax], sD[ax]);
+      disp[ax * cap + i] = g;
+      const float dd = __fmul_rn(usecola, __fadd_rn(D[ax], 0.0f));
+      const double f = __dsub_rn(__dmul_rn(m15omega, (double) g), __ddiv_rn((double) dd, A));
+      vel[ax] = (float) __dadd_rn((double) vel[ax], __dmul_rn(f, dda));
+      s[ax] += (double) vel[ax];
+    }
+    v.x = vel[0]; v.y = vel[1]; v.z = vel[2];
+    pB[i] = v;
+  }
+  block_sum3(s[0], s[1], s[2]);
+  if (threadIdx.x == 0) { partial[3 * blockIdx.x] = s[0]; partial[3 * blockIdx.x + 1] = s[1]; partial[3 * blockIdx.x + 2] = s[2]; }
+}
+
+template <typename T, int ID32>
+__global__ void __launch_bounds__(256, MGP_SD_BLOCKS)
+k_drift_sd_fused(size_t n, float4 *__restrict__ pA, const float4 *__restrict__ pB, SdRes R, size_t cap, double sVx, double sVy,
+                 double sVz, double dyyy, float usecola, float boxf) {
+  const double sV[3] = {sVx, sVy, sVz};
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+    float4 p = pA[i];
+    const float4 v = pB[i];
+    float D[3];
+    sd_resident_value<T, ID32>(R, __float_as_uint(p.w), __float_as_uint(v.w), i, cap, D);
+    float x[3] = {p.x, p.y, p.z};
+    const float vel[3] = {v.x, v.y, v.z};
+#pragma unroll
+    for (int ax = 0; ax < 3; ax++) {
+      float t = (float) __dadd_rn((double) x[ax], __dmul_rn(__dsub_rn((double) vel[ax], sV[ax]), dyyy));
+      t = __fadd_rn(t, __fmul_rn(usecola, __fadd_rn(D[ax], 0.0f)));
+      while (t >= boxf) t -= boxf;
+      while (t < 0) t += boxf;
+      if (t == boxf) t = 0.0f;
+      x[ax] = t;
+    }
+    p.x = x[0]; p.y = x[1]; p.z = x[2];
+    pA[i] = p;
+  }
+}
+
 void sd_kick(Ctx &c, double A, double dda, const double sumD[3], double sumV[3]) {
   REQUIRE(c.sd_set[0] && c.sd_set[1], MGP_ERR_STATE, "mgp_kick (scale-dependent): assign FIELD_ddDddy first");
   const size_t n = c.np;
   const unsigned g = grid_for(n, 256, 8);
   reduce_alloc(c, (size_t) g * 3 + 16);
   double *res = c.d_red + (size_t) g * 3;
+  if (c.sd_res[0] >= 0) {
+    const SdRes R = sd_res_of(c, 0);
+    const bool id32 = (double) R.ns * R.ns * R.ns < 4294967296.0;
+    const double m15 = -1.5 * c.cfg.omega;
+    const float uc = (float) c.cfg.use_cola;
+#define KICK_FUSED(T, I) k_kick_sd_fused<T, I><<<g, 256, 0, c.stream>>>(n, c.pA, c.pB, R, c.disp, c.cap, sumD[0], sumD[1], sumD[2], m15, uc, A, dda, c.d_red)
+    if (c.gbytes == 4) { if (id32) KICK_FUSED(float, 1); else KICK_FUSED(float, 0); }
+    else { if (id32) KICK_FUSED(double, 1); else KICK_FUSED(double, 0); }
+#undef KICK_FUSED
+  } else
   k_kick_sd<<<g, 256, 0, c.stream>>>(n, c.pB, c.sdf[0], c.sd_zero[1] ? nullptr : c.sdf[1], c.disp, c.cap, sumD[0], sumD[1],
                                      sumD[2], -1.5 * c.cfg.omega, (float) c.cfg.use_cola, A, dda, c.d_red);
   k_final_reduce<<<1, 256, 0, c.stream>>>(c.d_red, (int) g, 3, 3, 1.0, res);
@@ -563,7 +718,17 @@ k_drift_sd(size_t n, float4 *__restrict__ pA, const float4 *__restrict__ pB, con
 void sd_drift(Ctx &c, double dyyy, const double sumV[3]) {
   REQUIRE(c.sd_set[2] && c.sd_set[3], MGP_ERR_STATE, "mgp_drift (scale-dependent): assign FIELD_deltaD first");
   const size_t n = c.np;
-  if (n) {
+  if (n && c.sd_res[1] >= 0) {
+    const SdRes R = sd_res_of(c, 1);
+    const bool id32 = (double) R.ns * R.ns * R.ns < 4294967296.0;
+    const float uc = (float) c.cfg.use_cola, bx = (float) c.cfg.box;
+    const unsigned g = grid_for(n, 256);
+#define DRIFT_FUSED(T, I) k_drift_sd_fused<T, I><<<g, 256, 0, c.stream>>>(n, c.pA, c.pB, R, c.cap, sumV[0], sumV[1], sumV[2], dyyy, uc, bx)
+    if (c.gbytes == 4) { if (id32) DRIFT_FUSED(float, 1); else DRIFT_FUSED(float, 0); }
+    else { if (id32) DRIFT_FUSED(double, 1); else DRIFT_FUSED(double, 0); }
+#undef DRIFT_FUSED
+    c.launches++;
+  } else if (n) {
     k_drift_sd<<<grid_for(n, 256), 256, 0, c.stream>>>(n, c.pA, c.pB, c.sdf[2], c.sd_zero[3] ? nullptr : c.sdf[3], c.cap, sumV[0],
                                                       sumV[1], sumV[2], dyyy, (float) c.cfg.use_cola, (float) c.cfg.box);
     c.launches++;
@@ -589,6 +754,7 @@ void sd_free(Ctx &c) {
 // host [n][3] <-> device [3][cap]
 void sd_copy_field(Ctx &c, int slot, float *host, bool to_host) {
   REQUIRE(slot >= 0 && slot < 4 && c.sdf[slot], MGP_ERR_STATE, "scale-dependent field storage missing");
+  if (to_host) sd_materialise(c, slot / 2); else c.sd_res[slot / 2] = -1;
   std::vector<float> tmp(c.np);
   for (int a = 0; a < 3; a++) {
     float *dev = c.sdf[slot] + (size_t) a * c.cap;
