@@ -580,7 +580,8 @@ struct SdRes {
   int ns, p0, npl, N, NZ, x0, nx;
 };
 
-template <typename T, int ID32>
+// EXACT: Nmesh is a multiple of Nsample, every lattice point is a mesh point and the read-out is one load per grid
+template <typename T, int ID32, int EXACT>
 __device__ __forceinline__ void sd_resident_value(const SdRes &R, unsigned idlo, unsigned idhi, size_t i, size_t cap, float D[3]) {
   const unsigned long long ns2 = (unsigned long long) R.ns * R.ns;
   const unsigned long long id = ID32 ? (unsigned long long) idlo : (((unsigned long long) idhi << 32) | idlo);
@@ -591,8 +592,14 @@ __device__ __forceinline__ void sd_resident_value(const SdRes &R, unsigned idlo,
   }
   const unsigned rem = (unsigned) (id - (unsigned long long) n * ns2);
   double r[3];
-  sd_interp<T>(n, (int) (rem / R.ns), (int) (rem % R.ns), R.ns, R.N, R.NZ, R.x0, R.nx, (const T *) R.g0, (const T *) R.g1,
-               (const T *) R.g2, r);
+  if (EXACT) {
+    const int f = R.N / R.ns;
+    const size_t e = (((size_t) ((int) n * f - R.x0)) * R.N + (size_t) (rem / R.ns) * f) * (size_t) (2 * R.NZ) + (size_t) (rem % R.ns) * f;
+    r[0] = (double) ((const T *) R.g0)[e]; r[1] = (double) ((const T *) R.g1)[e]; r[2] = (double) ((const T *) R.g2)[e];
+  } else {
+    sd_interp<T>(n, (int) (rem / R.ns), (int) (rem % R.ns), R.ns, R.N, R.NZ, R.x0, R.nx, (const T *) R.g0, (const T *) R.g1,
+                 (const T *) R.g2, r);
+  }
   D[0] = sd_value<T>(r[0], R.m0); D[1] = sd_value<T>(r[1], R.m1); D[2] = sd_value<T>(r[2], R.m2);
 }
 
@@ -607,8 +614,8 @@ static SdRes sd_res_of(const Ctx &c, int pr) {
 }
 
 // Kick with the D + D2 field read straight from the grids it was transformed in (no per-particle copy)
-template <typename T, int ID32>
-__global__ void __launch_bounds__(256, MGP_SD_BLOCKS)
+template <typename T, int ID32, int EXACT, int BL>
+__global__ void __launch_bounds__(256, BL)
 k_kick_sd_fused(size_t n, const float4 *__restrict__ pA, float4 *__restrict__ pB, SdRes R, float *__restrict__ disp, size_t cap,
                 double sDx, double sDy, double sDz, double m15omega, float usecola, double A, double dda,
                 double *__restrict__ partial) {
@@ -619,7 +626,7 @@ k_kick_sd_fused(size_t n, const float4 *__restrict__ pA, float4 *__restrict__ pB
     const unsigned idlo = __float_as_uint(pA[i].w);
     const float dsp[3] = {disp[i], disp[cap + i], disp[2 * cap + i]};      // all loads before the first store
     float D[3];
-    sd_resident_value<T, ID32>(R, idlo, __float_as_uint(v.w), i, cap, D);
+    sd_resident_value<T, ID32, EXACT>(R, idlo, __float_as_uint(v.w), i, cap, D);
     float vel[3] = {v.x, v.y, v.z};
 #pragma unroll
     for (int ax = 0; ax < 3; ax++) {
@@ -637,8 +644,8 @@ k_kick_sd_fused(size_t n, const float4 *__restrict__ pA, float4 *__restrict__ pB
   if (threadIdx.x == 0) { partial[3 * blockIdx.x] = s[0]; partial[3 * blockIdx.x + 1] = s[1]; partial[3 * blockIdx.x + 2] = s[2]; }
 }
 
-template <typename T, int ID32>
-__global__ void __launch_bounds__(256, MGP_SD_BLOCKS)
+template <typename T, int ID32, int EXACT>
+__global__ void __launch_bounds__(256, EXACT ? MGP_SD_BLOCKS : 4)
 k_drift_sd_fused(size_t n, float4 *__restrict__ pA, const float4 *__restrict__ pB, SdRes R, size_t cap, double sVx, double sVy,
                  double sVz, double dyyy, float usecola, float boxf) {
   const double sV[3] = {sVx, sVy, sVz};
@@ -646,7 +653,7 @@ k_drift_sd_fused(size_t n, float4 *__restrict__ pA, const float4 *__restrict__ p
     float4 p = pA[i];
     const float4 v = pB[i];
     float D[3];
-    sd_resident_value<T, ID32>(R, __float_as_uint(p.w), __float_as_uint(v.w), i, cap, D);
+    sd_resident_value<T, ID32, EXACT>(R, __float_as_uint(p.w), __float_as_uint(v.w), i, cap, D);
     float x[3] = {p.x, p.y, p.z};
     const float vel[3] = {v.x, v.y, v.z};
 #pragma unroll
@@ -674,9 +681,13 @@ void sd_kick(Ctx &c, double A, double dda, const double sumD[3], double sumV[3])
     const bool id32 = (double) R.ns * R.ns * R.ns < 4294967296.0;
     const double m15 = -1.5 * c.cfg.omega;
     const float uc = (float) c.cfg.use_cola;
-#define KICK_FUSED(T, I) k_kick_sd_fused<T, I><<<g, 256, 0, c.stream>>>(n, c.pA, c.pB, R, c.disp, c.cap, sumD[0], sumD[1], sumD[2], m15, uc, A, dda, c.d_red)
-    if (c.gbytes == 4) { if (id32) KICK_FUSED(float, 1); else KICK_FUSED(float, 0); }
-    else { if (id32) KICK_FUSED(double, 1); else KICK_FUSED(double, 0); }
+    const bool exact = c.N % R.ns == 0;
+    static const int kb = getenv("MGP_KICK_BLOCKS") ? atoi(getenv("MGP_KICK_BLOCKS")) : 4;     // developer knob
+#define KICK_FUSED(T, I, E, B) k_kick_sd_fused<T, I, E, B><<<g, 256, 0, c.stream>>>(n, c.pA, c.pB, R, c.disp, c.cap, sumD[0], sumD[1], sumD[2], m15, uc, A, dda, c.d_red)
+#define KICK_FUSED_T(T) do { if (id32 && exact) { if (kb == 5) KICK_FUSED(T, 1, 1, 5); else if (kb == 4) KICK_FUSED(T, 1, 1, 4); else KICK_FUSED(T, 1, 1, 6); } \
+                             else if (id32) KICK_FUSED(T, 1, 0, 4); else if (exact) KICK_FUSED(T, 0, 1, 5); else KICK_FUSED(T, 0, 0, 4); } while (0)
+    if (c.gbytes == 4) KICK_FUSED_T(float); else KICK_FUSED_T(double);
+#undef KICK_FUSED_T
 #undef KICK_FUSED
   } else
   k_kick_sd<<<g, 256, 0, c.stream>>>(n, c.pB, c.sdf[0], c.sd_zero[1] ? nullptr : c.sdf[1], c.disp, c.cap, sumD[0], sumD[1],
@@ -723,9 +734,11 @@ void sd_drift(Ctx &c, double dyyy, const double sumV[3]) {
     const bool id32 = (double) R.ns * R.ns * R.ns < 4294967296.0;
     const float uc = (float) c.cfg.use_cola, bx = (float) c.cfg.box;
     const unsigned g = grid_for(n, 256);
-#define DRIFT_FUSED(T, I) k_drift_sd_fused<T, I><<<g, 256, 0, c.stream>>>(n, c.pA, c.pB, R, c.cap, sumV[0], sumV[1], sumV[2], dyyy, uc, bx)
-    if (c.gbytes == 4) { if (id32) DRIFT_FUSED(float, 1); else DRIFT_FUSED(float, 0); }
-    else { if (id32) DRIFT_FUSED(double, 1); else DRIFT_FUSED(double, 0); }
+    const bool exact = c.N % R.ns == 0;
+#define DRIFT_FUSED(T, I, E) k_drift_sd_fused<T, I, E><<<g, 256, 0, c.stream>>>(n, c.pA, c.pB, R, c.cap, sumV[0], sumV[1], sumV[2], dyyy, uc, bx)
+#define DRIFT_FUSED_T(T) do { if (id32 && exact) DRIFT_FUSED(T, 1, 1); else if (id32) DRIFT_FUSED(T, 1, 0); else if (exact) DRIFT_FUSED(T, 0, 1); else DRIFT_FUSED(T, 0, 0); } while (0)
+    if (c.gbytes == 4) DRIFT_FUSED_T(float); else DRIFT_FUSED_T(double);
+#undef DRIFT_FUSED_T
 #undef DRIFT_FUSED
     c.launches++;
   } else if (n) {
