@@ -277,9 +277,18 @@ def run_ours(args):
     own = {k: phases.get(k, 0.0) for k in ("PtoMesh", "MtoParticles", "Forces", "ComputeFifthForce", "Kick", "Drift", "Sort", "Pofk", "SDField", "SDAssign")}
     dom = max(("PtoMesh", "MtoParticles"), key=lambda k: own.get(k, 0.0))
     ach = kern_bytes[dom] / (own[dom] * 1e-3) / 1e9 if own.get(dom) else None
-    roof = {"bound": "hbm", "kernel": {"PtoMesh": ["k_deposit_atomic", "k_deposit_tile", "k_deposit_rowseg"][args.deposit_mode] + " (CIC deposit)",
-                       "MtoParticles": "k_gather (trilinear gather)"}[dom],
-            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None, "traffic": None,
+    kname = {"PtoMesh": ["k_deposit_atomic", "k_deposit_tile", "k_deposit_rowseg"][args.deposit_mode], "MtoParticles": "k_gather"}[dom]
+    traffic = None          # DRAM bytes per launch of that kernel from the committed ncu --set full capture (same command, 256^3)
+    try:
+        if N == 256 and world == 1:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01b_traffic.json")))
+            traffic = next((v for k, v in tr.items() if k.startswith(kname)), None)
+    except Exception:
+        pass
+    roof = {"bound": "hbm", "kernel": kname + {"PtoMesh": " (CIC deposit, incl. the fill kernel in the timed phase)", "MtoParticles": " (trilinear gather)"}[dom],
+            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None, "traffic": traffic,
+            "note": "the deposit is bound by the L2 reduction unit, not by HBM: 8 RED.ADD.F64 per particle at ~0.72 cycles per lane and SM "
+                    "= 0.29 ms of its 0.32 ms at 256^3 (DESIGN.md section 5); the whole step runs at roofline.step.frac of the copy bandwidth",
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)",
             "step": {"algorithmic_bytes_per_particle": A_min, "achieved": A_min * npart_total / (ms_per_step * 1e-3) / 1e9,
                      "frac": A_min * npart_total / (ms_per_step * 1e-3) / 1e9 / peak},
