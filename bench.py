@@ -274,6 +274,17 @@ def run_ours(args):
     # dominant hand-written kernels: deposit (PtoMesh phase) and gather (MtoParticles phase)
     kern_bytes = {"PtoMesh": (16 + g) * (N ** 3) / max(world, 1),            # Pos(+id) 16 B read, grid g write per cell
                   "MtoParticles": (16 + 3 * g + 12) * (N ** 3) / max(world, 1)}   # Pos 16 R, 3 grids R, Disp 12 W
+    # whole-step roofline per GPU: HBM time of the algorithmic bytes + NVLink time of the slab transposes
+    # (g * n/P * (P-1)/P bytes per distributed FFT and direction; 770 GB/s measured peer copy)
+    nfft = {"lcdm": 4, "fofr": 6, "dgp": 6}[model] + ((6 if args.sd_mode == "merged" else 12) if use_sd else 0)
+    n_loc = npart_total / world
+    t_hbm = A_min * n_loc / (peak * 1e9)
+    nvl_bytes = nfft * g * n_loc * (world - 1) / world
+    t_nvl = nvl_bytes / 770e9
+    step_roof = {"algorithmic_bytes_per_particle": A_min, "ffts_per_step": nfft,
+                 "achieved": A_min * n_loc / (ms_per_step * 1e-3) / 1e9, "hbm_ms": t_hbm * 1e3,
+                 "nvlink_bytes_per_gpu": nvl_bytes, "nvlink_ms": t_nvl * 1e3, "nvlink_peak": "770 GB/s per direction (B200_PROFILING.md, measured peer copy)",
+                 "frac": (t_hbm + t_nvl) / (ms_per_step * 1e-3)}
     own = {k: phases.get(k, 0.0) for k in ("PtoMesh", "MtoParticles", "Forces", "ComputeFifthForce", "Kick", "Drift", "Sort", "Pofk", "SDField", "SDAssign")}
     dom = max(("PtoMesh", "MtoParticles"), key=lambda k: own.get(k, 0.0))
     ach = kern_bytes[dom] / (own[dom] * 1e-3) / 1e9 if own.get(dom) else None
@@ -290,8 +301,7 @@ def run_ours(args):
             "note": "the deposit is bound by the L2 reduction unit, not by HBM: 8 RED.ADD.F64 per particle at ~0.72 cycles per lane and SM "
                     "= 0.29 ms of its 0.32 ms at 256^3 (DESIGN.md section 5); the whole step runs at roofline.step.frac of the copy bandwidth",
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)",
-            "step": {"algorithmic_bytes_per_particle": A_min, "achieved": A_min * npart_total / (ms_per_step * 1e-3) / 1e9,
-                     "frac": A_min * npart_total / (ms_per_step * 1e-3) / 1e9 / peak},
+            "step": step_roof,
             "phases_ms": {k: round(v, 4) for k, v in phases.items()}}
     line = {"metric": "particle-updates/sec per COLA PM step", "value": value, "unit": "particle-updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,

@@ -69,6 +69,31 @@ k_migrate_pack(size_t n, const float4 *__restrict__ pA, const float4 *__restrict
   }
 }
 
+// After the exchange the array holds [0, n): the old particles with the leavers still in place, and [n, n + nrecv):
+// the arrivals.  Instead of a full sort, the leavers' slots below the new count are refilled with the live particles
+// above it (order inside a cell-sorted array is only perturbed at ~1 % of the positions, which the warp-aggregated
+// deposit and the gather tolerate; the periodic sort restores it).
+__global__ void __launch_bounds__(256)
+k_compact_lists(size_t n, size_t ntot, size_t newn, const float4 *__restrict__ pA, double scale, int N, int block, int P, int me,
+                unsigned *__restrict__ counters, uint32_t *__restrict__ holes, uint32_t *__restrict__ movers) {
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < ntot; i += (size_t) gridDim.x * blockDim.x) {
+    const bool leaver = i < n && owner_of(pA[i].x, scale, N, block, P) != me;
+    if (i < newn) { if (leaver) holes[atomicAdd(&counters[0], 1u)] = (uint32_t) i; }
+    else if (!leaver) movers[atomicAdd(&counters[1], 1u)] = (uint32_t) i;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_compact_move(const unsigned *__restrict__ counters, const uint32_t *__restrict__ holes, const uint32_t *__restrict__ movers,
+               float4 *__restrict__ pA, float4 *__restrict__ pB, float4 *__restrict__ pC, float2 *__restrict__ pE) {
+  const unsigned h = counters[0] < counters[1] ? counters[0] : counters[1];
+  for (size_t k = blockIdx.x * (size_t) blockDim.x + threadIdx.x; k < h; k += (size_t) gridDim.x * blockDim.x) {
+    const uint32_t d = holes[k], s = movers[k];
+    pA[d] = pA[s]; pB[d] = pB[s];
+    if (pC) { pC[d] = pC[s]; pE[d] = pE[s]; }
+  }
+}
+
 void particles_migrate(Ctx &c) {
   if (c.P == 1) return;
   const int P = c.P, me = c.rank;
@@ -76,8 +101,8 @@ void particles_migrate(Ctx &c) {
   const double scale = (double) c.N / c.cfg.box;
   const int block = (c.N + P - 1) / P;
   if (!c.mig_dev) {
-    CK(cudaMalloc(&c.mig_dev, (size_t) (P * P + 3 * P) * sizeof(unsigned)));
-    CK(cudaMallocHost(&c.mig_host, (size_t) (P * P + 3 * P) * sizeof(unsigned)));
+    CK(cudaMalloc(&c.mig_dev, (size_t) (P * P + 3 * P + 2) * sizeof(unsigned)));
+    CK(cudaMallocHost(&c.mig_host, (size_t) (P * P + 3 * P + 2) * sizeof(unsigned)));
   }
   unsigned *d_cnt = c.mig_dev;              // [P]      my per-destination counts
   unsigned *d_all = c.mig_dev + P;          // [P][P]   all ranks' counts (row = sender)
@@ -152,12 +177,30 @@ void particles_migrate(Ctx &c) {
     }
     CKNCCL(ncclGroupEnd());
   }
+  c.have_disp = false;
+  c.sd_req_valid = false;
+  const size_t ntot = n + nrecv, newn = n + nrecv - nsend;
+  static const bool compact_env = !(getenv("MGP_COMPACT") && atoi(getenv("MGP_COMPACT")) == 0);
+  const bool exact_needed = c.cfg.deposit_mode != MGP_DEPOSIT_ATOMIC;
+  const bool sort_due = !c.cfg.sort_particles || c.drifts_since_sort >= c.cfg.sort_particles;
+  if (compact_env && !exact_needed && !sort_due && c.cfg.sort_particles) {
+    // hole compaction: leavers' slots below the new count are refilled from above it
+    unsigned *d_two = c.mig_dev + P + P * P + 2 * P;          // two spare counters behind the pack cursors
+    CK(cudaMemsetAsync(d_two, 0, 2 * sizeof(unsigned), c.stream));
+    k_compact_lists<<<grid_for(ntot, 256), 256, 0, c.stream>>>(n, ntot, newn, c.pA, scale, c.N, block, P, me, d_two, c.key[0], c.perm[0]);
+    k_compact_move<<<grid_for(nsend ? nsend : 1, 256), 256, 0, c.stream>>>(d_two, c.key[0], c.perm[0], c.pA, c.pB,
+                                                                        c.cfg.scale_dependent ? nullptr : c.pC, (float2 *) c.pE);
+    c.launches += 2;
+    c.np = newn;
+    c.np_after_sort = SIZE_MAX;
+    c.sorted = false;
+    return;
+  }
   // the leavers are still in place; the sort that follows drops them (ownership is recomputed there)
-  c.np = n + nrecv;
-  c.np_after_sort = n + nrecv - nsend;
+  c.np = ntot;
+  c.np_after_sort = newn;
   c.sorted = false;
   c.drifts_since_sort = 1 << 30;
-  c.have_disp = false;
 }
 
 }  // namespace mgp
