@@ -136,6 +136,10 @@ int mgp_destroy(mgp_ctx *ctx);
 /* slab layout as the reference globals: Local_nx, Local_x_start, Local_np, Local_p_start, NumPart */
 int mgp_get_layout(mgp_ctx *ctx, int *local_nx, int *local_x_start, int *local_np,
                    int *local_p_start, uint64_t *numpart);
+/* k-space layout of this rank's grids after mgp_fft_r2c: 0 = [kx][ky][kz] as FFTW's non-transposed in-place r2c
+ * (2LPT.c:50, single rank); 1 = [ky_local][kz][kx], the slab-decomposed transforms' transposed output (what
+ * FFTW_MPI_TRANSPOSED_OUT would give); *ky_start / *ky_local = the ky rows this rank holds.  Pointers may be NULL. */
+int mgp_kspace_layout(mgp_ctx *ctx, int *transposed, int *ky_start, int *ky_local);
 
 /* ---- particle store (struct part_data, vars.h:293-321; GPU-resident SoA) ---- */
 /* load n particles of this rank from host arrays laid out [n][3] (D2, id may be NULL) */

@@ -72,6 +72,7 @@ def load_library(path=None):
     L.mgp_destroy.argtypes = [C.c_void_p]
     L.mgp_nccl_unique_id.argtypes = [C.c_void_p]
     L.mgp_get_layout.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4 + [C.POINTER(C.c_uint64)]
+    L.mgp_kspace_layout.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 3
     fp, dp, up = C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_uint64)
     L.mgp_upload_particles.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mgp_download_particles.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -178,6 +179,9 @@ class PM:
         npart = C.c_uint64()
         self._ck(self.L.mgp_get_layout(self.ctx, *[C.byref(x) for x in lay], C.byref(npart)))
         self.local_nx, self.local_x_start, self.local_np, self.local_p_start = [x.value for x in lay]
+        kl = [C.c_int() for _ in range(3)]
+        self._ck(self.L.mgp_kspace_layout(self.ctx, *[C.byref(x) for x in kl]))
+        self.k_transposed, self.ky_start, self.ky_local = [x.value for x in kl]
         self.sumDxyz = np.zeros(3)
         self.sumxyz = np.zeros(3)
 
@@ -276,11 +280,16 @@ class PM:
         self._ck(self.L.mgp_upload_sd_fields(self.ctx, _ptr(a), _ptr(b)))
 
     def upload_grid_k(self, gid, arr_k):
-        """k-space array [N][N][N/2+1] complex -> the padded slab layout (single rank)."""
+        """k-space array [N][N][N/2+1] complex (all kx, ky, kz) -> this rank's k-space layout: the padded slab
+        [kx][ky][kz] on a single rank, the transposed rows [ky_local][kz][kx] with slab-decomposed transforms."""
         N = self.N
-        full = np.zeros((self.local_nx + 1, N, N // 2 + 1), self.cdtype)
-        full[: self.local_nx] = arr_k
-        self.upload_grid(gid, full.reshape(-1).view(self.gdtype))
+        full = np.zeros(((self.local_nx + 1) * N * (N // 2 + 1)), self.cdtype)
+        if self.k_transposed:
+            rows = np.asarray(arr_k)[:, self.ky_start:self.ky_start + self.ky_local, :].transpose(1, 2, 0)
+            full[: rows.size] = rows.reshape(-1)
+        else:
+            full[: self.local_nx * N * (N // 2 + 1)] = np.asarray(arr_k).reshape(-1)
+        self.upload_grid(gid, full.view(self.gdtype))
 
     # ---- the reference's per-step functions ----
     @staticmethod
@@ -374,9 +383,13 @@ class PM:
         return a.reshape(self.local_nx + 1, self.N, 2 * (self.N // 2 + 1))
 
     def download_grid_k(self, gid):
-        """k-space view [kx][ky][kz] (single rank)."""
-        a = self.download_grid(gid)
-        return a.reshape(-1).view(self.cdtype).reshape(self.local_nx + 1, self.N, self.N // 2 + 1)[: self.local_nx]
+        """k-space view [kx][ky][kz] on a single rank; [kx][ky_local][kz] (this rank's ky rows) when the transforms
+        are slab-decomposed and the library keeps k-space transposed."""
+        a = self.download_grid(gid).reshape(-1).view(self.cdtype)
+        N, NZ = self.N, self.N // 2 + 1
+        if self.k_transposed:
+            return a[: self.ky_local * NZ * N].reshape(self.ky_local, NZ, N).transpose(2, 0, 1)
+        return a.reshape(self.local_nx + 1, N, NZ)[: self.local_nx]
 
     def upload_grid(self, gid, arr):
         a = np.ascontiguousarray(arr, dtype=self.gdtype).reshape(-1)

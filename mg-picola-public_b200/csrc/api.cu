@@ -39,6 +39,10 @@ static Ctx *create(const mgp_config *cfg) {
     c.N = cfg->nmesh; c.NZ = cfg->nmesh / 2 + 1;
     c.P = cfg->nranks; c.rank = cfg->rank;
     c.gbytes = cfg->grid_bytes;
+    {
+      const char *fs = getenv("MGP_FORCE_SLAB");     // developer / test knob: the multi-rank transform path on one rank
+      c.slab = c.P > 1 || (fs && atoi(fs) != 0);
+    }
     if (c.P > 1) {
       REQUIRE(c.N % c.P == 0, MGP_ERR_INVALID, "mgp_create: nranks must divide Nmesh");
       REQUIRE(cfg->nccl_unique_id != nullptr, MGP_ERR_INVALID, "mgp_create: nccl_unique_id required when nranks > 1");
@@ -149,7 +153,7 @@ static void move_particles(Ctx &c) {
 static void ptomesh(Ctx &c, const mgp_step_scalars *s) {
   if (c.cfg.scale_dependent) sd_drop(c);
   ensure_order(c);
-  if (needs_mg_arrays(c) && c.P == 1) {
+  if (needs_mg_arrays(c) && !c.slab) {
     // CopyDensityArray (mg.h:381) without the copy: deposit straight into mgarray_two and transform
     // out of place into P3D, which leaves delta(x) in mgarray_two exactly as the reference has it
     { PhaseTimer t(c, PH_PTOMESH); deposit_density(c, MGP_GRID_MG_TWO); }
@@ -303,6 +307,15 @@ int mgp_get_layout(mgp_ctx *ctx, int *local_nx, int *local_x_start, int *local_n
   if (local_np) *local_np = c.npl;
   if (local_p_start) *local_p_start = c.p0;
   if (numpart) *numpart = c.np;
+  API_END
+}
+
+int mgp_kspace_layout(mgp_ctx *ctx, int *transposed, int *ky_start, int *ky_local) {
+  API_BEGIN
+  CTX(ctx);
+  if (transposed) *transposed = c.slab ? 1 : 0;
+  if (ky_start) *ky_start = c.slab ? c.y0 : 0;
+  if (ky_local) *ky_local = c.slab ? c.ny_loc : c.N;
   API_END
 }
 

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "mgpicola.h"
+#include "xfft.cuh"
 
 namespace mgp {
 
@@ -61,6 +62,7 @@ struct Ctx {
   mgp_config cfg{};
   int N = 0, NZ = 0;          // Nmesh, Nmesh/2+1
   int P = 1, rank = 0;
+  bool slab = false;          // slab-decomposed transforms + transposed k-space: P > 1 (or MGP_FORCE_SLAB=1 on one rank)
   int nx = 0, x0 = 0;         // Local_nx, Local_x_start
   int npl = 0, p0 = 0;        // Local_np, Local_p_start
   int left = 0, right = 0;    // LeftTask / RightTask
@@ -88,6 +90,13 @@ struct Ctx {
   cudaStream_t comm_stream = nullptr;          // high-priority stream the transposes of a batched transform run on
   cudaEvent_t ev_fft[3] = {nullptr, nullptr, nullptr}, ev_tr[3] = {nullptr, nullptr, nullptr};
   void *fft_work = nullptr;                    // cuFFT work area shared by all plans
+  // x-transform fused with the slab exchange (xfft.cuh): power-of-two Nmesh on the peer-memory path
+  bool xf_on = false;
+  xf::Plan xf_plan{};
+  void *xf_tw = nullptr;                       // twiddle tables of the passes (complex, grid precision)
+  int xf_tk = 0, xf_grid = 0;                  // lines per tile, persistent grid size
+  size_t xf_smem = 0;
+  cufftHandle plan2d_r2c_oop = 0;              // 2-D r2c from a grid into the transpose buffer (the pull source)
 
   // particles (SoA of 16-byte records; see DESIGN.md "data layout")
   uint64_t np = 0, cap = 0;

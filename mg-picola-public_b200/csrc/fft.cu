@@ -13,6 +13,8 @@
 #include "common.cuh"
 #include "reduce.cuh"
 
+#include <cmath>
+
 namespace mgp {
 
 typedef long long int lli;
@@ -27,8 +29,6 @@ static size_t make_plan_many(cufftHandle *plan, int rank, lli *n, lli *inembed, 
 }
 
 // ------------------------------------------------------------------ peer-memory plumbing (P > 1)
-
-struct PeerPtrs { void *p[16]; };
 
 static void p2p_teardown(Ctx &c) {
   for (int r = 0; r < 16; r++) {
@@ -50,6 +50,11 @@ static void p2p_setup(Ctx &c) {
   static_assert(sizeof(Handles) == 128, "cudaIpcMemHandle_t is 64 bytes");
   CK(cudaMalloc(&c.sync_flags, 16 * sizeof(uint32_t)));
   CK(cudaMemset(c.sync_flags, 0, 16 * sizeof(uint32_t)));
+  if (P == 1) {                      // MGP_FORCE_SLAB on one rank: the only peer is this rank itself
+    c.peer_tbuf[0] = c.tbuf_a; c.peer_flags[0] = c.sync_flags;
+    c.p2p = true;
+    return;
+  }
   Handles mine;
   memset(&mine, 0, sizeof(mine));
   if (ok && cudaIpcGetMemHandle(&mine.buf, c.tbuf_a) != cudaSuccess) ok = 0;
@@ -144,11 +149,90 @@ __global__ void k_transpose_bwd_p2p(const C *__restrict__ in, PeerPtrs out, int 
   }
 }
 
+// ------------------------------------------------------------------ fused x-transform + exchange (xfft.cuh)
+
+template <typename C, int TK>
+static void xfft_prepare(Ctx &c) {
+  CK(cudaFuncSetAttribute(xf::k_xfft_bwd_p2p<C, TK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c.xf_smem));
+  CK(cudaFuncSetAttribute(xf::k_xfft_fwd_p2p<C, TK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c.xf_smem));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, xf::k_xfft_bwd_p2p<C, TK>, xf::kThreads, c.xf_smem));
+  REQUIRE(occ >= 1, MGP_ERR_CUDA, "fused x-transform: kernel does not fit on an SM");
+  const long long ntiles = (long long) c.ny_loc * ((c.NZ + TK - 1) / TK);
+  long long g = (long long) kSMs * occ;
+  c.xf_grid = (int) (ntiles < g ? ntiles : g);
+}
+
+// Chooses the tile (TK lines of N complex values, at most 64 KB so that two CTAs share an SM and one tile's global
+// traffic overlaps the other's butterflies) and uploads the twiddle tables.  Leaves xf_on = false when Nmesh is not
+// a power of two or the peer-memory path is off: those cases keep cuFFT's 1-D plan + the transpose kernels.
+static void xfft_setup(Ctx &c) {
+  c.xf_on = false;
+  const char *env = getenv("MGP_XFFT");
+  if (!c.p2p || (env && atoi(env) == 0)) return;
+  if (!xf::make_plan(c.N, c.xf_plan)) return;
+  const size_t cb = c.gbytes == 4 ? sizeof(float2) : sizeof(double2);
+  int tk = 16;
+  while (tk > 4 && (size_t) tk * c.N * cb > 64 * 1024) tk >>= 1;
+  if (const char *e = getenv("MGP_XFFT_TK")) { const int v = atoi(e); if (v == 4 || v == 8 || v == 16) tk = v; }
+  if ((size_t) tk * c.N * cb > 200 * 1024) return;
+  c.xf_tk = tk;
+  c.xf_smem = (size_t) tk * c.N * cb;
+  const xf::Plan &pl = c.xf_plan;
+  std::vector<double2> tw(pl.twtotal);
+  for (int i = 0; i < pl.npass; i++) {
+    const int L = pl.R[i] << pl.lgM[i];
+    for (int t = 0; t < L; t++) {
+      const long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double) t / (long double) L;
+      tw[pl.twoff[i] + t] = make_double2((double) cosl(a), (double) sinl(a));
+    }
+  }
+  CK(cudaMalloc(&c.xf_tw, (size_t) pl.twtotal * cb));
+  if (c.gbytes == 4) {
+    std::vector<float2> twf(pl.twtotal);
+    for (int t = 0; t < pl.twtotal; t++) twf[t] = make_float2((float) tw[t].x, (float) tw[t].y);
+    CK(cudaMemcpy(c.xf_tw, twf.data(), (size_t) pl.twtotal * cb, cudaMemcpyHostToDevice));
+    if (tk == 4) xfft_prepare<float2, 4>(c); else if (tk == 8) xfft_prepare<float2, 8>(c); else xfft_prepare<float2, 16>(c);
+  } else {
+    CK(cudaMemcpy(c.xf_tw, tw.data(), (size_t) pl.twtotal * cb, cudaMemcpyHostToDevice));
+    if (tk == 4) xfft_prepare<double2, 4>(c); else if (tk == 8) xfft_prepare<double2, 8>(c); else xfft_prepare<double2, 16>(c);
+  }
+  c.xf_on = true;
+}
+
+// backward x-transform of the local transposed k-space `in`, every x stored into slot `slot` of its owner's buffer
+template <typename C>
+static void xfft_bwd(Ctx &c, const void *in, int slot, cudaStream_t st) {
+  PeerPtrs pp;
+  for (int r = 0; r < 16; r++) pp.p[r] = c.peer_tbuf[r] ? (char *) c.peer_tbuf[r] + (size_t) slot * c.grid_bytes() : nullptr;
+#define XF_LAUNCH(TK)                                                                                              \
+  xf::k_xfft_bwd_p2p<C, TK><<<c.xf_grid, xf::kThreads, c.xf_smem, st>>>((const C *) in, pp, c.xf_plan, (const C *) c.xf_tw, \
+                                                                        c.nx, c.y0, c.N, c.NZ, c.ny_loc)
+  if (c.xf_tk == 4) XF_LAUNCH(4); else if (c.xf_tk == 8) XF_LAUNCH(8); else XF_LAUNCH(16);
+#undef XF_LAUNCH
+  CK(cudaGetLastError());
+  c.launches++;
+}
+
+// forward x-transform: pulls slot 0 of every owner's buffer, writes the local transposed k-space `out`
+template <typename C>
+static void xfft_fwd(Ctx &c, void *out, cudaStream_t st) {
+  PeerPtrs pp;
+  for (int r = 0; r < 16; r++) pp.p[r] = c.peer_tbuf[r];
+#define XF_LAUNCH(TK)                                                                                              \
+  xf::k_xfft_fwd_p2p<C, TK><<<c.xf_grid, xf::kThreads, c.xf_smem, st>>>(pp, (C *) out, c.xf_plan, (const C *) c.xf_tw, c.nx, \
+                                                                        c.y0, c.N, c.NZ, c.ny_loc)
+  if (c.xf_tk == 4) XF_LAUNCH(4); else if (c.xf_tk == 8) XF_LAUNCH(8); else XF_LAUNCH(16);
+#undef XF_LAUNCH
+  CK(cudaGetLastError());
+  c.launches++;
+}
+
 void fft_setup(Ctx &c) {
   const int N = c.N, NZ = c.NZ;
   const bool f32 = c.gbytes == 4;
   size_t ws = 0, w;
-  if (c.P == 1) {
+  if (!c.slab) {
     lli n[3] = {N, N, N};
     lli rembed[3] = {N, N, 2 * NZ}, cembed[3] = {N, N, NZ};
     const lli rdist = (lli) c.grid_vals, cdist = (lli) (c.grid_vals / 2);
@@ -174,6 +258,11 @@ void fft_setup(Ctx &c) {
     CK(cudaMalloc(&c.tbuf_a, 3 * c.grid_bytes()));     // three slots: the batched c2r pipelines its three transposes
     CK(cudaMalloc(&c.tbuf_b, c.grid_bytes()));
     p2p_setup(c);
+    xfft_setup(c);
+    if (c.xf_on) {
+      w = make_plan_many(&c.plan2d_r2c_oop, 2, n2, rembed, 1, N * 2 * NZ, cembed, 1, N * NZ, f32 ? CUFFT_R2C : CUFFT_D2Z, c.nx, c.stream);
+      ws = w > ws ? w : ws;
+    }
     if (c.p2p) {
       int lo = 0, hi = 0;
       CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -185,7 +274,7 @@ void fft_setup(Ctx &c) {
     }
   }
   if (ws) CK(cudaMalloc(&c.fft_work, ws));     // shared cuFFT work area
-  cufftHandle all[7] = {c.plan_r2c, c.plan_c2r, c.plan_c2r3, c.plan2d_r2c, c.plan2d_c2r, c.plan1d_x, c.plan_r2c_oop};
+  cufftHandle all[8] = {c.plan_r2c, c.plan_c2r, c.plan_c2r3, c.plan2d_r2c, c.plan2d_c2r, c.plan1d_x, c.plan_r2c_oop, c.plan2d_r2c_oop};
   for (cufftHandle h : all)
     if (h && ws) CKFFT(cufftSetWorkArea(h, c.fft_work));
   c.have_plans = true;
@@ -195,10 +284,10 @@ void fft_teardown(Ctx &c) {
   p2p_teardown(c);
   for (int a = 0; a < 3; a++) { if (c.ev_fft[a]) cudaEventDestroy(c.ev_fft[a]); if (c.ev_tr[a]) cudaEventDestroy(c.ev_tr[a]); }
   if (c.comm_stream) cudaStreamDestroy(c.comm_stream);
-  cufftHandle all[7] = {c.plan_r2c, c.plan_c2r, c.plan_c2r3, c.plan2d_r2c, c.plan2d_c2r, c.plan1d_x, c.plan_r2c_oop};
+  cufftHandle all[8] = {c.plan_r2c, c.plan_c2r, c.plan_c2r3, c.plan2d_r2c, c.plan2d_c2r, c.plan1d_x, c.plan_r2c_oop, c.plan2d_r2c_oop};
   for (cufftHandle h : all)
     if (h) cufftDestroy(h);
-  cudaFree(c.fft_work); cudaFree(c.tbuf_a); cudaFree(c.tbuf_b);
+  cudaFree(c.fft_work); cudaFree(c.tbuf_a); cudaFree(c.tbuf_b); cudaFree(c.xf_tw);
 }
 
 // ------------------------------------------------------------------ slab transposes (P > 1)
@@ -284,6 +373,19 @@ static void all_to_all(Ctx &c, const void *send, void *recv, size_t block_bytes)
 template <typename R, typename C>
 static void dist_r2c(Ctx &c, void *g) {
   const int N = c.N, NZ = c.NZ, nxb = c.nx, nyl = c.ny_loc;
+  if (c.xf_on) {
+    // 2-D r2c out of place into this rank's transpose buffer; the fused kernel pulls the x-lines from their owners
+    if (sizeof(R) == 4) CKFFT(cufftExecR2C(c.plan2d_r2c_oop, (cufftReal *) g, (cufftComplex *) c.tbuf_a));
+    else CKFFT(cufftExecD2Z(c.plan2d_r2c_oop, (cufftDoubleReal *) g, (cufftDoubleComplex *) c.tbuf_a));
+    c.launches += 2;
+    {
+      PhaseTimer t(c, PH_COMM);
+      p2p_barrier(c);                       // every rank's 2-D transform is complete and visible
+      xfft_fwd<C>(c, g, c.stream);
+      p2p_barrier(c);                       // every rank has finished reading this rank's buffer
+    }
+    return;
+  }
   if (sizeof(R) == 4) CKFFT(cufftExecR2C(c.plan2d_r2c, (cufftReal *) g, (cufftComplex *) g));
   else CKFFT(cufftExecD2Z(c.plan2d_r2c, (cufftDoubleReal *) g, (cufftDoubleComplex *) g));
   if (c.p2p) {
@@ -314,6 +416,18 @@ static void dist_r2c(Ctx &c, void *g) {
 template <typename R, typename C>
 static void dist_c2r(Ctx &c, void *g) {
   const int N = c.N, NZ = c.NZ, nxb = c.nx, nyl = c.ny_loc;
+  if (c.xf_on) {
+    {
+      PhaseTimer t(c, PH_COMM);
+      p2p_barrier(c);                       // every rank is done with its transpose buffer
+      xfft_bwd<C>(c, g, 0, c.stream);
+      p2p_barrier(c);                       // every rank's stores have landed
+    }
+    if (sizeof(R) == 4) CKFFT(cufftExecC2R(c.plan2d_c2r, (cufftComplex *) c.tbuf_a, (cufftReal *) g));
+    else CKFFT(cufftExecZ2D(c.plan2d_c2r, (cufftDoubleComplex *) c.tbuf_a, (cufftDoubleReal *) g));
+    c.launches += 2;
+    return;
+  }
   if (sizeof(R) == 4) CKFFT(cufftExecC2C(c.plan1d_x, (cufftComplex *) g, (cufftComplex *) g, CUFFT_INVERSE));
   else CKFFT(cufftExecZ2Z(c.plan1d_x, (cufftDoubleComplex *) g, (cufftDoubleComplex *) g, CUFFT_INVERSE));
   if (c.p2p) {
@@ -351,6 +465,26 @@ static void dist_c2r3(Ctx &c, int block) {
   const int N = c.N, NZ = c.NZ, nxb = c.nx, nyl = c.ny_loc;
   const size_t gb = c.grid_bytes();
   cudaStream_t S = c.stream, T = c.comm_stream;
+  if (c.xf_on) {
+    // fused x-transform + exchange of component a on the communication stream, the 2-D c2r of the components that
+    // have landed on the compute stream:   comm: [B][X 0][B][X 1][B][X 2][B]     compute: [2-D 0][2-D 1][2-D 2]
+    CK(cudaEventRecord(c.ev_fft[0], S));
+    CK(cudaStreamWaitEvent(T, c.ev_fft[0], 0));
+    p2p_barrier(c, T);                      // every rank is done with all three slots of its transpose buffer
+    for (int a = 0; a < 3; a++) {
+      xfft_bwd<C>(c, c.grid[block_grid(block, a)], a, T);
+      p2p_barrier(c, T);                    // component a has landed everywhere
+      CK(cudaEventRecord(c.ev_tr[a], T));
+    }
+    for (int a = 0; a < 3; a++) {
+      CK(cudaStreamWaitEvent(S, c.ev_tr[a], 0));
+      void *src = (char *) c.tbuf_a + (size_t) a * gb, *g = c.grid[block_grid(block, a)];
+      if (sizeof(R) == 4) CKFFT(cufftExecC2R(c.plan2d_c2r, (cufftComplex *) src, (cufftReal *) g));
+      else CKFFT(cufftExecZ2D(c.plan2d_c2r, (cufftDoubleComplex *) src, (cufftDoubleReal *) g));
+    }
+    c.launches += 6;
+    return;
+  }
   for (int a = 0; a < 3; a++) {
     void *g = c.grid[block_grid(block, a)];
     if (sizeof(R) == 4) CKFFT(cufftExecC2C(c.plan1d_x, (cufftComplex *) g, (cufftComplex *) g, CUFFT_INVERSE));
@@ -381,7 +515,7 @@ static void dist_c2r3(Ctx &c, int block) {
 void fft_r2c(Ctx &c, int gid) {
   PhaseTimer t(c, PH_FFT);
   void *g = c.grid[gid];
-  if (c.P > 1) {
+  if (c.slab) {
     if (c.gbytes == 4) dist_r2c<float, float2>(c, g); else dist_r2c<double, double2>(c, g);
     return;
   }
@@ -393,7 +527,7 @@ void fft_r2c(Ctx &c, int gid) {
 // single rank only: dst(k) = r2c(src(x)), src is left untouched
 void fft_r2c_to(Ctx &c, int src, int dst) {
   PhaseTimer t(c, PH_FFT);
-  REQUIRE(c.P == 1, MGP_ERR_STATE, "out-of-place r2c is a single-rank path");
+  REQUIRE(!c.slab, MGP_ERR_STATE, "out-of-place r2c is a single-rank path");
   if (c.gbytes == 4) CKFFT(cufftExecR2C(c.plan_r2c_oop, (cufftReal *) c.grid[src], (cufftComplex *) c.grid[dst]));
   else CKFFT(cufftExecD2Z(c.plan_r2c_oop, (cufftDoubleReal *) c.grid[src], (cufftDoubleComplex *) c.grid[dst]));
   c.launches += 3;
@@ -402,7 +536,7 @@ void fft_r2c_to(Ctx &c, int src, int dst) {
 void fft_c2r(Ctx &c, int gid) {
   PhaseTimer t(c, PH_FFT);
   void *g = c.grid[gid];
-  if (c.P > 1) {
+  if (c.slab) {
     if (c.gbytes == 4) dist_c2r<float, float2>(c, g); else dist_c2r<double, double2>(c, g);
     return;
   }
@@ -415,12 +549,12 @@ void fft_c2r_forces(Ctx &c) { fft_c2r_block(c, 0); }
 
 void fft_c2r_block(Ctx &c, int block) {
   REQUIRE(block == 0 || (block == 1 && c.aux_block), MGP_ERR_STATE, "batched c2r: block not allocated");
-  if (c.P > 1 && c.p2p) {
+  if (c.slab && c.p2p) {
     PhaseTimer t(c, PH_FFT);
     if (c.gbytes == 4) dist_c2r3<float, float2>(c, block); else dist_c2r3<double, double2>(c, block);
     return;
   }
-  if (c.P > 1) {
+  if (c.slab) {
     for (int a = 0; a < 3; a++) fft_c2r(c, block_grid(block, a));
     return;
   }

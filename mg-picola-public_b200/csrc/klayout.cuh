@@ -4,7 +4,7 @@
 
 namespace mgp {
 
-// k-space layout of this rank: P == 1: [kx][ky][kz]; P > 1 (transposed): [ky_local][kz][kx]
+// k-space layout of this rank: single-rank 3-D plans: [kx][ky][kz]; slab transforms (P > 1): transposed [ky_local][kz][kx]
 struct KL {
   int N, NZ, transposed, j0, nyl;
   size_t total;
@@ -12,8 +12,8 @@ struct KL {
 
 static inline KL layout_of(const Ctx &c) {
   KL L;
-  L.N = c.N; L.NZ = c.NZ; L.transposed = c.P > 1; L.j0 = c.y0; L.nyl = c.ny_loc;
-  L.total = c.P > 1 ? (size_t) c.ny_loc * c.NZ * c.N : (size_t) c.N * c.N * c.NZ;
+  L.N = c.N; L.NZ = c.NZ; L.transposed = c.slab; L.j0 = c.y0; L.nyl = c.ny_loc;
+  L.total = c.slab ? (size_t) c.ny_loc * c.NZ * c.N : (size_t) c.N * c.N * c.NZ;
   return L;
 }
 

@@ -1,0 +1,21 @@
+"""CPU check of the fused x-transform + slab-exchange kernels (csrc/xfft.cuh): tests/host/xfft_emul.cu runs the
+phase functions the kernels consist of, thread by thread, for several emulated ranks and compares with a direct
+DFT in long double (both directions, double and float, every tile width)."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_xfft_phases_match_direct_dft(tmp_path):
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = str(tmp_path / "xfft_emul")
+    subprocess.run([nvcc, "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-I", os.path.join(ROOT, "mg-picola-public_b200", "csrc"),
+                    "-o", exe, os.path.join(ROOT, "tests", "host", "xfft_emul.cu")], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout[-2000:]
