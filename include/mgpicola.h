@@ -252,6 +252,11 @@ int mgp_upload_grid(mgp_ctx *ctx, int grid_id, const void *host);
 /* in-place transforms of one grid (my_fftw_execute on r2c / c2r plans, wrappers.c:42-46) */
 int mgp_fft_r2c(mgp_ctx *ctx, int grid_id);
 int mgp_fft_c2r(mgp_ctx *ctx, int grid_id);
+/* developer probe of the slab exchange (slab-decomposed contexts only): mean device time in ms of `reps` back-to-back
+ * executions of one piece -- 0 flag barrier, 1 fused backward x-transform + push, 2 fused pull + forward x-transform,
+ * 3 / 4 backward / forward transpose kernel, 5 copy-engine peer copy of the remote share of a slab, 6 / 7 the backward /
+ * forward strided copy-engine blocks of the DMA exchange.  Clobbers the force grids and the transpose buffers. */
+int mgp_debug_time_exchange(mgp_ctx *ctx, int which, int reps, float *ms);
 
 /* ---- instrumentation ---- */
 /* number of kernels this library has launched on ctx since creation / last reset */

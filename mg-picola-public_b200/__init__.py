@@ -73,6 +73,7 @@ def load_library(path=None):
     L.mgp_nccl_unique_id.argtypes = [C.c_void_p]
     L.mgp_get_layout.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 4 + [C.POINTER(C.c_uint64)]
     L.mgp_kspace_layout.argtypes = [C.c_void_p] + [C.POINTER(C.c_int)] * 3
+    L.mgp_debug_time_exchange.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]
     fp, dp, up = C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_uint64)
     L.mgp_upload_particles.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mgp_download_particles.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -403,6 +404,11 @@ class PM:
         self._ck(self.L.mgp_fft_c2r(self.ctx, gid))
 
     # ---- instrumentation ----
+    def debug_time_exchange(self, which, reps=5):
+        ms = C.c_float()
+        self._ck(self.L.mgp_debug_time_exchange(self.ctx, which, reps, C.byref(ms)))
+        return ms.value
+
     def launch_count(self, reset=False):
         return int(self.L.mgp_launch_count(self.ctx, int(reset)))
 

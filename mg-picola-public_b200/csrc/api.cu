@@ -619,6 +619,14 @@ int mgp_fft_r2c(mgp_ctx *ctx, int grid_id) {
   API_END
 }
 
+int mgp_debug_time_exchange(mgp_ctx *ctx, int which, int reps, float *ms) {
+  API_BEGIN
+  CTX(ctx);
+  REQUIRE(ms != nullptr && reps >= 1, MGP_ERR_INVALID, "mgp_debug_time_exchange: bad arguments");
+  fft_debug_exchange(c, which, reps, ms);
+  API_END
+}
+
 int mgp_fft_c2r(mgp_ctx *ctx, int grid_id) {
   API_BEGIN
   CTX(ctx);

@@ -92,11 +92,17 @@ struct Ctx {
   void *fft_work = nullptr;                    // cuFFT work area shared by all plans
   // x-transform fused with the slab exchange (xfft.cuh): power-of-two Nmesh on the peer-memory path
   bool xf_on = false;
-  xf::Plan xf_plan{};
+  int xf_lgn = 0, xf_lgnxb = 0;                // log2 Nmesh, log2 Local_nx
   void *xf_tw = nullptr;                       // twiddle tables of the passes (complex, grid precision)
   int xf_tk = 0, xf_grid = 0;                  // lines per tile, persistent grid size
   size_t xf_smem = 0;
   cufftHandle plan2d_r2c_oop = 0;              // 2-D r2c from a grid into the transpose buffer (the pull source)
+  // exchange engine of the fused path: 1 = the x-transform kernel packs / unpacks a local staging buffer (slots 3-5 of
+  // tbuf_a, laid out [rank][x_local][ky_local][kz]) and the copy engines move one strided block per peer over NVLink
+  // (cudaMemcpy2DAsync on the peer mappings); 0 = the kernel's own loads / stores go to peer memory
+  int xf_dma = 0;
+  cudaStream_t cp_stream[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_cp_go = nullptr, ev_cp_done[4] = {nullptr, nullptr, nullptr, nullptr};
 
   // particles (SoA of 16-byte records; see DESIGN.md "data layout")
   uint64_t np = 0, cap = 0;
@@ -238,6 +244,7 @@ void fft_r2c_to(Ctx &c, int src_grid, int dst_grid);
 void fft_c2r_forces(Ctx &c);
 void fft_c2r_block(Ctx &c, int block);      // block 0: grids 1, 2, 3; block 1: grids 0, 4, 5 (scale_dependent only)
 void halo_fill_block(Ctx &c, int block);
+void fft_debug_exchange(Ctx &c, int which, int reps, float *ms);
 inline int block_grid(int block, int a) { return block == 0 ? 1 + a : (a == 0 ? 0 : 3 + a); }
 void halo_add_density(Ctx &c, int grid_id);
 void halo_fill_forces(Ctx &c);

@@ -151,65 +151,133 @@ __global__ void k_transpose_bwd_p2p(const C *__restrict__ in, PeerPtrs out, int 
 
 // ------------------------------------------------------------------ fused x-transform + exchange (xfft.cuh)
 
-template <typename C, int TK>
-static void xfft_prepare(Ctx &c) {
-  CK(cudaFuncSetAttribute(xf::k_xfft_bwd_p2p<C, TK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c.xf_smem));
-  CK(cudaFuncSetAttribute(xf::k_xfft_fwd_p2p<C, TK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c.xf_smem));
-  int occ = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, xf::k_xfft_bwd_p2p<C, TK>, xf::kThreads, c.xf_smem));
-  REQUIRE(occ >= 1, MGP_ERR_CUDA, "fused x-transform: kernel does not fit on an SM");
-  const long long ntiles = (long long) c.ny_loc * ((c.NZ + TK - 1) / TK);
-  long long g = (long long) kSMs * occ;
-  c.xf_grid = (int) (ntiles < g ? ntiles : g);
+// one switch over the supported Nmesh = 2^lgn; OP is a functor template taking <C, LGN>
+#define XF_DISPATCH_LGN(lgn, OP)                                                                             \
+  switch (lgn) {                                                                                             \
+    case 4: OP(4); break; case 5: OP(5); break; case 6: OP(6); break; case 7: OP(7); break; case 8: OP(8); break; \
+    case 9: OP(9); break; case 10: OP(10); break; case 11: OP(11); break; case 12: OP(12); break;             \
+    default: throw mgp::Error(MGP_ERR_STATE, "fused x-transform: unsupported Nmesh");                        \
+  }
+
+template <typename C, int LGN>
+static bool xfft_prepare(Ctx &c) {
+  constexpr int TK = xf::tile_lines(LGN, sizeof(C));
+  if constexpr (TK == 0) {
+    return false;
+  } else {
+    c.xf_tk = TK;
+    c.xf_smem = ((size_t) TK << LGN) * sizeof(C);
+    CK(cudaFuncSetAttribute(xf::k_xfft_bwd_p2p<C, LGN, TK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c.xf_smem));
+    CK(cudaFuncSetAttribute(xf::k_xfft_fwd_p2p<C, LGN, TK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) c.xf_smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, xf::k_xfft_bwd_p2p<C, LGN, TK>, xf::kThreads, c.xf_smem));
+    REQUIRE(occ >= 1, MGP_ERR_CUDA, "fused x-transform: kernel does not fit on an SM");
+    const long long ntiles = (long long) c.ny_loc * ((c.NZ + TK - 1) / TK);
+    const long long g = (long long) kSMs * occ;
+    c.xf_grid = (int) (ntiles < g ? ntiles : g);
+    return true;
+  }
 }
 
-// Chooses the tile (TK lines of N complex values, at most 64 KB so that two CTAs share an SM and one tile's global
-// traffic overlaps the other's butterflies) and uploads the twiddle tables.  Leaves xf_on = false when Nmesh is not
-// a power of two or the peer-memory path is off: those cases keep cuFFT's 1-D plan + the transpose kernels.
+// Picks the kernel instance of this Nmesh (tile = TK lines of N complex values, at most 64 KB so that two CTAs share
+// an SM) and uploads the twiddle tables.  Leaves xf_on = false when Nmesh is not a power of two in [16, 4096], the
+// slabs are not a power of two wide, or the peer-memory path is off: those cases keep cuFFT's 1-D plan + the
+// transpose kernels.
 static void xfft_setup(Ctx &c) {
   c.xf_on = false;
   const char *env = getenv("MGP_XFFT");
   if (!c.p2p || (env && atoi(env) == 0)) return;
-  if (!xf::make_plan(c.N, c.xf_plan)) return;
-  const size_t cb = c.gbytes == 4 ? sizeof(float2) : sizeof(double2);
-  int tk = 16;
-  while (tk > 4 && (size_t) tk * c.N * cb > 64 * 1024) tk >>= 1;
-  if (const char *e = getenv("MGP_XFFT_TK")) { const int v = atoi(e); if (v == 4 || v == 8 || v == 16) tk = v; }
-  if ((size_t) tk * c.N * cb > 200 * 1024) return;
-  c.xf_tk = tk;
-  c.xf_smem = (size_t) tk * c.N * cb;
-  const xf::Plan &pl = c.xf_plan;
-  std::vector<double2> tw(pl.twtotal);
-  for (int i = 0; i < pl.npass; i++) {
-    const int L = pl.R[i] << pl.lgM[i];
+  int lgn = 0;
+  while ((1 << lgn) < c.N) lgn++;
+  if ((1 << lgn) != c.N || lgn < xf::kMinLgN || lgn > xf::kMaxLgN) return;
+  int lgx = 0;
+  while ((1 << lgx) < c.nx) lgx++;
+  if ((1 << lgx) != c.nx || c.nx * c.P != c.N) return;
+  c.xf_lgn = lgn; c.xf_lgnxb = lgx;
+  bool ok = false;
+  if (c.gbytes == 4) {
+#define OP(L) ok = xfft_prepare<float2, L>(c)
+    XF_DISPATCH_LGN(lgn, OP)
+#undef OP
+  } else {
+#define OP(L) ok = xfft_prepare<double2, L>(c)
+    XF_DISPATCH_LGN(lgn, OP)
+#undef OP
+  }
+  if (!ok) return;
+  const int np = xf::plan_npass(lgn);
+  const int total = xf::plan_twtotal(lgn);
+  std::vector<double2> tw(total);
+  for (int i = 0; i < np; i++) {
+    const int L = 1 << (xf::plan_lgR(lgn, i) + xf::plan_lgM(lgn, i));
     for (int t = 0; t < L; t++) {
       const long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double) t / (long double) L;
-      tw[pl.twoff[i] + t] = make_double2((double) cosl(a), (double) sinl(a));
+      tw[xf::plan_twoff(lgn, i) + t] = make_double2((double) cosl(a), (double) sinl(a));
     }
   }
-  CK(cudaMalloc(&c.xf_tw, (size_t) pl.twtotal * cb));
+  const size_t cb = c.gbytes == 4 ? sizeof(float2) : sizeof(double2);
+  CK(cudaMalloc(&c.xf_tw, (size_t) total * cb));
   if (c.gbytes == 4) {
-    std::vector<float2> twf(pl.twtotal);
-    for (int t = 0; t < pl.twtotal; t++) twf[t] = make_float2((float) tw[t].x, (float) tw[t].y);
-    CK(cudaMemcpy(c.xf_tw, twf.data(), (size_t) pl.twtotal * cb, cudaMemcpyHostToDevice));
-    if (tk == 4) xfft_prepare<float2, 4>(c); else if (tk == 8) xfft_prepare<float2, 8>(c); else xfft_prepare<float2, 16>(c);
+    std::vector<float2> twf(total);
+    for (int t = 0; t < total; t++) twf[t] = make_float2((float) tw[t].x, (float) tw[t].y);
+    CK(cudaMemcpy(c.xf_tw, twf.data(), (size_t) total * cb, cudaMemcpyHostToDevice));
   } else {
-    CK(cudaMemcpy(c.xf_tw, tw.data(), (size_t) pl.twtotal * cb, cudaMemcpyHostToDevice));
-    if (tk == 4) xfft_prepare<double2, 4>(c); else if (tk == 8) xfft_prepare<double2, 8>(c); else xfft_prepare<double2, 16>(c);
+    CK(cudaMemcpy(c.xf_tw, tw.data(), (size_t) total * cb, cudaMemcpyHostToDevice));
   }
+  const char *dma = getenv("MGP_XFFT_DMA");
+  c.xf_dma = dma ? (atoi(dma) != 0) : 1;
   c.xf_on = true;
+}
+
+// staging slot `slot` (0..2) of rank r: the second half of its transpose buffer
+static inline char *stage_of(Ctx &c, int r, int slot) { return (char *) c.peer_tbuf[r] + (size_t) (3 + slot) * c.grid_bytes(); }
+
+// One strided block per peer through the copy engines (cudaMemcpy2DAsync on the peer mappings), forked from `st` onto
+// the copy streams and joined back.  Block of (this rank -> rank r): [nxb x-planes][nyl ky rows][NZ] complex.
+//   backward: staging slot (packed [r][xl][jl][kz] by the x-transform kernel) -> r's landing slot [xl][ky0_me + jl][kz]
+//   forward : this rank's 2-D transform output `src2d` [xl][ky][kz], rows of r -> r's staging slot 0 at [me][xl][jl][kz]
+static void exchange_dma(Ctx &c, cudaStream_t st, bool forward, const void *src2d, int slot) {
+  const size_t cb = c.gbytes == 4 ? sizeof(float2) : sizeof(double2);
+  const size_t row = (size_t) c.ny_loc * c.NZ * cb;           // one x-plane of one rank's ky rows: contiguous
+  const size_t plane = (size_t) c.N * c.NZ * cb;              // one full x-plane
+  const size_t blk = (size_t) c.nx * row;
+  CK(cudaEventRecord(c.ev_cp_go, st));
+  for (int q = 0; q < 4; q++) CK(cudaStreamWaitEvent(c.cp_stream[q], c.ev_cp_go, 0));
+  for (int i = 0; i < c.P; i++) {
+    const int r = (c.rank + 1 + i) % c.P;                      // staggered: no two ranks start on the same destination
+    cudaStream_t cs = c.cp_stream[i & 3];
+    if (forward) {
+      const char *src = (const char *) src2d + (size_t) r * row;
+      char *dst = stage_of(c, r, 0) + (size_t) c.rank * blk;
+      CK(cudaMemcpy2DAsync(dst, row, src, plane, row, (size_t) c.nx, cudaMemcpyDefault, cs));
+    } else {
+      const char *src = stage_of(c, c.rank, slot) + (size_t) r * blk;
+      char *dst = (char *) c.peer_tbuf[r] + (size_t) slot * c.grid_bytes() + (size_t) c.rank * row;
+      CK(cudaMemcpy2DAsync(dst, plane, src, row, row, (size_t) c.nx, cudaMemcpyDefault, cs));
+    }
+  }
+  for (int q = 0; q < 4; q++) {
+    CK(cudaEventRecord(c.ev_cp_done[q], c.cp_stream[q]));
+    CK(cudaStreamWaitEvent(st, c.ev_cp_done[q], 0));
+  }
 }
 
 // backward x-transform of the local transposed k-space `in`, every x stored into slot `slot` of its owner's buffer
 template <typename C>
 static void xfft_bwd(Ctx &c, const void *in, int slot, cudaStream_t st) {
   PeerPtrs pp;
-  for (int r = 0; r < 16; r++) pp.p[r] = c.peer_tbuf[r] ? (char *) c.peer_tbuf[r] + (size_t) slot * c.grid_bytes() : nullptr;
-#define XF_LAUNCH(TK)                                                                                              \
-  xf::k_xfft_bwd_p2p<C, TK><<<c.xf_grid, xf::kThreads, c.xf_smem, st>>>((const C *) in, pp, c.xf_plan, (const C *) c.xf_tw, \
-                                                                        c.nx, c.y0, c.N, c.NZ, c.ny_loc)
-  if (c.xf_tk == 4) XF_LAUNCH(4); else if (c.xf_tk == 8) XF_LAUNCH(8); else XF_LAUNCH(16);
-#undef XF_LAUNCH
+  // DMA exchange: the "owners" are the per-destination blocks of this rank's staging slot, [r][xl][jl][kz]
+  const size_t blk = (size_t) c.nx * c.ny_loc * c.NZ * sizeof(C);
+  for (int r = 0; r < 16; r++) {
+    if (c.xf_dma) pp.p[r] = r < c.P ? stage_of(c, c.rank, slot) + (size_t) r * blk : nullptr;
+    else pp.p[r] = c.peer_tbuf[r] ? (char *) c.peer_tbuf[r] + (size_t) slot * c.grid_bytes() : nullptr;
+  }
+  const int y0 = c.xf_dma ? 0 : c.y0, NY = c.xf_dma ? c.ny_loc : c.N;
+#define OP(L)                                                                                                   \
+  xf::k_xfft_bwd_p2p<C, L, xf::tile_lines(L, sizeof(C)) ? xf::tile_lines(L, sizeof(C)) : 4>                      \
+      <<<c.xf_grid, xf::kThreads, c.xf_smem, st>>>((const C *) in, pp, (const C *) c.xf_tw, c.xf_lgnxb, y0, NY, c.NZ, c.ny_loc)
+  XF_DISPATCH_LGN(c.xf_lgn, OP)
+#undef OP
   CK(cudaGetLastError());
   c.launches++;
 }
@@ -218,12 +286,17 @@ static void xfft_bwd(Ctx &c, const void *in, int slot, cudaStream_t st) {
 template <typename C>
 static void xfft_fwd(Ctx &c, void *out, cudaStream_t st) {
   PeerPtrs pp;
-  for (int r = 0; r < 16; r++) pp.p[r] = c.peer_tbuf[r];
-#define XF_LAUNCH(TK)                                                                                              \
-  xf::k_xfft_fwd_p2p<C, TK><<<c.xf_grid, xf::kThreads, c.xf_smem, st>>>(pp, (C *) out, c.xf_plan, (const C *) c.xf_tw, c.nx, \
-                                                                        c.y0, c.N, c.NZ, c.ny_loc)
-  if (c.xf_tk == 4) XF_LAUNCH(4); else if (c.xf_tk == 8) XF_LAUNCH(8); else XF_LAUNCH(16);
-#undef XF_LAUNCH
+  const size_t blk = (size_t) c.nx * c.ny_loc * c.NZ * sizeof(C);
+  for (int r = 0; r < 16; r++) {
+    if (c.xf_dma) pp.p[r] = r < c.P ? stage_of(c, c.rank, 0) + (size_t) r * blk : nullptr;
+    else pp.p[r] = c.peer_tbuf[r];
+  }
+  const int y0 = c.xf_dma ? 0 : c.y0, NY = c.xf_dma ? c.ny_loc : c.N;
+#define OP(L)                                                                                                   \
+  xf::k_xfft_fwd_p2p<C, L, xf::tile_lines(L, sizeof(C)) ? xf::tile_lines(L, sizeof(C)) : 4>                      \
+      <<<c.xf_grid, xf::kThreads, c.xf_smem, st>>>(pp, (C *) out, (const C *) c.xf_tw, c.xf_lgnxb, y0, NY, c.NZ, c.ny_loc)
+  XF_DISPATCH_LGN(c.xf_lgn, OP)
+#undef OP
   CK(cudaGetLastError());
   c.launches++;
 }
@@ -255,7 +328,9 @@ void fft_setup(Ctx &c) {
     lli n1[1] = {N};
     w = make_plan_many(&c.plan1d_x, 1, n1, n1, 1, N, n1, 1, N, f32 ? CUFFT_C2C : CUFFT_Z2Z, c.ny_loc * NZ, c.stream);
     ws = w > ws ? w : ws;
-    CK(cudaMalloc(&c.tbuf_a, 3 * c.grid_bytes()));     // three slots: the batched c2r pipelines its three transposes
+    // three landing slots (the batched c2r pipelines its three transposes) + three staging slots of the DMA exchange,
+    // one allocation so that a single peer mapping covers both
+    CK(cudaMalloc(&c.tbuf_a, 6 * c.grid_bytes()));
     CK(cudaMalloc(&c.tbuf_b, c.grid_bytes()));
     p2p_setup(c);
     xfft_setup(c);
@@ -267,6 +342,11 @@ void fft_setup(Ctx &c) {
       int lo = 0, hi = 0;
       CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
       CK(cudaStreamCreateWithPriority(&c.comm_stream, cudaStreamNonBlocking, hi));
+      CK(cudaEventCreateWithFlags(&c.ev_cp_go, cudaEventDisableTiming));
+      for (int q = 0; q < 4; q++) {
+        CK(cudaStreamCreateWithFlags(&c.cp_stream[q], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&c.ev_cp_done[q], cudaEventDisableTiming));
+      }
       for (int a = 0; a < 3; a++) {
         CK(cudaEventCreateWithFlags(&c.ev_fft[a], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c.ev_tr[a], cudaEventDisableTiming));
@@ -284,6 +364,8 @@ void fft_teardown(Ctx &c) {
   p2p_teardown(c);
   for (int a = 0; a < 3; a++) { if (c.ev_fft[a]) cudaEventDestroy(c.ev_fft[a]); if (c.ev_tr[a]) cudaEventDestroy(c.ev_tr[a]); }
   if (c.comm_stream) cudaStreamDestroy(c.comm_stream);
+  if (c.ev_cp_go) cudaEventDestroy(c.ev_cp_go);
+  for (int q = 0; q < 4; q++) { if (c.cp_stream[q]) cudaStreamDestroy(c.cp_stream[q]); if (c.ev_cp_done[q]) cudaEventDestroy(c.ev_cp_done[q]); }
   cufftHandle all[8] = {c.plan_r2c, c.plan_c2r, c.plan_c2r3, c.plan2d_r2c, c.plan2d_c2r, c.plan1d_x, c.plan_r2c_oop, c.plan2d_r2c_oop};
   for (cufftHandle h : all)
     if (h) cufftDestroy(h);
@@ -373,6 +455,21 @@ static void all_to_all(Ctx &c, const void *send, void *recv, size_t block_bytes)
 template <typename R, typename C>
 static void dist_r2c(Ctx &c, void *g) {
   const int N = c.N, NZ = c.NZ, nxb = c.nx, nyl = c.ny_loc;
+  if (c.xf_on && c.xf_dma) {
+    // 2-D r2c in place; the copy engines deliver every owner's ky rows into its staging slot; the fused kernel
+    // gathers the x-lines from the (local) staging slot, transforms them and writes the transposed k-space into g
+    if (sizeof(R) == 4) CKFFT(cufftExecR2C(c.plan2d_r2c, (cufftReal *) g, (cufftComplex *) g));
+    else CKFFT(cufftExecD2Z(c.plan2d_r2c, (cufftDoubleReal *) g, (cufftDoubleComplex *) g));
+    c.launches += 2;
+    {
+      PhaseTimer t(c, PH_COMM);
+      p2p_barrier(c);                       // every rank has consumed its staging slot
+      exchange_dma(c, c.stream, true, g, 0);
+      p2p_barrier(c);                       // every rank's blocks have landed
+    }
+    xfft_fwd<C>(c, g, c.stream);
+    return;
+  }
   if (c.xf_on) {
     // 2-D r2c out of place into this rank's transpose buffer; the fused kernel pulls the x-lines from their owners
     if (sizeof(R) == 4) CKFFT(cufftExecR2C(c.plan2d_r2c_oop, (cufftReal *) g, (cufftComplex *) c.tbuf_a));
@@ -417,7 +514,13 @@ template <typename R, typename C>
 static void dist_c2r(Ctx &c, void *g) {
   const int N = c.N, NZ = c.NZ, nxb = c.nx, nyl = c.ny_loc;
   if (c.xf_on) {
-    {
+    if (c.xf_dma) {
+      xfft_bwd<C>(c, g, 0, c.stream);       // x-transform + pack into the local staging slot
+      PhaseTimer t(c, PH_COMM);
+      p2p_barrier(c);                       // every rank is done with its landing slot
+      exchange_dma(c, c.stream, false, nullptr, 0);
+      p2p_barrier(c);                       // every rank's blocks have landed
+    } else {
       PhaseTimer t(c, PH_COMM);
       p2p_barrier(c);                       // every rank is done with its transpose buffer
       xfft_bwd<C>(c, g, 0, c.stream);
@@ -465,6 +568,31 @@ static void dist_c2r3(Ctx &c, int block) {
   const int N = c.N, NZ = c.NZ, nxb = c.nx, nyl = c.ny_loc;
   const size_t gb = c.grid_bytes();
   cudaStream_t S = c.stream, T = c.comm_stream;
+  if (c.xf_on && c.xf_dma) {
+    // compute stream: the three x-transform + pack kernels back to back, then the 2-D c2r of each component as it lands;
+    // communication stream: flag barrier, the copy-engine blocks of component a (while the SMs transform a + 1), barrier
+    //   compute: [X 0][X 1][X 2]        [2-D 0][2-D 1][2-D 2]
+    //   DMA    :      [B][copy 0][B][copy 1][B][copy 2][B]
+    for (int a = 0; a < 3; a++) {
+      xfft_bwd<C>(c, c.grid[block_grid(block, a)], a, S);
+      CK(cudaEventRecord(c.ev_fft[a], S));
+    }
+    for (int a = 0; a < 3; a++) {
+      CK(cudaStreamWaitEvent(T, c.ev_fft[a], 0));
+      if (a == 0) p2p_barrier(c, T);        // every rank is done with all three landing slots
+      exchange_dma(c, T, false, nullptr, a);
+      p2p_barrier(c, T);                    // component a has landed everywhere
+      CK(cudaEventRecord(c.ev_tr[a], T));
+    }
+    for (int a = 0; a < 3; a++) {
+      CK(cudaStreamWaitEvent(S, c.ev_tr[a], 0));
+      void *src = (char *) c.tbuf_a + (size_t) a * gb, *g = c.grid[block_grid(block, a)];
+      if (sizeof(R) == 4) CKFFT(cufftExecC2R(c.plan2d_c2r, (cufftComplex *) src, (cufftReal *) g));
+      else CKFFT(cufftExecZ2D(c.plan2d_c2r, (cufftDoubleComplex *) src, (cufftDoubleReal *) g));
+    }
+    c.launches += 6;
+    return;
+  }
   if (c.xf_on) {
     // fused x-transform + exchange of component a on the communication stream, the 2-D c2r of the components that
     // have landed on the compute stream:   comm: [B][X 0][B][X 1][B][X 2][B]     compute: [2-D 0][2-D 1][2-D 2]
@@ -508,6 +636,58 @@ static void dist_c2r3(Ctx &c, int block) {
     else CKFFT(cufftExecZ2D(c.plan2d_c2r, (cufftDoubleComplex *) src, (cufftDoubleReal *) g));
   }
   c.launches += 9 + 3;
+}
+
+// Developer probe (mgp_debug_time_exchange): device time of ONE piece of the slab exchange, repeated `reps` times back
+// to back between two flag barriers, without the transforms around it.  which: 0 flag barrier, 1 fused backward
+// (x-transform + push), 2 fused forward (pull + x-transform), 3 backward transpose kernel, 4 forward transpose kernel,
+// 5 cudaMemcpyAsync of the remote share of one slab from the next rank's buffer (copy-engine reference), 6 / 7 the
+// backward / forward strided copy-engine blocks of the DMA exchange.
+// Overwrites grid 1 / the transpose buffers: call it outside a step.
+void fft_debug_exchange(Ctx &c, int which, int reps, float *ms) {
+  REQUIRE(c.slab && c.p2p, MGP_ERR_STATE, "exchange probe: needs the peer-memory slab path");
+  REQUIRE(which == 0 || which >= 3 || c.xf_on, MGP_ERR_STATE, "exchange probe: fused x-transform is off");
+  const int N = c.N, NZ = c.NZ, nxb = c.nx, nyl = c.ny_loc;
+  void *g = c.grid[1];
+  PeerPtrs pp;
+  for (int r = 0; r < 16; r++) pp.p[r] = c.peer_tbuf[r];
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  p2p_barrier(c);
+  CK(cudaEventRecord(e0, c.stream));
+  for (int it = 0; it < reps; it++) {
+    switch (which) {
+      case 0: p2p_barrier(c); break;
+      case 1: if (c.gbytes == 4) xfft_bwd<float2>(c, g, 0, c.stream); else xfft_bwd<double2>(c, g, 0, c.stream); break;
+      case 2: if (c.gbytes == 4) xfft_fwd<float2>(c, g, c.stream); else xfft_fwd<double2>(c, g, c.stream); break;
+      case 3: {
+        dim3 gr((N + 31) / 32, (NZ + 31) / 32, nyl), bl(32, 8);
+        if (c.gbytes == 4) k_transpose_bwd_p2p<float2><<<gr, bl, 0, c.stream>>>((const float2 *) g, pp, nxb, c.y0, N, NZ, nyl);
+        else k_transpose_bwd_p2p<double2><<<gr, bl, 0, c.stream>>>((const double2 *) g, pp, nxb, c.y0, N, NZ, nyl);
+        break;
+      }
+      case 4: {
+        dim3 gr((nxb + 31) / 32, (NZ + 31) / 32, N), bl(32, 8);
+        if (c.gbytes == 4) k_transpose_fwd_p2p<float2><<<gr, bl, 0, c.stream>>>((const float2 *) g, pp, nxb, c.x0, N, NZ, nyl);
+        else k_transpose_fwd_p2p<double2><<<gr, bl, 0, c.stream>>>((const double2 *) g, pp, nxb, c.x0, N, NZ, nyl);
+        break;
+      }
+      case 6: exchange_dma(c, c.stream, false, nullptr, 0); break;
+      case 7: exchange_dma(c, c.stream, true, g, 0); break;
+      default: {
+        const size_t bytes = (size_t) nxb * N * NZ * (c.gbytes == 4 ? sizeof(float2) : sizeof(double2)) / c.P * (c.P - 1);
+        if (bytes) CK(cudaMemcpyAsync(c.tbuf_b, c.peer_tbuf[c.right], bytes, cudaMemcpyDefault, c.stream));
+        break;
+      }
+    }
+  }
+  CK(cudaEventRecord(e1, c.stream));
+  p2p_barrier(c);
+  CK(cudaStreamSynchronize(c.stream));
+  CK(cudaGetLastError());
+  CK(cudaEventElapsedTime(ms, e0, e1));
+  *ms /= (float) (reps > 0 ? reps : 1);
+  CK(cudaEventDestroy(e0)); CK(cudaEventDestroy(e1));
 }
 
 // ------------------------------------------------------------------ public (module) entry points

@@ -8,10 +8,11 @@
 //   forward (r2c direction): a CTA pulls the same tile from the owners of the x-planes (NVLink loads), transforms it
 //     and writes the lines of the local transposed k-space.
 //
-// Transform: power-of-two N, in-place in shared memory, radix-16/8/4/2 passes held in registers.  Backward runs
-// decimation in frequency (natural in, digit-reversed out: the scatter to the owners undoes the permutation for
-// free); forward runs the transposed flow graph (decimation in time: digit-reversed in, natural out: the gather from
-// the owners applies the permutation for free).  Unnormalised in both directions, like FFTW / cuFFT.
+// Transform: N = 2^LGN (a template parameter: every radix, stride, twiddle offset and digit shuffle is a compile-time
+// constant), in place in shared memory, radix-16/8/4/2 passes held in registers.  Backward runs decimation in
+// frequency (natural in, digit-reversed out: the scatter to the owners undoes the permutation for free); forward
+// runs the transposed flow graph (decimation in time: digit-reversed in, natural out: the gather from the owners
+// applies the permutation for free).  Unnormalised in both directions, like FFTW / cuFFT.
 //
 // Shared-memory tile: element (x, k) of the TK lines lives at row x, column k ^ (x & (TK-1)).  A butterfly touches
 // whole rows (TK lanes = TK columns of one row: conflict-free for every stride); the swizzle makes the x-contiguous
@@ -34,54 +35,61 @@ struct PeerPtrs { void *p[16]; };
 
 namespace xf {
 
-constexpr int kMaxPass = 4;
+constexpr int kThreads = 256;
+constexpr int kMinLgN = 4, kMaxLgN = 12;
 
-struct Plan {
-  int N, npass;
-  int R[kMaxPass], lgR[kMaxPass], lgM[kMaxPass];   // decimation-in-frequency order: pass i works on sub-transforms
-                                                   // of length L_i = R_i << lgM_i (L_0 = N, L_{i+1} = M_i)
-  int twoff[kMaxPass];                             // exp(+2 pi i t / L_i), t < L_i, starts here in the twiddle table
-  int twtotal;
-};
+// ------------------------------------------------------------------ the pass plan of N = 2^lgn (compile time)
+// decimation-in-frequency order: pass i works on sub-transforms of length L_i = R_i * M_i (L_0 = N, L_{i+1} = M_i)
 
-// false: N is not a power of two in [16, 4096]
-inline bool make_plan(int N, Plan &pl) {
-  if (N < 16 || N > 4096 || (N & (N - 1))) return false;
-  pl.N = N; pl.npass = 0; pl.twtotal = 0;
-  int rem = N;
-  while (rem > 1) {
-    int R;
-    if (rem == 32) R = 8;                 // 32 = 8 * 4 rather than 16 * 2
-    else if (rem >= 16) R = 16;
-    else R = rem;                         // 8, 4 or 2
-    int lgR = 0; while ((1 << lgR) < R) lgR++;
-    const int M = rem / R;
-    int lgM = 0; while ((1 << lgM) < M) lgM++;
-    pl.R[pl.npass] = R; pl.lgR[pl.npass] = lgR; pl.lgM[pl.npass] = lgM;
-    pl.twoff[pl.npass] = pl.twtotal; pl.twtotal += rem;
-    pl.npass++;
-    rem = M;
+__host__ __device__ constexpr int plan_lgR(int lgn, int i) {
+  int rem = lgn, r = 0;
+  for (int p = 0; p <= i; p++) {
+    r = rem == 5 ? 3 : (rem >= 4 ? 4 : rem);      // 32 = 8 * 4 rather than 16 * 2
+    rem -= r;
   }
-  return true;
+  return r;
+}
+__host__ __device__ constexpr int plan_lgM(int lgn, int i) {
+  int rem = lgn;
+  for (int p = 0; p <= i; p++) rem -= plan_lgR(lgn, p);
+  return rem;
+}
+__host__ __device__ constexpr int plan_npass(int lgn) {
+  int n = 0;
+  while (plan_lgM(lgn, n) > 0) n++;
+  return n + 1;
+}
+__host__ __device__ constexpr int plan_twoff(int lgn, int i) {      // exp(+2 pi i t / L_i), t < L_i, starts here in the twiddle table
+  int off = 0;
+  for (int p = 0; p < i; p++) off += 1 << (plan_lgR(lgn, p) + plan_lgM(lgn, p));
+  return off;
+}
+__host__ __device__ constexpr int plan_twtotal(int lgn) { return plan_twoff(lgn, plan_npass(lgn)); }
+
+// lines per tile: at most 64 KB of shared memory per CTA so that two CTAs share an SM (one tile's global traffic
+// overlaps the other's butterflies); 0 = the tile does not fit at all
+__host__ __device__ constexpr int tile_lines(int lgn, int cbytes) {
+  int tk = 16;
+  while (tk > 4 && ((size_t) tk << lgn) * cbytes > 64 * 1024) tk >>= 1;
+  return (((size_t) tk << lgn) * cbytes > 200 * 1024) ? 0 : tk;
 }
 
-// position p of the decimation-in-frequency output holds frequency digit_rev(p)
-XF_HD int digit_rev(const Plan &pl, int p) {
-  int f = 0, sh = 0;
-  for (int i = 0; i < pl.npass; i++) {
-    f += ((p >> pl.lgM[i]) & (pl.R[i] - 1)) << sh;
-    sh += pl.lgR[i];
-  }
+// position p of the decimation-in-frequency output holds frequency digit_rev(p); digit_rev_inv is the inverse map
+template <int LGN> XF_HD int digit_rev(int p) {
+  constexpr int NP = plan_npass(LGN);
+  int f = (p >> plan_lgM(LGN, 0)) & ((1 << plan_lgR(LGN, 0)) - 1);
+  if (NP > 1) f |= ((p >> plan_lgM(LGN, 1)) & ((1 << plan_lgR(LGN, 1)) - 1)) << plan_lgR(LGN, 0);
+  if (NP > 2) f |= ((p >> plan_lgM(LGN, 2)) & ((1 << plan_lgR(LGN, 2)) - 1)) << (plan_lgR(LGN, 0) + plan_lgR(LGN, 1));
   return f;
 }
-XF_HD int digit_rev_inv(const Plan &pl, int x) {
-  int p = 0;
-  for (int i = 0; i < pl.npass; i++) {
-    p += (x & (pl.R[i] - 1)) << pl.lgM[i];
-    x >>= pl.lgR[i];
-  }
+template <int LGN> XF_HD int digit_rev_inv(int x) {
+  constexpr int NP = plan_npass(LGN);
+  int p = (x & ((1 << plan_lgR(LGN, 0)) - 1)) << plan_lgM(LGN, 0);
+  if (NP > 1) p |= ((x >> plan_lgR(LGN, 0)) & ((1 << plan_lgR(LGN, 1)) - 1)) << plan_lgM(LGN, 1);
+  if (NP > 2) p |= ((x >> (plan_lgR(LGN, 0) + plan_lgR(LGN, 1))) & ((1 << plan_lgR(LGN, 2)) - 1)) << plan_lgM(LGN, 2);
   return p;
 }
+static_assert(plan_npass(kMaxLgN) <= 3, "digit_rev handles three passes");
 
 // ------------------------------------------------------------------ complex helpers
 
@@ -160,18 +168,24 @@ template <typename C> XF_HD C tw_load(const C *p) {
 #endif
 }
 
-// One radix-R butterfly (work item w of pass i) on the tile.  DIT = false: DFT_R then twiddle (decimation in
-// frequency); DIT = true: twiddle then DFT_R (the transposed graph).  tw = table of this pass, exp(+2 pi i t / L).
-template <int R, int SIGN, bool DIT, int TK, typename C>
-XF_HD void butterfly(C *s, const C *tw, int lgM, int w) {
-  const int k = w & (TK - 1), bb = w / TK;
-  const int M = 1 << lgM;
-  const int blk = bb >> lgM, b = bb & (M - 1);
-  const int base = blk * (R << lgM) + b;
+// One radix-R butterfly of pass I on line k: inputs x_j = base + j * M.  DIT = false: DFT_R then twiddle
+// (decimation in frequency); DIT = true: twiddle then DFT_R (the transposed graph).
+template <int LGN, int I, int SIGN, bool DIT, int TK, typename C>
+XF_HD void butterfly(C *s, const C *twtab, int bb, int k) {
+  constexpr int LGR = plan_lgR(LGN, I), LGM = plan_lgM(LGN, I), R = 1 << LGR, M = 1 << LGM;
+  const C *tw = twtab + plan_twoff(LGN, I);
+  const int blk = bb >> LGM, b = bb & (M - 1);
+  const int base = (blk << (LGR + LGM)) + b;
   C v[R];
+  if (M >= TK) {           // x_j & (TK-1) does not depend on j: one column, constant row stride
+    const C *p = s + base * TK + (k ^ (base & (TK - 1)));
 #pragma unroll
-  for (int j = 0; j < R; j++) v[j] = s[sidx<TK>(base + (j << lgM), k)];
-  if (DIT && lgM > 0) {
+    for (int j = 0; j < R; j++) v[j] = p[j * (M * TK)];
+  } else {
+#pragma unroll
+    for (int j = 0; j < R; j++) v[j] = s[sidx<TK>(base + j * M, k)];
+  }
+  if (DIT && M > 1) {
 #pragma unroll
     for (int j = 1; j < R; j++) {
       C t = tw_load(tw + b * j);
@@ -180,7 +194,7 @@ XF_HD void butterfly(C *s, const C *tw, int lgM, int w) {
     }
   }
   Dft<R, SIGN, C>::run(v);
-  if (!DIT && lgM > 0) {
+  if (!DIT && M > 1) {
 #pragma unroll
     for (int q = 1; q < R; q++) {
       C t = tw_load(tw + b * q);
@@ -188,56 +202,27 @@ XF_HD void butterfly(C *s, const C *tw, int lgM, int w) {
       v[q] = cmul(v[q], t);
     }
   }
+  if (M >= TK) {
+    C *p = s + base * TK + (k ^ (base & (TK - 1)));
 #pragma unroll
-  for (int q = 0; q < R; q++) s[sidx<TK>(base + (q << lgM), k)] = v[q];
-}
-
-// all work items of pass i that belong to thread tid of nthr
-template <int SIGN, bool DIT, int TK, typename C>
-XF_HD void phase_pass(C *s, const Plan &pl, const C *twtab, int i, int tid, int nthr) {
-  const int R = pl.R[i], lgM = pl.lgM[i];
-  const int items = TK * (pl.N >> pl.lgR[i]);
-  const C *tw = twtab + pl.twoff[i];
-  for (int w = tid; w < items; w += nthr) {
-    switch (R) {
-      case 16: butterfly<16, SIGN, DIT, TK, C>(s, tw, lgM, w); break;
-      case 8: butterfly<8, SIGN, DIT, TK, C>(s, tw, lgM, w); break;
-      case 4: butterfly<4, SIGN, DIT, TK, C>(s, tw, lgM, w); break;
-      default: butterfly<2, SIGN, DIT, TK, C>(s, tw, lgM, w); break;
-    }
+    for (int q = 0; q < R; q++) p[q * (M * TK)] = v[q];
+  } else {
+#pragma unroll
+    for (int q = 0; q < R; q++) s[sidx<TK>(base + q * M, k)] = v[q];
   }
 }
 
-// ------------------------------------------------------------------ global side, backward (local lines -> owners of x)
-
-// lines [jl][k0 + k][x], x contiguous: lanes run along x
-template <int TK, typename C>
-XF_HD void phase_load_lines(C *s, const C *__restrict__ in, int N, int NZ, int jl, int k0, int tid, int nthr) {
-  const int tot = TK * N;
-  for (int e = tid; e < tot; e += nthr) {
-    const int k = e / N, x = e - k * N;
-    C v = mk<C>(0, 0);
-    if (k0 + k < NZ) v = in[((size_t) jl * NZ + (k0 + k)) * N + x];
-    s[sidx<TK>(x, k)] = v;
-  }
+// all butterflies of pass I that belong to thread tid of nthr (nthr a multiple of TK: the line k of a thread is fixed)
+template <int LGN, int I, int SIGN, bool DIT, int TK, typename C>
+XF_HD void phase_pass(C *s, const C *twtab, int tid, int nthr) {
+  constexpr int items = TK << (LGN - plan_lgR(LGN, I));
+  const int k = tid & (TK - 1);
+  for (int w = tid; w < items; w += nthr) butterfly<LGN, I, SIGN, DIT, TK, C>(s, twtab, w / TK, k);
 }
 
-// position p holds x = digit_rev(p); it goes to rank x / nxb as [xl][ky = y0 + jl][kz]: lanes run along kz
-template <int TK, typename C>
-XF_HD void phase_store_owners(const C *s, const PeerPtrs &out, const Plan &pl, int nxb, int y0, int NY, int NZ, int jl,
-                              int k0, int tid, int nthr) {
-  const int N = pl.N;
-  const int tot = TK * N;
-  for (int e = tid; e < tot; e += nthr) {
-    const int k = e & (TK - 1), p = e / TK;
-    if (k0 + k >= NZ) continue;
-    const int x = digit_rev(pl, p);
-    const int r = x / nxb, xl = x - r * nxb;
-    ((C *) out.p[r])[((size_t) xl * NY + (y0 + jl)) * NZ + (k0 + k)] = s[sidx<TK>(p, k)];
-  }
-}
+// ------------------------------------------------------------------ global side
 
-// ------------------------------------------------------------------ global side, forward (owners of x -> local lines)
+constexpr int kBatch = 8;      // independent global loads a thread keeps in flight
 
 template <typename C> XF_HD C peer_load(const C *p) {
 #if defined(__CUDA_ARCH__)
@@ -245,11 +230,11 @@ template <typename C> XF_HD C peer_load(const C *p) {
   C v;
   if (sizeof(C) == 16) {
     double a, b;
-    asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "l"(p));
     v.x = (typename RealOf<C>::type) a; v.y = (typename RealOf<C>::type) b;
   } else {
     float a, b;
-    asm volatile("ld.relaxed.sys.global.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "l"(p));
     v.x = (typename RealOf<C>::type) a; v.y = (typename RealOf<C>::type) b;
   }
   return v;
@@ -258,30 +243,83 @@ template <typename C> XF_HD C peer_load(const C *p) {
 #endif
 }
 
-// element x of line (jl, k0 + k) lives on rank x / nxb at [xl][ky = y0 + jl][kz]; it is written to the position
-// whose digit reversal it is, so that the decimation-in-time passes deliver natural order
-template <int TK, typename C>
-XF_HD void phase_load_owners(C *s, const PeerPtrs &in, const Plan &pl, int nxb, int y0, int NY, int NZ, int jl, int k0,
-                             int tid, int nthr) {
-  const int N = pl.N;
-  const int tot = TK * N;
-  for (int e = tid; e < tot; e += nthr) {
-    const int k = e & (TK - 1), x = e / TK;
-    C v = mk<C>(0, 0);
-    if (k0 + k < NZ) {
-      const int r = x / nxb, xl = x - r * nxb;
-      v = peer_load((const C *) in.p[r] + ((size_t) xl * NY + (y0 + jl)) * NZ + (k0 + k));
+// backward, load: lines [jl][k0 + k][x], x contiguous: lanes run along x
+template <int LGN, int TK, typename C>
+XF_HD void phase_load_lines(C *s, const C *__restrict__ in, int NZ, int jl, int k0, int tid, int nthr) {
+  constexpr int N = 1 << LGN, tot = TK * N;
+  const C *src = in + ((size_t) jl * NZ + k0) * N;
+  for (int e0 = tid; e0 < tot; e0 += kBatch * nthr) {
+    C v[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; u++) {
+      const int e = e0 + u * nthr;
+      v[u] = mk<C>(0, 0);
+      if (e < tot && k0 + (e >> LGN) < NZ) v[u] = src[e];
     }
-    s[sidx<TK>(digit_rev_inv(pl, x), k)] = v;
+#pragma unroll
+    for (int u = 0; u < kBatch; u++) {
+      const int e = e0 + u * nthr;
+      if (e < tot) s[sidx<TK>(e & (N - 1), e >> LGN)] = v[u];
+    }
   }
 }
 
-template <int TK, typename C>
-XF_HD void phase_store_lines(const C *s, C *__restrict__ out, int N, int NZ, int jl, int k0, int tid, int nthr) {
-  const int tot = TK * N;
+// backward, store: position p holds x = digit_rev(p); it goes to rank x >> lg_nxb as [xl][ky = y0 + jl][kz]:
+// lanes run along kz (runs of TK complex values)
+template <int LGN, int TK, typename C>
+XF_HD void phase_store_owners(const C *s, const PeerPtrs &out, int lg_nxb, int y0, int NY, int NZ, int jl, int k0,
+                              int tid, int nthr) {
+  constexpr int N = 1 << LGN, tot = TK * N;
+  const int k = tid & (TK - 1);
+  if (k0 + k >= NZ) return;
+  const size_t col = (size_t) (y0 + jl) * NZ + (k0 + k);
+  const size_t xstride = (size_t) NY * NZ;
   for (int e = tid; e < tot; e += nthr) {
-    const int k = e / N, x = e - k * N;
-    if (k0 + k < NZ) out[((size_t) jl * NZ + (k0 + k)) * N + x] = s[sidx<TK>(x, k)];
+    const int p = e / TK;
+    const int x = digit_rev<LGN>(p);
+    const int r = x >> lg_nxb, xl = x & ((1 << lg_nxb) - 1);
+    ((C *) out.p[r])[(size_t) xl * xstride + col] = s[sidx<TK>(p, k)];
+  }
+}
+
+// forward, load: element x of line (jl, k0 + k) lives on rank x >> lg_nxb at [xl][ky = y0 + jl][kz]; it is written to
+// the position whose digit reversal it is, so that the decimation-in-time passes deliver natural order
+template <int LGN, int TK, typename C>
+XF_HD void phase_load_owners(C *s, const PeerPtrs &in, int lg_nxb, int y0, int NY, int NZ, int jl, int k0, int tid,
+                             int nthr) {
+  constexpr int N = 1 << LGN, tot = TK * N;
+  const int k = tid & (TK - 1);
+  const bool live = k0 + k < NZ;
+  const size_t col = (size_t) (y0 + jl) * NZ + (k0 + k);
+  const size_t xstride = (size_t) NY * NZ;
+  for (int e0 = tid; e0 < tot; e0 += kBatch * nthr) {
+    C v[kBatch];
+#pragma unroll
+    for (int u = 0; u < kBatch; u++) {
+      const int e = e0 + u * nthr;
+      v[u] = mk<C>(0, 0);
+      if (e < tot && live) {
+        const int x = e / TK;
+        const int r = x >> lg_nxb, xl = x & ((1 << lg_nxb) - 1);
+        v[u] = peer_load((const C *) in.p[r] + (size_t) xl * xstride + col);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kBatch; u++) {
+      const int e = e0 + u * nthr;
+      if (e < tot) s[sidx<TK>(digit_rev_inv<LGN>(e / TK), k)] = v[u];
+    }
+  }
+}
+
+// forward, store: the lines of the local transposed k-space, x contiguous
+template <int LGN, int TK, typename C>
+XF_HD void phase_store_lines(const C *s, C *__restrict__ out, int NZ, int jl, int k0, int tid, int nthr) {
+  constexpr int N = 1 << LGN, tot = TK * N;
+  C *dst = out + ((size_t) jl * NZ + k0) * N;
+  for (int e = tid; e < tot; e += nthr) {
+    const int k = e >> LGN, x = e & (N - 1);
+    if (k0 + k < NZ) dst[e] = s[sidx<TK>(x, k)];
   }
 }
 
@@ -289,48 +327,45 @@ XF_HD void phase_store_lines(const C *s, C *__restrict__ out, int N, int NZ, int
 
 #if defined(__CUDACC__)
 
-constexpr int kThreads = 256;
-
-// backward: in = local [nyl][NZ][N] (transposed k-space); out.p[r] = rank r's landing buffer [nxb][N][NZ]
-template <typename C, int TK>
+// backward: in = local [nyl][NZ][N] (transposed k-space); out.p[r] = rank r's landing buffer [nxb][NY][NZ]
+template <typename C, int LGN, int TK>
 __global__ void __launch_bounds__(kThreads, 2)
-k_xfft_bwd_p2p(const C *__restrict__ in, const __grid_constant__ PeerPtrs out, const __grid_constant__ Plan pl, const C *__restrict__ twtab, int nxb, int y0, int NY,
-               int NZ, int nyl) {
+k_xfft_bwd_p2p(const C *__restrict__ in, const __grid_constant__ PeerPtrs out, const C *__restrict__ twtab, int lg_nxb,
+               int y0, int NY, int NZ, int nyl) {
   extern __shared__ __align__(16) unsigned char xf_smem[];
   C *s = reinterpret_cast<C *>(xf_smem);
-  const int N = pl.N;
   const int ktiles = (NZ + TK - 1) / TK, ntiles = nyl * ktiles;
   for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int jl = t / ktiles, k0 = (t - jl * ktiles) * TK;
-    phase_load_lines<TK, C>(s, in, N, NZ, jl, k0, threadIdx.x, kThreads);
+    phase_load_lines<LGN, TK, C>(s, in, NZ, jl, k0, threadIdx.x, kThreads);
     __syncthreads();
-    for (int i = 0; i < pl.npass; i++) {
-      phase_pass<+1, false, TK, C>(s, pl, twtab, i, threadIdx.x, kThreads);
-      __syncthreads();
-    }
-    phase_store_owners<TK, C>(s, out, pl, nxb, y0, NY, NZ, jl, k0, threadIdx.x, kThreads);
+    phase_pass<LGN, 0, +1, false, TK, C>(s, twtab, threadIdx.x, kThreads);
+    __syncthreads();
+    if constexpr (plan_npass(LGN) > 1) { phase_pass<LGN, 1, +1, false, TK, C>(s, twtab, threadIdx.x, kThreads); __syncthreads(); }
+    if constexpr (plan_npass(LGN) > 2) { phase_pass<LGN, 2, +1, false, TK, C>(s, twtab, threadIdx.x, kThreads); __syncthreads(); }
+    phase_store_owners<LGN, TK, C>(s, out, lg_nxb, y0, NY, NZ, jl, k0, threadIdx.x, kThreads);
     __syncthreads();
   }
 }
 
-// forward: in.p[r] = rank r's [nxb][N][NZ] (output of its local 2-D r2c); out = local [nyl][NZ][N]
-template <typename C, int TK>
+// forward: in.p[r] = rank r's [nxb][NY][NZ] (output of its local 2-D r2c); out = local [nyl][NZ][N]
+template <typename C, int LGN, int TK>
 __global__ void __launch_bounds__(kThreads, 2)
-k_xfft_fwd_p2p(const __grid_constant__ PeerPtrs in, C *__restrict__ out, const __grid_constant__ Plan pl, const C *__restrict__ twtab, int nxb, int y0, int NY,
-               int NZ, int nyl) {
+k_xfft_fwd_p2p(const __grid_constant__ PeerPtrs in, C *__restrict__ out, const C *__restrict__ twtab, int lg_nxb, int y0,
+               int NY, int NZ, int nyl) {
   extern __shared__ __align__(16) unsigned char xf_smem[];
   C *s = reinterpret_cast<C *>(xf_smem);
-  const int N = pl.N;
   const int ktiles = (NZ + TK - 1) / TK, ntiles = nyl * ktiles;
   for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int jl = t / ktiles, k0 = (t - jl * ktiles) * TK;
-    phase_load_owners<TK, C>(s, in, pl, nxb, y0, NY, NZ, jl, k0, threadIdx.x, kThreads);
+    phase_load_owners<LGN, TK, C>(s, in, lg_nxb, y0, NY, NZ, jl, k0, threadIdx.x, kThreads);
     __syncthreads();
-    for (int i = pl.npass - 1; i >= 0; i--) {
-      phase_pass<-1, true, TK, C>(s, pl, twtab, i, threadIdx.x, kThreads);
-      __syncthreads();
-    }
-    phase_store_lines<TK, C>(s, out, N, NZ, jl, k0, threadIdx.x, kThreads);
+    // the transposed graph runs the passes in reverse order
+    if constexpr (plan_npass(LGN) > 2) { phase_pass<LGN, 2, -1, true, TK, C>(s, twtab, threadIdx.x, kThreads); __syncthreads(); }
+    if constexpr (plan_npass(LGN) > 1) { phase_pass<LGN, 1, -1, true, TK, C>(s, twtab, threadIdx.x, kThreads); __syncthreads(); }
+    phase_pass<LGN, 0, -1, true, TK, C>(s, twtab, threadIdx.x, kThreads);
+    __syncthreads();
+    phase_store_lines<LGN, TK, C>(s, out, NZ, jl, k0, threadIdx.x, kThreads);
     __syncthreads();
   }
 }

@@ -12,13 +12,13 @@
 using namespace mgp;
 using namespace mgp::xf;
 
-template <typename C> std::vector<C> twiddles(const Plan &pl) {
-  std::vector<C> tw(pl.twtotal);
-  for (int i = 0; i < pl.npass; i++) {
-    const int L = pl.R[i] << pl.lgM[i];
+template <typename C, int LGN> std::vector<C> twiddles() {
+  std::vector<C> tw(plan_twtotal(LGN));
+  for (int i = 0; i < plan_npass(LGN); i++) {
+    const int L = 1 << (plan_lgR(LGN, i) + plan_lgM(LGN, i));
     for (int t = 0; t < L; t++) {
       const long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double) t / (long double) L;
-      tw[pl.twoff[i] + t] = mk<C>((typename RealOf<C>::type) cosl(a), (typename RealOf<C>::type) sinl(a));
+      tw[plan_twoff(LGN, i) + t] = mk<C>((typename RealOf<C>::type) cosl(a), (typename RealOf<C>::type) sinl(a));
     }
   }
   return tw;
@@ -28,12 +28,12 @@ static double frand() { return (double) rand() / RAND_MAX - 0.5; }
 
 // global field A[x][ky][kz] (x < N, ky < NY, kz < NZ); rank r owns x-planes [r*nxb, (r+1)*nxb) in "real-side" layout
 // [xl][NY][NZ] and ky-rows [r*nyl, (r+1)*nyl) in the transposed layout [jl][NZ][N].
-template <typename C, int TK>
-static int run_case(int N, int P, int NY, int NZ, int nthr, double tol) {
-  Plan pl;
-  if (!make_plan(N, pl)) { printf("no plan for N=%d\n", N); return 1; }
+template <typename C, int LGN, int TK>
+static int run_case(int P, int NY, int NZ, int nthr, double tol) {
+  constexpr int N = 1 << LGN;
   const int nxb = N / P, nyl = NY / P;
-  std::vector<C> tw = twiddles<C>(pl);
+  int lgx = 0; while ((1 << lgx) < nxb) lgx++;
+  std::vector<C> tw = twiddles<C, LGN>();
   std::vector<C> smem((size_t) TK * N);
   const int ktiles = (NZ + TK - 1) / TK;
   int bad = 0;
@@ -50,10 +50,13 @@ static int run_case(int N, int P, int NY, int NZ, int nthr, double tol) {
     for (int r = 0; r < P; r++)
       for (int t = 0; t < nyl * ktiles; t++) {
         const int jl = t / ktiles, k0 = (t - jl * ktiles) * TK;
-        for (int tid = 0; tid < nthr; tid++) phase_load_lines<TK, C>(smem.data(), lines[r].data(), N, NZ, jl, k0, tid, nthr);
-        for (int i = 0; i < pl.npass; i++)
-          for (int tid = 0; tid < nthr; tid++) phase_pass<+1, false, TK, C>(smem.data(), pl, tw.data(), i, tid, nthr);
-        for (int tid = 0; tid < nthr; tid++) phase_store_owners<TK, C>(smem.data(), pp, pl, nxb, r * nyl, NY, NZ, jl, k0, tid, nthr);
+        for (int tid = 0; tid < nthr; tid++) phase_load_lines<LGN, TK, C>(smem.data(), lines[r].data(), NZ, jl, k0, tid, nthr);
+        for (int tid = 0; tid < nthr; tid++) phase_pass<LGN, 0, +1, false, TK, C>(smem.data(), tw.data(), tid, nthr);
+        if constexpr (plan_npass(LGN) > 1)
+          for (int tid = 0; tid < nthr; tid++) phase_pass<LGN, 1, +1, false, TK, C>(smem.data(), tw.data(), tid, nthr);
+        if constexpr (plan_npass(LGN) > 2)
+          for (int tid = 0; tid < nthr; tid++) phase_pass<LGN, 2, +1, false, TK, C>(smem.data(), tw.data(), tid, nthr);
+        for (int tid = 0; tid < nthr; tid++) phase_store_owners<LGN, TK, C>(smem.data(), pp, lgx, r * nyl, NY, NZ, jl, k0, tid, nthr);
       }
     double emax = 0, vmax = 0;
     for (int r = 0; r < P; r++)
@@ -92,10 +95,13 @@ static int run_case(int N, int P, int NY, int NZ, int nthr, double tol) {
     for (int r = 0; r < P; r++)
       for (int t = 0; t < nyl * ktiles; t++) {
         const int jl = t / ktiles, k0 = (t - jl * ktiles) * TK;
-        for (int tid = 0; tid < nthr; tid++) phase_load_owners<TK, C>(smem.data(), pp, pl, nxb, r * nyl, NY, NZ, jl, k0, tid, nthr);
-        for (int i = pl.npass - 1; i >= 0; i--)
-          for (int tid = 0; tid < nthr; tid++) phase_pass<-1, true, TK, C>(smem.data(), pl, tw.data(), i, tid, nthr);
-        for (int tid = 0; tid < nthr; tid++) phase_store_lines<TK, C>(smem.data(), out[r].data(), N, NZ, jl, k0, tid, nthr);
+        for (int tid = 0; tid < nthr; tid++) phase_load_owners<LGN, TK, C>(smem.data(), pp, lgx, r * nyl, NY, NZ, jl, k0, tid, nthr);
+        if constexpr (plan_npass(LGN) > 2)
+          for (int tid = 0; tid < nthr; tid++) phase_pass<LGN, 2, -1, true, TK, C>(smem.data(), tw.data(), tid, nthr);
+        if constexpr (plan_npass(LGN) > 1)
+          for (int tid = 0; tid < nthr; tid++) phase_pass<LGN, 1, -1, true, TK, C>(smem.data(), tw.data(), tid, nthr);
+        for (int tid = 0; tid < nthr; tid++) phase_pass<LGN, 0, -1, true, TK, C>(smem.data(), tw.data(), tid, nthr);
+        for (int tid = 0; tid < nthr; tid++) phase_store_lines<LGN, TK, C>(smem.data(), out[r].data(), NZ, jl, k0, tid, nthr);
       }
     double emax = 0, vmax = 0;
     for (int r = 0; r < P; r++)
@@ -122,34 +128,47 @@ static int run_case(int N, int P, int NY, int NZ, int nthr, double tol) {
   return bad;
 }
 
+template <int LGN> static int check_digits() {
+  constexpr int N = 1 << LGN;
+  int prod = 0;
+  for (int i = 0; i < plan_npass(LGN); i++) prod += plan_lgR(LGN, i);
+  if (prod != LGN) { printf("plan product mismatch N=%d\n", N); return 1; }
+  std::vector<int> seen(N, 0);
+  for (int p = 0; p < N; p++) {
+    const int f = digit_rev<LGN>(p);
+    if (f < 0 || f >= N || seen[f]++) { printf("digit_rev not a permutation N=%d\n", N); return 1; }
+    if (digit_rev_inv<LGN>(f) != p) { printf("digit_rev_inv mismatch N=%d p=%d\n", N, p); return 1; }
+  }
+  return 0;
+}
+
+// the instance the library launches for this size and precision (tile_lines), 256 threads, plus odd thread counts
+#define CASE_LIB(C, LGN, P, NY, NZ, TOL) bad += run_case<C, LGN, tile_lines(LGN, sizeof(C))>(P, NY, NZ, 256, TOL)
+
 int main() {
   int bad = 0;
   srand(12345);
-  // digit reversal is a permutation and its own inverse map
-  for (int N = 16; N <= 4096; N *= 2) {
-    Plan pl; make_plan(N, pl);
-    int prod = 1; for (int i = 0; i < pl.npass; i++) prod *= pl.R[i];
-    if (prod != N) { printf("plan product mismatch N=%d\n", N); bad++; }
-    std::vector<int> seen(N, 0);
-    for (int p = 0; p < N; p++) {
-      const int f = digit_rev(pl, p);
-      if (f < 0 || f >= N || seen[f]++) { printf("digit_rev not a permutation N=%d\n", N); bad++; break; }
-      if (digit_rev_inv(pl, f) != p) { printf("digit_rev_inv mismatch N=%d p=%d\n", N, p); bad++; break; }
-    }
-  }
+  bad += check_digits<4>() + check_digits<5>() + check_digits<6>() + check_digits<7>() + check_digits<8>() +
+         check_digits<9>() + check_digits<10>() + check_digits<11>() + check_digits<12>();
   const double td = 2e-14, tf = 2e-5;
-  bad += run_case<double2, 16>(16, 2, 4, 9, 256, td);
-  bad += run_case<double2, 8>(32, 1, 2, 3, 64, td);
-  bad += run_case<double2, 4>(64, 2, 2, 5, 256, td);
-  bad += run_case<double2, 16>(128, 4, 4, 17, 256, td);
-  bad += run_case<double2, 16>(256, 8, 8, 9, 256, td);
-  bad += run_case<double2, 8>(512, 2, 2, 3, 256, td);
-  bad += run_case<double2, 4>(1024, 8, 8, 2, 256, td);
-  bad += run_case<double2, 8>(1024, 1, 1, 2, 96, td);
-  bad += run_case<double2, 4>(2048, 2, 2, 1, 256, td);
-  bad += run_case<float2, 16>(256, 2, 2, 17, 256, tf);
-  bad += run_case<float2, 8>(1024, 4, 4, 2, 256, tf);
-  bad += run_case<float2, 16>(64, 1, 1, 33, 32, tf);
+  CASE_LIB(double2, 4, 2, 4, 9, td);
+  CASE_LIB(double2, 5, 1, 2, 17, td);
+  CASE_LIB(double2, 6, 4, 4, 33, td);
+  CASE_LIB(double2, 7, 8, 8, 5, td);
+  CASE_LIB(double2, 8, 2, 2, 17, td);
+  CASE_LIB(double2, 9, 8, 8, 9, td);
+  CASE_LIB(double2, 10, 4, 4, 3, td);
+  CASE_LIB(double2, 11, 2, 2, 1, td);
+  CASE_LIB(float2, 4, 1, 1, 9, tf);
+  CASE_LIB(float2, 7, 2, 2, 17, tf);
+  CASE_LIB(float2, 9, 4, 4, 9, tf);
+  CASE_LIB(float2, 10, 8, 8, 5, tf);
+  CASE_LIB(float2, 12, 2, 2, 1, tf);
+  // other tile widths and thread counts than the library's
+  bad += run_case<double2, 5, 8>(1, 2, 3, 64, td);
+  bad += run_case<double2, 6, 4>(2, 2, 5, 96, td);
+  bad += run_case<double2, 9, 4>(2, 2, 5, 128, td);
+  bad += run_case<double2, 8, 8>(4, 4, 9, 32, td);
   printf(bad ? "FAILED (%d)\n" : "ALL OK\n", bad);
   return bad ? 1 : 0;
 }

@@ -118,9 +118,7 @@ def test_fft_roundtrip_and_nonhermitian_c2r(mgp, require_gpu, gb):
     assert np.abs(k - ref).max() / np.abs(ref).max() < tol
     # c2r of a spectrum that is NOT Hermitian on the kz = 0 / Nyquist planes (as Forces produces)
     ck = (rng.standard_normal((N, N, N // 2 + 1)) + 1j * rng.standard_normal((N, N, N // 2 + 1))).astype(pm.cdtype)
-    buf = np.zeros((N + 1, N, N // 2 + 1), pm.cdtype)
-    buf[:N] = ck
-    pm.upload_grid(mgp.GRID_DENSITY, buf.view(pm.gdtype).reshape(N + 1, N, nzp))
+    pm.upload_grid_k(mgp.GRID_DENSITY, ck)
     pm.fft_c2r(mgp.GRID_DENSITY)
     r = pm.download_grid(mgp.GRID_DENSITY)[:N, :, :N]
     ref = po.c2r(ck.astype(np.complex128), N)

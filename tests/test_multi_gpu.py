@@ -19,11 +19,11 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-def _run(world, tmp, nmesh, steps, model, gb, mode, extra=()):
+def _run(world, tmp, nmesh, steps, model, gb, mode, extra=(), env=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
            "--master-port", "29517", os.path.join(ROOT, "tests", "mgpu_worker.py"), "--nmesh", str(nmesh), "--steps", str(steps),
            "--model", model, "--gb", str(gb), "--mode", str(mode), "--out", str(tmp)] + list(extra)
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, **(env or {})))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     return [dict(np.load(os.path.join(tmp, "rank%d.npz" % k))) for k in range(world)]
 
@@ -50,14 +50,22 @@ def _oracle(nmesh, steps, model):
     return pos, vel, np.stack(pks)
 
 
+# exchange engines of the slab transforms (fft.cu): the default (x-transform kernel fused with pack / unpack + copy-engine
+# blocks over NVLink), the x-transform kernel storing / loading peer memory itself, the cuFFT 1-D plan + transpose kernel
+# over peer memory, and pack / NCCL all-to-all / unpack
+ENGINES = {"dma": {}, "sm": {"MGP_XFFT_DMA": "0"}, "transpose": {"MGP_XFFT": "0"}, "nccl": {"MGP_P2P": "0"}}
+
+
 @pytest.mark.parametrize("world", [2, 4, 8])
-@pytest.mark.parametrize("model,gb,mode", [("fofr", 8, 0), ("lcdm", 4, 2), ("dgp", 8, 1)])
-def test_slab_decomposed_steps_match_oracle(require_gpu, tmp_path, world, model, gb, mode):
+@pytest.mark.parametrize("model,gb,mode,engine", [("fofr", 8, 0, "dma"), ("lcdm", 4, 2, "dma"), ("dgp", 8, 1, "dma"),
+                                                  ("fofr", 8, 0, "sm"), ("lcdm", 4, 2, "sm"), ("fofr", 8, 0, "transpose"),
+                                                  ("fofr", 8, 0, "nccl")])
+def test_slab_decomposed_steps_match_oracle(require_gpu, tmp_path, world, model, gb, mode, engine):
     if _ngpu() < world:
         pytest.skip("needs %d GPUs" % world)
     from mgpicola_b200 import slab
     N, steps, box = 32, 2, 100.0
-    ranks = _run(world, tmp_path, N, steps, model, gb, mode)
+    ranks = _run(world, tmp_path, N, steps, model, gb, mode, env=ENGINES[engine])
     pos, vel, pks = _oracle(N, steps, model)
     all_ids = np.concatenate([r["id"] for r in ranks])
     assert np.array_equal(np.sort(all_ids), np.arange(N ** 3, dtype=np.uint64))          # nobody lost, nobody duplicated
