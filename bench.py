@@ -315,6 +315,10 @@ def run_ours(args):
                                           else "reference-structured: 4 fields, 12 extra c2r/step")) if use_sd
                                       else "scale-independent growth (reference build MODEL=FOFR_LCDM / DGP)"),
                        "nmesh": N, "npart": npart_total, "grid_bytes": g, "scale_dependent": use_sd, "sd_mode": args.sd_mode if use_sd else None, "deposit_mode": args.deposit_mode, "sort_interval": args.sort_interval,
+                       "slab_transform": (None if world == 1 else
+                                          ("2-D cuFFT + x-transform kernel fused with the exchange (stores / loads on peer memory over NVLink)"
+                                           if (N & (N - 1)) == 0 and os.environ.get("MGP_XFFT", "1") != "0" and os.environ.get("MGP_P2P", "1") != "0"
+                                           else "2-D cuFFT + transpose kernel storing into peer memory + 1-D cuFFT (Nmesh not a power of two)")),
                        "l2": "inputs larger than L2 (particles %.1f GB, grids %.1f GB each)" % (N ** 3 * 56 / 1e9, N ** 3 * g / 1e9),
                        "ic_seconds_gpu": round(t_ic, 2)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "e2e": e2e}

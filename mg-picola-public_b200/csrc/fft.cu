@@ -172,8 +172,18 @@ static bool xfft_prepare(Ctx &c) {
     int occ = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, xf::k_xfft_bwd_p2p<C, LGN, TK>, xf::kThreads, c.xf_smem));
     REQUIRE(occ >= 1, MGP_ERR_CUDA, "fused x-transform: kernel does not fit on an SM");
-    const long long ntiles = (long long) c.ny_loc * ((c.NZ + TK - 1) / TK);
-    const long long g = (long long) kSMs * occ;
+    const long long ntiles = (long long) c.ny_loc * xf::tiles_per_line(c.NZ, TK, 128 / (int) sizeof(C));
+    // persistent grid; MGP_XFFT_TRIM CTAs fewer than the machine holds, so that the one-warp flag-barrier kernels of the
+    // communication stream find a free slot while an x-transform kernel owns every register of the other SMs
+    const char *tr = getenv("MGP_XFFT_TRIM");
+    // CTAs per SM: on several ranks the kernel waits on NVLink most of the time; one CTA per SM leaves half of the
+    // registers and shared memory to the 2-D cuFFT kernels of the other components, which then overlap the exchange
+    // (2 x B200, 512^3: batched inverse transform 3.34 -> 2.88 ms); alone on the GPU two CTAs per SM are faster
+    int cps_want = c.P > 1 ? 1 : 2;
+    if (const char *cps = getenv("MGP_XFFT_CPS")) cps_want = atoi(cps);
+    if (cps_want >= 1 && cps_want < occ) occ = cps_want;
+    long long g = (long long) kSMs * occ - (tr ? atoi(tr) : 1);
+    if (g < 1) g = 1;
     c.xf_grid = (int) (ntiles < g ? ntiles : g);
     return true;
   }
@@ -224,8 +234,6 @@ static void xfft_setup(Ctx &c) {
   } else {
     CK(cudaMemcpy(c.xf_tw, tw.data(), (size_t) total * cb, cudaMemcpyHostToDevice));
   }
-  const char *dma = getenv("MGP_XFFT_DMA");
-  c.xf_dma = dma ? (atoi(dma) != 0) : 1;
   c.xf_on = true;
 }
 
@@ -328,9 +336,13 @@ void fft_setup(Ctx &c) {
     lli n1[1] = {N};
     w = make_plan_many(&c.plan1d_x, 1, n1, n1, 1, N, n1, 1, N, f32 ? CUFFT_C2C : CUFFT_Z2Z, c.ny_loc * NZ, c.stream);
     ws = w > ws ? w : ws;
-    // three landing slots (the batched c2r pipelines its three transposes) + three staging slots of the DMA exchange,
-    // one allocation so that a single peer mapping covers both
-    CK(cudaMalloc(&c.tbuf_a, 6 * c.grid_bytes()));
+    // three landing slots (the batched c2r pipelines its three transposes) + three staging slots when the DMA
+    // exchange is selected (MGP_XFFT_DMA=1), one allocation so that a single peer mapping covers both
+    {
+      const char *dma = getenv("MGP_XFFT_DMA");
+      c.xf_dma = dma ? (atoi(dma) != 0) : 0;
+    }
+    CK(cudaMalloc(&c.tbuf_a, (c.xf_dma ? 6 : 3) * c.grid_bytes()));
     CK(cudaMalloc(&c.tbuf_b, c.grid_bytes()));
     p2p_setup(c);
     xfft_setup(c);
@@ -642,8 +654,10 @@ static void dist_c2r3(Ctx &c, int block) {
 // to back between two flag barriers, without the transforms around it.  which: 0 flag barrier, 1 fused backward
 // (x-transform + push), 2 fused forward (pull + x-transform), 3 backward transpose kernel, 4 forward transpose kernel,
 // 5 cudaMemcpyAsync of the remote share of one slab from the next rank's buffer (copy-engine reference), 6 / 7 the
-// backward / forward strided copy-engine blocks of the DMA exchange.
+// backward / forward strided copy-engine blocks of the DMA exchange, 8 the batched inverse transform of the force grids
+// (the whole pipeline), 9 one local 2-D c2r.
 // Overwrites grid 1 / the transpose buffers: call it outside a step.
+void fft_c2r_block(Ctx &c, int block);
 void fft_debug_exchange(Ctx &c, int which, int reps, float *ms) {
   REQUIRE(c.slab && c.p2p, MGP_ERR_STATE, "exchange probe: needs the peer-memory slab path");
   REQUIRE(which == 0 || which >= 3 || c.xf_on, MGP_ERR_STATE, "exchange probe: fused x-transform is off");
@@ -672,6 +686,11 @@ void fft_debug_exchange(Ctx &c, int which, int reps, float *ms) {
         else k_transpose_fwd_p2p<double2><<<gr, bl, 0, c.stream>>>((const double2 *) g, pp, nxb, c.x0, N, NZ, nyl);
         break;
       }
+      case 8: fft_c2r_block(c, 0); break;
+      case 9:
+        if (c.gbytes == 4) CKFFT(cufftExecC2R(c.plan2d_c2r, (cufftComplex *) c.tbuf_a, (cufftReal *) g));
+        else CKFFT(cufftExecZ2D(c.plan2d_c2r, (cufftDoubleComplex *) c.tbuf_a, (cufftDoubleReal *) g));
+        break;
       case 6: exchange_dma(c, c.stream, false, nullptr, 0); break;
       case 7: exchange_dma(c, c.stream, true, g, 0); break;
       default: {

@@ -74,6 +74,12 @@ __host__ __device__ constexpr int tile_lines(int lgn, int cbytes) {
   return (((size_t) tk << lgn) * cbytes > 200 * 1024) ? 0 : tk;
 }
 
+// k-tiles of a line are laid so that the runs of TK values the exchange side moves start on 128-byte lines of the
+// owner's buffer [xl][ky][kz]: row (xl, ky) starts ((ky * NZ) mod A) elements past a line (A = elements per 128 bytes,
+// NY * NZ * xl being a multiple of A), so tile kt of that row covers kz in [kt * TK - off, kt * TK - off + TK)
+__host__ __device__ constexpr int tiles_per_line(int NZ, int TK, int A) { return (NZ + A - 1 + TK - 1) / TK; }
+XF_HD int tile_k0(int ky, int NZ, int kt, int TK, int A) { return kt * TK - (int) (((long long) ky * NZ) & (A - 1)); }
+
 // position p of the decimation-in-frequency output holds frequency digit_rev(p); digit_rev_inv is the inverse map
 template <int LGN> XF_HD int digit_rev(int p) {
   constexpr int NP = plan_npass(LGN);
@@ -247,14 +253,14 @@ template <typename C> XF_HD C peer_load(const C *p) {
 template <int LGN, int TK, typename C>
 XF_HD void phase_load_lines(C *s, const C *__restrict__ in, int NZ, int jl, int k0, int tid, int nthr) {
   constexpr int N = 1 << LGN, tot = TK * N;
-  const C *src = in + ((size_t) jl * NZ + k0) * N;
+  const C *src = in + ((long long) jl * NZ + k0) * N;       // k0 may be negative (first tile of a line): guarded below
   for (int e0 = tid; e0 < tot; e0 += kBatch * nthr) {
     C v[kBatch];
 #pragma unroll
     for (int u = 0; u < kBatch; u++) {
       const int e = e0 + u * nthr;
       v[u] = mk<C>(0, 0);
-      if (e < tot && k0 + (e >> LGN) < NZ) v[u] = src[e];
+      if (e < tot && k0 + (e >> LGN) < NZ && k0 + (e >> LGN) >= 0) v[u] = src[e];
     }
 #pragma unroll
     for (int u = 0; u < kBatch; u++) {
@@ -271,7 +277,7 @@ XF_HD void phase_store_owners(const C *s, const PeerPtrs &out, int lg_nxb, int y
                               int tid, int nthr) {
   constexpr int N = 1 << LGN, tot = TK * N;
   const int k = tid & (TK - 1);
-  if (k0 + k >= NZ) return;
+  if (k0 + k >= NZ || k0 + k < 0) return;
   const size_t col = (size_t) (y0 + jl) * NZ + (k0 + k);
   const size_t xstride = (size_t) NY * NZ;
   for (int e = tid; e < tot; e += nthr) {
@@ -289,8 +295,8 @@ XF_HD void phase_load_owners(C *s, const PeerPtrs &in, int lg_nxb, int y0, int N
                              int nthr) {
   constexpr int N = 1 << LGN, tot = TK * N;
   const int k = tid & (TK - 1);
-  const bool live = k0 + k < NZ;
-  const size_t col = (size_t) (y0 + jl) * NZ + (k0 + k);
+  const bool live = k0 + k < NZ && k0 + k >= 0;
+  const size_t col = (size_t) ((long long) (y0 + jl) * NZ + (k0 + k));
   const size_t xstride = (size_t) NY * NZ;
   for (int e0 = tid; e0 < tot; e0 += kBatch * nthr) {
     C v[kBatch];
@@ -316,10 +322,10 @@ XF_HD void phase_load_owners(C *s, const PeerPtrs &in, int lg_nxb, int y0, int N
 template <int LGN, int TK, typename C>
 XF_HD void phase_store_lines(const C *s, C *__restrict__ out, int NZ, int jl, int k0, int tid, int nthr) {
   constexpr int N = 1 << LGN, tot = TK * N;
-  C *dst = out + ((size_t) jl * NZ + k0) * N;
+  C *dst = out + ((long long) jl * NZ + k0) * N;
   for (int e = tid; e < tot; e += nthr) {
     const int k = e >> LGN, x = e & (N - 1);
-    if (k0 + k < NZ) dst[e] = s[sidx<TK>(x, k)];
+    if (k0 + k < NZ && k0 + k >= 0) dst[e] = s[sidx<TK>(x, k)];
   }
 }
 
@@ -334,9 +340,11 @@ k_xfft_bwd_p2p(const C *__restrict__ in, const __grid_constant__ PeerPtrs out, c
                int y0, int NY, int NZ, int nyl) {
   extern __shared__ __align__(16) unsigned char xf_smem[];
   C *s = reinterpret_cast<C *>(xf_smem);
-  const int ktiles = (NZ + TK - 1) / TK, ntiles = nyl * ktiles;
+  constexpr int A = 128 / (int) sizeof(C);
+  const int ktiles = tiles_per_line(NZ, TK, A), ntiles = nyl * ktiles;
   for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int jl = t / ktiles, k0 = (t - jl * ktiles) * TK;
+    const int jl = t / ktiles, k0 = tile_k0(y0 + jl, NZ, t - jl * ktiles, TK, A);
+    if (k0 >= NZ || k0 + TK <= 0) continue;           // empty tile (the offset moved it off the line)
     phase_load_lines<LGN, TK, C>(s, in, NZ, jl, k0, threadIdx.x, kThreads);
     __syncthreads();
     phase_pass<LGN, 0, +1, false, TK, C>(s, twtab, threadIdx.x, kThreads);
@@ -355,9 +363,11 @@ k_xfft_fwd_p2p(const __grid_constant__ PeerPtrs in, C *__restrict__ out, const C
                int NY, int NZ, int nyl) {
   extern __shared__ __align__(16) unsigned char xf_smem[];
   C *s = reinterpret_cast<C *>(xf_smem);
-  const int ktiles = (NZ + TK - 1) / TK, ntiles = nyl * ktiles;
+  constexpr int A = 128 / (int) sizeof(C);
+  const int ktiles = tiles_per_line(NZ, TK, A), ntiles = nyl * ktiles;
   for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-    const int jl = t / ktiles, k0 = (t - jl * ktiles) * TK;
+    const int jl = t / ktiles, k0 = tile_k0(y0 + jl, NZ, t - jl * ktiles, TK, A);
+    if (k0 >= NZ || k0 + TK <= 0) continue;           // empty tile (the offset moved it off the line)
     phase_load_owners<LGN, TK, C>(s, in, lg_nxb, y0, NY, NZ, jl, k0, threadIdx.x, kThreads);
     __syncthreads();
     // the transposed graph runs the passes in reverse order

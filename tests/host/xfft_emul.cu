@@ -35,7 +35,8 @@ static int run_case(int P, int NY, int NZ, int nthr, double tol) {
   int lgx = 0; while ((1 << lgx) < nxb) lgx++;
   std::vector<C> tw = twiddles<C, LGN>();
   std::vector<C> smem((size_t) TK * N);
-  const int ktiles = (NZ + TK - 1) / TK;
+  constexpr int A = 128 / (int) sizeof(C);
+  const int ktiles = tiles_per_line(NZ, TK, A);
   int bad = 0;
   // ---------------- backward: transposed k-space lines -> owners of x, sign +
   {
@@ -49,7 +50,8 @@ static int run_case(int P, int NY, int NZ, int nthr, double tol) {
     for (int r = 0; r < 16; r++) pp.p[r] = r < P ? land[r].data() : nullptr;
     for (int r = 0; r < P; r++)
       for (int t = 0; t < nyl * ktiles; t++) {
-        const int jl = t / ktiles, k0 = (t - jl * ktiles) * TK;
+        const int jl = t / ktiles, k0 = tile_k0(r * nyl + jl, NZ, t - jl * ktiles, TK, A);
+        if (k0 >= NZ || k0 + TK <= 0) continue;
         for (int tid = 0; tid < nthr; tid++) phase_load_lines<LGN, TK, C>(smem.data(), lines[r].data(), NZ, jl, k0, tid, nthr);
         for (int tid = 0; tid < nthr; tid++) phase_pass<LGN, 0, +1, false, TK, C>(smem.data(), tw.data(), tid, nthr);
         if constexpr (plan_npass(LGN) > 1)
@@ -94,7 +96,8 @@ static int run_case(int P, int NY, int NZ, int nthr, double tol) {
     for (int r = 0; r < 16; r++) pp.p[r] = r < P ? src[r].data() : nullptr;
     for (int r = 0; r < P; r++)
       for (int t = 0; t < nyl * ktiles; t++) {
-        const int jl = t / ktiles, k0 = (t - jl * ktiles) * TK;
+        const int jl = t / ktiles, k0 = tile_k0(r * nyl + jl, NZ, t - jl * ktiles, TK, A);
+        if (k0 >= NZ || k0 + TK <= 0) continue;
         for (int tid = 0; tid < nthr; tid++) phase_load_owners<LGN, TK, C>(smem.data(), pp, lgx, r * nyl, NY, NZ, jl, k0, tid, nthr);
         if constexpr (plan_npass(LGN) > 2)
           for (int tid = 0; tid < nthr; tid++) phase_pass<LGN, 2, -1, true, TK, C>(smem.data(), tw.data(), tid, nthr);

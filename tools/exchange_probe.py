@@ -25,8 +25,11 @@ slab = N * N * (N // 2 + 1) * 2 * gb / world            # complex bytes of one r
 remote = slab * (world - 1) / world
 names = ["flag barrier", "fused bwd (x-FFT + push)", "fused fwd (pull + x-FFT)", "transpose bwd (push)", "transpose fwd (push)",
          "copy-engine peer copy of the remote share", "DMA exchange bwd (strided blocks to every peer)",
-         "DMA exchange fwd (strided blocks to every peer)"]
+         "DMA exchange fwd (strided blocks to every peer)", "batched c2r of the 3 force grids (pipeline)", "one local 2-D c2r"]
+only = [int(x) for x in os.environ.get('PROBE_ONLY', '').split(',') if x]
 for which, nm in enumerate(names):
+    if only and which not in only:
+        continue
     try:
         pm.debug_time_exchange(which, 2)
         ms = pm.debug_time_exchange(which, 6)
