@@ -199,7 +199,14 @@ static void xfft_setup(Ctx &c) {
   if (!c.p2p || (env && atoi(env) == 0)) return;
   int lgn = 0;
   while ((1 << lgn) < c.N) lgn++;
-  if ((1 << lgn) != c.N || lgn < xf::kMinLgN || lgn > xf::kMaxLgN) return;
+  if ((1 << lgn) != c.N) {
+    // mesh sizes with factors 3 and 5 (the 2- and 4-GPU weak-scaling meshes 320 and 400): mixed-radix instances,
+    // opt-in until they have been timed on a GPU
+    const char *mx = getenv("MGP_XFFT_MIXED");
+    if (mx && atoi(mx) != 0 && xfm_supported(c.N) && xfm_prepare(c)) { c.xf_mixed = true; c.xf_on = true; }
+    return;
+  }
+  if (lgn < xf::kMinLgN || lgn > xf::kMaxLgN) return;
   int lgx = 0;
   while ((1 << lgx) < c.nx) lgx++;
   if ((1 << lgx) != c.nx || c.nx * c.P != c.N) return;
@@ -281,6 +288,7 @@ static void xfft_bwd(Ctx &c, const void *in, int slot, cudaStream_t st) {
     else pp.p[r] = c.peer_tbuf[r] ? (char *) c.peer_tbuf[r] + (size_t) slot * c.grid_bytes() : nullptr;
   }
   const int y0 = c.xf_dma ? 0 : c.y0, NY = c.xf_dma ? c.ny_loc : c.N;
+  if (c.xf_mixed) { xfm_bwd(c, in, pp, y0, NY, st); c.launches++; return; }
 #define OP(L)                                                                                                   \
   xf::k_xfft_bwd_p2p<C, L, xf::tile_lines(L, sizeof(C)) ? xf::tile_lines(L, sizeof(C)) : 4>                      \
       <<<c.xf_grid, xf::kThreads, c.xf_smem, st>>>((const C *) in, pp, (const C *) c.xf_tw, c.xf_lgnxb, y0, NY, c.NZ, c.ny_loc)
@@ -300,6 +308,7 @@ static void xfft_fwd(Ctx &c, void *out, cudaStream_t st) {
     else pp.p[r] = c.peer_tbuf[r];
   }
   const int y0 = c.xf_dma ? 0 : c.y0, NY = c.xf_dma ? c.ny_loc : c.N;
+  if (c.xf_mixed) { xfm_fwd(c, out, pp, y0, NY, st); c.launches++; return; }
 #define OP(L)                                                                                                   \
   xf::k_xfft_fwd_p2p<C, L, xf::tile_lines(L, sizeof(C)) ? xf::tile_lines(L, sizeof(C)) : 4>                      \
       <<<c.xf_grid, xf::kThreads, c.xf_smem, st>>>(pp, (C *) out, (const C *) c.xf_tw, c.xf_lgnxb, y0, NY, c.NZ, c.ny_loc)
