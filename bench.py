@@ -73,33 +73,66 @@ def amplitude_table(nmesh, box):
 # ------------------------------------------------------------------ clocks
 
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons DURING the timed region: NVML polled every 10 ms (a timed region of ten 4 ms steps
+    gets a handful of samples); `nvidia-smi` every 200 ms when NVML cannot be initialised."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
     def __init__(self, device=0, period=0.2):
         super().__init__(daemon=True)
         self.device, self.period, self.stop_flag = device, period, False
         self.sm, self.reasons, self.sm_max = [], set(), None
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(device)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.masks = [(pynvml.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"),
+                          (pynvml.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                          (pynvml.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"),
+                          (pynvml.nvmlClocksEventReasonSwPowerCap, "sw_power_cap")]
+            self.nvml = pynvml
+            self.period = 0.01
+        except Exception:
+            self.nvml = None
 
-    def run(self):
+    def _sample_nvml(self):
+        n = self.nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        bits = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        for mask, nm in self.masks:
+            if bits & int(mask):
+                self.reasons.add(nm)
+
+    def _sample_smi(self):
         q = "clocks.sm,clocks.max.sm,clocks_throttle_reasons.hw_slowdown,clocks_throttle_reasons.hw_thermal_slowdown," \
             "clocks_throttle_reasons.sw_thermal_slowdown,clocks_throttle_reasons.sw_power_cap"
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+        self.sm.append(float(out[0]))
+        self.sm_max = float(out[1])
+        for nm, v in zip(self.NAMES, out[2:]):
+            if "Active" in v and "Not" not in v:
+                self.reasons.add(nm)
+
+    def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.sm.append(float(out[0]))
-                self.sm_max = float(out[1])
-                for nm, v in zip(names, out[2:]):
-                    if "Active" in v and "Not" not in v:
-                        self.reasons.add(nm)
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
-                pass
+                if self.nvml is not None:        # NVML query failed: fall back to nvidia-smi for the rest of the run
+                    self.nvml, self.period = None, 0.2
             time.sleep(self.period)
 
     def result(self):
         self.stop_flag = True
         self.join(timeout=6)
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max,
-                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "source": "nvml, 10 ms period" if self.nvml is not None else "nvidia-smi, 200 ms period"}
 
 
 # ------------------------------------------------------------------ our arm
