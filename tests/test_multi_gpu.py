@@ -50,16 +50,16 @@ def _oracle(nmesh, steps, model):
     return pos, vel, np.stack(pks)
 
 
-# exchange engines of the slab transforms (fft.cu): the default (x-transform kernel fused with pack / unpack + copy-engine
-# blocks over NVLink), the x-transform kernel storing / loading peer memory itself, the cuFFT 1-D plan + transpose kernel
-# over peer memory, and pack / NCCL all-to-all / unpack
-ENGINES = {"dma": {}, "sm": {"MGP_XFFT_DMA": "0"}, "transpose": {"MGP_XFFT": "0"}, "nccl": {"MGP_P2P": "0"}}
+# exchange engines of the slab transforms (fft.cu): the default (x-transform kernel that stores / loads peer memory itself;
+# N = 32 is a power of two), the same kernel around a local staging buffer + copy-engine blocks over NVLink, the cuFFT 1-D
+# plan + transpose kernel over peer memory, and pack / NCCL all-to-all / unpack
+ENGINES = {"fused": {}, "dma": {"MGP_XFFT_DMA": "1"}, "transpose": {"MGP_XFFT": "0"}, "nccl": {"MGP_P2P": "0"}}
+CASES = [(w, "fofr", 8, 0, "fused") for w in (2, 4, 8)] + [(w, "lcdm", 4, 2, "fused") for w in (2, 4, 8)] + \
+        [(w, "dgp", 8, 1, "fused") for w in (2, 4, 8)] + \
+        [(w, "fofr", 8, 0, e) for w in (2, 8) for e in ("dma", "transpose", "nccl")] + [(2, "lcdm", 4, 2, "dma")]
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-@pytest.mark.parametrize("model,gb,mode,engine", [("fofr", 8, 0, "dma"), ("lcdm", 4, 2, "dma"), ("dgp", 8, 1, "dma"),
-                                                  ("fofr", 8, 0, "sm"), ("lcdm", 4, 2, "sm"), ("fofr", 8, 0, "transpose"),
-                                                  ("fofr", 8, 0, "nccl")])
+@pytest.mark.parametrize("world,model,gb,mode,engine", CASES)
 def test_slab_decomposed_steps_match_oracle(require_gpu, tmp_path, world, model, gb, mode, engine):
     if _ngpu() < world:
         pytest.skip("needs %d GPUs" % world)

@@ -26,4 +26,4 @@ for f in sorted(glob.glob("gpurun_out/n8_bench_*.json")):
               {k:v for k,v in d["roofline"]["phases_ms"].items() if k in ("FFT","Comm","MoveParticles","Sort")})
     except Exception as e: print(f, "failed", e)
 PY
-timeout 600 python -m pytest tests/test_multi_gpu.py -x -q -m gpu -k "8]" > gpurun_out/n8_mgpu_tests.log 2>&1; echo "rc=$?" >> gpurun_out/n8_mgpu_tests.log; tail -5 gpurun_out/n8_mgpu_tests.log
+timeout 600 python -m pytest tests/test_multi_gpu.py -x -q -m gpu -k "8-fofr or 8-lcdm or 8-dgp or (matches_reference and 8) or (on_slabs and 8)" > gpurun_out/n8_mgpu_tests.log 2>&1; echo "rc=$?" >> gpurun_out/n8_mgpu_tests.log; tail -5 gpurun_out/n8_mgpu_tests.log
