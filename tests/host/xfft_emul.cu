@@ -34,6 +34,11 @@ static int run_case(int P, int NY, int NZ, int nthr, double tol) {
   const int nxb = N / P, nyl = NY / P;
   int lgx = 0; while ((1 << lgx) < nxb) lgx++;
   std::vector<C> tw = twiddles<C, LGN>();
+  std::vector<long double> CT(N), ST(N);            // the reference DFT's own cos / sin table, long double
+  for (int t = 0; t < N; t++) {
+    const long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double) t / (long double) N;
+    CT[t] = cosl(a); ST[t] = sinl(a);
+  }
   std::vector<C> smem((size_t) TK * N);
   constexpr int A = 128 / (int) sizeof(C);
   const int ktiles = tiles_per_line(NZ, TK, A);
@@ -68,8 +73,7 @@ static int run_case(int P, int NY, int NZ, int nthr, double tol) {
           for (int x = 0; x < N; x++) {
             long double sr = 0, si = 0;
             for (int n = 0; n < N; n++) {
-              const long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double) (((long long) n * x) % N) / N;
-              const long double c = cosl(a), s = sinl(a);
+              const long double c = CT[((long long) n * x) % N], s = ST[((long long) n * x) % N];
               sr += in[n].x * c - in[n].y * s; si += in[n].x * s + in[n].y * c;
             }
             const int o = x / nxb, xl = x % nxb;
@@ -114,8 +118,7 @@ static int run_case(int P, int NY, int NZ, int nthr, double tol) {
             long double sr = 0, si = 0;
             for (int n = 0; n < N; n++) {
               const C v = src[n / nxb][((size_t) (n % nxb) * NY + (r * nyl + jl)) * NZ + k];
-              const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double) (((long long) n * f) % N) / N;
-              const long double c = cosl(a), s = sinl(a);
+              const long double c = CT[((long long) n * f) % N], s = -ST[((long long) n * f) % N];
               sr += v.x * c - v.y * s; si += v.x * s + v.y * c;
             }
             const C got = out[r][((size_t) jl * NZ + k) * N + f];
@@ -167,6 +170,10 @@ int main() {
   CASE_LIB(float2, 9, 4, 4, 9, tf);
   CASE_LIB(float2, 10, 8, 8, 5, tf);
   CASE_LIB(float2, 12, 2, 2, 1, tf);
+  // the dimensions of the 8-GPU runs: Nmesh 512 (NZ = 257) and 1024 (NZ = 513) on 8 ranks, ky = 0 .. 7 (every offset of a
+  // row against the 128-byte lines of the owner's buffer)
+  CASE_LIB(double2, 9, 8, 8, 257, td);
+  CASE_LIB(double2, 10, 8, 8, 513, td);
   // other tile widths and thread counts than the library's
   bad += run_case<double2, 5, 8>(1, 2, 3, 64, td);
   bad += run_case<double2, 6, 4>(2, 2, 5, 96, td);

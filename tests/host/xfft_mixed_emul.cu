@@ -38,6 +38,11 @@ static int run_case(int P, int NY, int NZ, int nthr, double tol) {
   static_assert(supported(N), "unsupported N");
   const int nxb = N / P, nyl = NY / P;
   std::vector<C> tw = twiddles<C, N>();
+  std::vector<long double> CT(N), ST(N);            // the reference DFT's own cos / sin table, long double
+  for (int t = 0; t < N; t++) {
+    const long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double) t / (long double) N;
+    CT[t] = cosl(a); ST[t] = sinl(a);
+  }
   std::vector<C> smem((size_t) TK * N);
   constexpr int A = 128 / (int) sizeof(C);
   const int ktiles = tiles_per_line(NZ, TK, A);
@@ -67,8 +72,7 @@ static int run_case(int P, int NY, int NZ, int nthr, double tol) {
           for (int x = 0; x < N; x++) {
             long double sr = 0, si = 0;
             for (int n = 0; n < N; n++) {
-              const long double a = 2.0L * 3.14159265358979323846264338327950288L * (long double) (((long long) n * x) % N) / N;
-              const long double c = cosl(a), s = sinl(a);
+              const long double c = CT[((long long) n * x) % N], s = ST[((long long) n * x) % N];
               sr += in[n].x * c - in[n].y * s; si += in[n].x * s + in[n].y * c;
             }
             const int o = x / nxb, xl = x % nxb;
@@ -108,8 +112,7 @@ static int run_case(int P, int NY, int NZ, int nthr, double tol) {
             long double sr = 0, si = 0;
             for (int n = 0; n < N; n++) {
               const C v = src[n / nxb][((size_t) (n % nxb) * NY + (r * nyl + jl)) * NZ + k];
-              const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double) (((long long) n * f) % N) / N;
-              const long double c = cosl(a), s = sinl(a);
+              const long double c = CT[((long long) n * f) % N], s = -ST[((long long) n * f) % N];
               sr += v.x * c - v.y * s; si += v.x * s + v.y * c;
             }
             const C got = out[r][((size_t) jl * NZ + k) * N + f];
