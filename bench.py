@@ -11,7 +11,7 @@ reference's COLA schedule (z_init = 9, linear in a).
 
 One JSON line on stdout (rank 0).  `value` = device-timed, particles resident in HBM.  `e2e` = the
 same step driven through the C ABI with HOST particle buffers (pinned): upload of Pos/Vel/D/D2/ID
-and download of Pos/Vel inside the timed region.  `roofline` = the dominant hand-written kernel
+and download of Pos/Vel inside the timed region (on several ranks every rank round-trips its own slab's particles).  `roofline` = the dominant hand-written kernel
 of the step, timed live with CUDA events on the library's stream.  `cpu_baseline` / `--impl
 reference` = the unmodified reference compiled against the oracle stand-ins (oracle/_ref), one core.
 """
@@ -293,6 +293,46 @@ def run_ours(args):
         dt = (time.perf_counter() - t0) / ne2e
         e2e = {"value": npart_total / dt, "unit": "particle-updates/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h + hid.numel() * 8), "ms_per_step": dt * 1e3, "steps": ne2e}
+
+    if world > 1 and not args.no_e2e:
+        # every rank round-trips ITS particles through pinned host buffers sized to the rank's capacity (the count per
+        # rank changes with the migration); wall clock between barriers, max over ranks
+        try:
+            import torch.distributed as dist
+            cap = int(np.ceil(pm.local_np * N * N * 1.5)) + 64
+            got = pm.download_particles()
+            n0 = len(got["id"])
+            keys = ("pos", "vel") if use_sd else ("pos", "vel", "D", "D2")
+            hp = {k: torch.empty((cap, 3), dtype=torch.float32).pin_memory() for k in keys}
+            hid = torch.empty((cap,), dtype=torch.int64).pin_memory()
+            for k in keys:
+                hp[k][:n0] = torch.from_numpy(got[k])
+            hid[:n0] = torch.from_numpy(got["id"].astype(np.int64))
+            del got
+            ne2e = max(2, min(args.steps, 5))
+            nbytes = 0
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(ne2e):
+                n = pm.numpart
+                nbytes += n * (12 * len(keys) + 8)
+                pm.upload_raw(hp["pos"].data_ptr(), hp["vel"].data_ptr(), hp["D"].data_ptr() if "D" in hp else 0,
+                              hp["D2"].data_ptr() if "D2" in hp else 0, hid.data_ptr(), n)
+                st.step()
+                pm.download_raw(hp["pos"].data_ptr(), hp["vel"].data_ptr(), 0, 0, hid.data_ptr())
+            barrier()
+            dt = (time.perf_counter() - t0) / ne2e
+            t = torch.tensor([dt, float(nbytes) / ne2e, float(pm.numpart) * 32.0], device="cuda", dtype=torch.float64)
+            tmax = t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            dt = float(tmax[0].item())
+            e2e = {"value": npart_total / dt, "unit": "particle-updates/s", "h2d_bytes_per_step": int(t[1].item()),
+                   "d2h_bytes_per_step": int(t[2].item()), "ms_per_step": dt * 1e3, "steps": ne2e,
+                   "note": "every rank uploads / downloads its own slab's particles (all ranks, summed bytes); max over ranks"}
+        except Exception as exc:       # the device-timed numbers above stand; say why there is no end-to-end one
+            e2e = None
+            sys.stderr.write("e2e on %d ranks failed: %r\n" % (world, exc))
 
     if rank != 0:
         pm.close()
