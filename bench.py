@@ -73,8 +73,9 @@ def amplitude_table(nmesh, box):
 # ------------------------------------------------------------------ clocks
 
 class ClockSampler(threading.Thread):
-    """SM clock and throttle reasons DURING the timed region: NVML polled every 10 ms (a timed region of ten 4 ms steps
-    gets a handful of samples); `nvidia-smi` every 200 ms when NVML cannot be initialised."""
+    """SM clock and throttle reasons DURING the timed region: NVML polled every 50 ms (rare enough not to disturb the
+    launches of a 4 ms step, which has two host synchronisations); `nvidia-smi` every 200 ms when NVML cannot be
+    initialised."""
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, device=0, period=0.2):
@@ -92,7 +93,7 @@ class ClockSampler(threading.Thread):
                           (pynvml.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"),
                           (pynvml.nvmlClocksEventReasonSwPowerCap, "sw_power_cap")]
             self.nvml = pynvml
-            self.period = 0.01
+            self.period = 0.05
         except Exception:
             self.nvml = None
 
@@ -132,7 +133,7 @@ class ClockSampler(threading.Thread):
         self.join(timeout=6)
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max,
                 "reasons": sorted(self.reasons), "samples": len(self.sm),
-                "source": "nvml, 10 ms period" if self.nvml is not None else "nvidia-smi, 200 ms period"}
+                "source": "nvml, 50 ms period" if self.nvml is not None else "nvidia-smi, 200 ms period"}
 
 
 # ------------------------------------------------------------------ our arm
