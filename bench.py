@@ -460,16 +460,75 @@ pofk_kmax 2.0
     return p
 
 
+def _ref_variant(args):
+    use_sd = args.scale_dependent if args.scale_dependent >= 0 else int(args.model in ("fofr", "dgp"))
+    if use_sd:
+        return use_sd, {"fofr": "fofr", "dgp": "dgp_sd", "lcdm": "fofr"}[args.model]     # MODEL=FOFR / DGP -DSCALEDEPENDENT
+    return use_sd, ("dgp" if args.model == "dgp" else "lcdm")  # 'lcdm' = -DFOFRGRAVITY without SCALEDEPENDENT (MODEL=FOFR_LCDM)
+
+
+def cpu_reference_ranks(args, sample_nmesh):
+    """The reference as the multi-rank program it is: its unmodified driver (main.c) on K ranks = K processes of the
+    multi-process MPI stand-in (oracle/shim/shim_mpi_mp.c, started by oracle/mprun.py; bit-identical to the one-rank
+    run in double precision, tests/test_ref_multirank.py).  Time per step = difference of the reference's own
+    "TimeStepping" timer (timer.c) between a 6-step and a 2-step run, which cancels the set-up and the extra force
+    evaluation of an output interval.  None when it cannot run here."""
+    import re
+    import tempfile
+    from oracle import mprun
+    use_sd, variant = _ref_variant(args)
+    if not mprun.available(variant):
+        return None
+    N = sample_nmesh
+    logical = os.cpu_count() or 1
+    K = 1
+    while K * 2 <= min(max(logical // 2, 2), N // 4, 32):          # half the logical CPUs (SMT), a power of two dividing Nmesh
+        K *= 2
+    if K < 2:
+        return None
+    nm_full = args.nmesh if args.nmesh else WEAK_NMESH.get(args.gpus, 256)
+    box = box_for(nm_full) * N / nm_full
+    tt = {}
+    for nsteps in (2, 6):
+        wd = tempfile.mkdtemp(prefix="mgp_refmp_")
+        pf = write_paramfile(wd, N, box, args.model, nsteps, lcdm_growth=0 if use_sd else 1)
+        rc, out, errs = mprun.run([mprun.exe_path(variant), pf], K, scratch_mb=mprun.scratch_mb_for(N), timeout=900)
+        m = re.search(r"TimeStepping\s+([0-9.]+)", out or "")
+        if rc != 0 or not m:
+            sys.stderr.write("multi-rank reference run failed (rc %s): %s\n" % (rc, " | ".join(e[-200:] for e in errs if e.strip())))
+            return None
+        tt[nsteps] = float(m.group(1))
+    dt = (tt[6] - tt[2]) / 4.0
+    if not dt > 0:
+        return None
+    return {"value": N ** 3 / dt, "unit": "particle-updates/s", "cores": K, "kind": "reference", "ms_per_step": dt * 1e3,
+            "sample": "the unmodified reference driver (variant %s%s) on %d ranks of a multi-process MPI stand-in (no MPI / FFTW / GSL on "
+                      "the box: shared-memory MPI, CPU FFT and mini-GSL stand-ins), %s workload at Npart=Nmesh=%d^3 (Box=%g); per-step time = "
+                      "(TimeStepping of a 6-step run - TimeStepping of a 2-step run) / 4 from the reference's own timer; %d logical CPUs on the host"
+                      % (variant, ", SCALEDEPENDENT: 12 extra c2r + 4 field assignments per step" if use_sd else "", K, args.model, N, box, logical)}
+
+
 def cpu_reference(args, sample_nmesh, steps, warmup):
+    """The reference's CPU path on the box's host cores: on several ranks when the multi-process MPI stand-in can run
+    (cpu_reference_ranks), plus -- always -- the one-rank run stepped through its own GetDisplacements / Kick / Drift."""
+    one = cpu_reference_one(args, sample_nmesh, steps, warmup)
+    try:
+        many = None if os.environ.get("MGP_BENCH_REF_RANKS", "1") == "0" else cpu_reference_ranks(args, sample_nmesh)
+    except Exception as exc:
+        sys.stderr.write("multi-rank reference run failed: %r\n" % (exc,))
+        many = None
+    if many is None or one.get("value") is None or many["value"] <= one["value"]:
+        return one                                   # no ranks to be had (or no faster): the one-core figure stands
+    many["one_core"] = {"value": one["value"], "ms_per_step": one.get("ms_per_step")}
+    return many
+
+
+def cpu_reference_one(args, sample_nmesh, steps, warmup):
     """Times the unmodified reference (oracle/_ref, built by oracle/Makefile) stepping the same
     workload on one host core: its own GetDisplacements / Kick / Drift, wall clock per step."""
     import tempfile
     from oracle import ref_lib
-    use_sd = args.scale_dependent if args.scale_dependent >= 0 else int(args.model in ("fofr", "dgp"))
-    if use_sd:
-        variant = {"fofr": "fofr", "dgp": "dgp_sd", "lcdm": "fofr"}[args.model]     # MODEL=FOFR / DGP -DSCALEDEPENDENT
-    else:
-        variant = "dgp" if args.model == "dgp" else "lcdm"  # 'lcdm' = -DFOFRGRAVITY without SCALEDEPENDENT (MODEL=FOFR_LCDM)
+    use_sd, variant = _ref_variant(args)
     if not ref_lib.available(variant):
         return {"value": None, "unit": "particle-updates/s", "cores": 1, "kind": "reference",
                 "sample": "oracle/_ref not built (needs /root/reference at build time)"}
