@@ -460,6 +460,21 @@ pofk_kmax 2.0
     return p
 
 
+def usable_cpus():
+    """Logical CPUs this process may actually use: the affinity mask, capped by the cgroup CPU quota."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return n
+
+
 def _ref_variant(args):
     use_sd = args.scale_dependent if args.scale_dependent >= 0 else int(args.model in ("fofr", "dgp"))
     if use_sd:
@@ -480,11 +495,11 @@ def cpu_reference_ranks(args, sample_nmesh):
     if not mprun.available(variant):
         return None
     N = sample_nmesh
-    logical = os.cpu_count() or 1
+    logical = usable_cpus()
     K = 1
-    while K * 2 <= min(max(logical // 2, 2), N // 4, 32):          # half the logical CPUs (SMT), a power of two dividing Nmesh
+    while K * 2 <= min(max(logical // 2, 2), N // 4, 32):          # half the usable logical CPUs (SMT), a power of two dividing Nmesh
         K *= 2
-    if K < 2:
+    if K < 2 or logical < 2:
         return None
     nm_full = args.nmesh if args.nmesh else WEAK_NMESH.get(args.gpus, 256)
     box = box_for(nm_full) * N / nm_full
@@ -492,7 +507,8 @@ def cpu_reference_ranks(args, sample_nmesh):
     for nsteps in (2, 6):
         wd = tempfile.mkdtemp(prefix="mgp_refmp_")
         pf = write_paramfile(wd, N, box, args.model, nsteps, lcdm_growth=0 if use_sd else 1)
-        rc, out, errs = mprun.run([mprun.exe_path(variant), pf], K, scratch_mb=mprun.scratch_mb_for(N), timeout=900)
+        # bounded: a 6-step run at 128^3 takes ~20 s on 4 ranks; a box that cannot give the ranks their cores falls back
+        rc, out, errs = mprun.run([mprun.exe_path(variant), pf], K, scratch_mb=mprun.scratch_mb_for(N), timeout=150)
         m = re.search(r"TimeStepping\s+([0-9.]+)", out or "")
         if rc != 0 or not m:
             sys.stderr.write("multi-rank reference run failed (rc %s): %s\n" % (rc, " | ".join(e[-200:] for e in errs if e.strip())))
