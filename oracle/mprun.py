@@ -24,6 +24,15 @@ def available(variant):
     return os.path.exists(exe_path(variant))
 
 
+def _die_with_parent():
+    """preexec: SIGKILL this rank when the launcher dies (a rank waiting in a barrier would otherwise spin for ever)."""
+    try:
+        import ctypes
+        ctypes.CDLL("libc.so.6").prctl(1, 9)          # PR_SET_PDEATHSIG, SIGKILL
+    except Exception:
+        pass
+
+
 def run(cmd, nranks, slot_mb=64, scratch_mb=64, cwd=None, timeout=3600, env=None, rank_env=None):
     """Runs `cmd` (list) on `nranks` ranks.  Returns (returncode, stdout of rank 0, tail of every rank's stderr).
     scratch_mb must hold one complex half-spectrum of the mesh: Nmesh^2 (Nmesh/2+1) * 16 bytes (double grids)."""
@@ -48,7 +57,7 @@ def run(cmd, nranks, slot_mb=64, scratch_mb=64, cwd=None, timeout=3600, env=None
             e.update(MGPSHIM_RANK=str(r), MGPSHIM_SIZE=str(nranks), MGPSHIM_SHM=shm, MGPSHIM_SLOT_MB=str(slot_mb),
                      MGPSHIM_SCRATCH_MB=str(scratch_mb))
             out = subprocess.PIPE if r == 0 else subprocess.DEVNULL
-            procs.append(subprocess.Popen(cmd, cwd=cwd, env=e, stdout=out, stderr=subprocess.PIPE, text=True))
+            procs.append(subprocess.Popen(cmd, cwd=cwd, env=e, stdout=out, stderr=subprocess.PIPE, text=True, preexec_fn=_die_with_parent))
         t0 = time.time()
         # rank 0's stdout can be large: drain it in this thread while polling the others
         import threading
