@@ -49,7 +49,7 @@ def run(cmd, nranks, slot_mb=64, scratch_mb=64, cwd=None, timeout=3600, env=None
     try:
         os.ftruncate(fd, 8192 + nranks * (slot_mb << 20) + (scratch_mb << 20) + 8192)     # sparse file
         os.close(fd)
-        procs = []
+        procs, errfiles = [], []
         for r in range(nranks):
             e = dict(os.environ, **(env or {}))
             if rank_env is not None:
@@ -57,7 +57,9 @@ def run(cmd, nranks, slot_mb=64, scratch_mb=64, cwd=None, timeout=3600, env=None
             e.update(MGPSHIM_RANK=str(r), MGPSHIM_SIZE=str(nranks), MGPSHIM_SHM=shm, MGPSHIM_SLOT_MB=str(slot_mb),
                      MGPSHIM_SCRATCH_MB=str(scratch_mb))
             out = subprocess.PIPE if r == 0 else subprocess.DEVNULL
-            procs.append(subprocess.Popen(cmd, cwd=cwd, env=e, stdout=out, stderr=subprocess.PIPE, text=True, preexec_fn=_die_with_parent))
+            errf = tempfile.TemporaryFile(mode="w+")          # a file, not a pipe: nobody drains it while the ranks run
+            errfiles.append(errf)
+            procs.append(subprocess.Popen(cmd, cwd=cwd, env=e, stdout=out, stderr=errf, text=True, preexec_fn=_die_with_parent))
         t0 = time.time()
         # rank 0's stdout can be large: drain it in this thread while polling the others
         import threading
@@ -82,9 +84,12 @@ def run(cmd, nranks, slot_mb=64, scratch_mb=64, cwd=None, timeout=3600, env=None
                 p.kill()
         th.join(timeout=5)
         errs = []
-        for p in procs:
+        for p, f in zip(procs, errfiles):
             try:
-                errs.append((p.stderr.read() or "")[-2000:])
+                p.wait(timeout=5)
+                f.seek(0)
+                errs.append(f.read()[-2000:])
+                f.close()
             except Exception:
                 errs.append("")
         return rc, "".join(chunks), errs
