@@ -93,6 +93,7 @@ struct Ctx {
   // x-transform fused with the slab exchange (xfft.cuh): power-of-two Nmesh on the peer-memory path
   bool xf_on = false;
   int xf_lgn = 0, xf_lgnxb = 0;                // log2 Nmesh, log2 Local_nx
+  bool xf_wide = false;                        // wide-tile instances (xfft_wide.cu; opt-in MGP_XFFT_WIDE=1)
   bool xf_mixed = false;                       // Nmesh = 2^a 3^b 5^c instance (xfft_mixed.cu; opt-in MGP_XFFT_MIXED=1)
   void *xf_tw = nullptr;                       // twiddle tables of the passes (complex, grid precision)
   int xf_tk = 0, xf_grid = 0;                  // lines per tile, persistent grid size
@@ -246,6 +247,10 @@ void fft_c2r_forces(Ctx &c);
 void fft_c2r_block(Ctx &c, int block);      // block 0: grids 1, 2, 3; block 1: grids 0, 4, 5 (scale_dependent only)
 void halo_fill_block(Ctx &c, int block);
 void fft_debug_exchange(Ctx &c, int which, int reps, float *ms);
+// xfft_wide.cu
+bool xfw_prepare(Ctx &c);
+void xfw_bwd(Ctx &c, const void *in, const PeerPtrs &pp, int y0, int NY, cudaStream_t st);
+void xfw_fwd(Ctx &c, void *out, const PeerPtrs &pp, int y0, int NY, cudaStream_t st);
 // xfft_mixed.cu
 bool xfm_supported(int n);
 bool xfm_prepare(Ctx &c);

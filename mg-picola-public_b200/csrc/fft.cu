@@ -242,6 +242,10 @@ static void xfft_setup(Ctx &c) {
     CK(cudaMemcpy(c.xf_tw, tw.data(), (size_t) total * cb, cudaMemcpyHostToDevice));
   }
   c.xf_on = true;
+  {
+    const char *w = getenv("MGP_XFFT_WIDE");       // wide tiles (twice the run length on the exchange side), opt-in
+    if (w && atoi(w) != 0 && xfw_prepare(c)) c.xf_wide = true;
+  }
 }
 
 // staging slot `slot` (0..2) of rank r: the second half of its transpose buffer
@@ -289,6 +293,7 @@ static void xfft_bwd(Ctx &c, const void *in, int slot, cudaStream_t st) {
   }
   const int y0 = c.xf_dma ? 0 : c.y0, NY = c.xf_dma ? c.ny_loc : c.N;
   if (c.xf_mixed) { xfm_bwd(c, in, pp, y0, NY, st); c.launches++; return; }
+  if (c.xf_wide) { xfw_bwd(c, in, pp, y0, NY, st); c.launches++; return; }
 #define OP(L)                                                                                                   \
   xf::k_xfft_bwd_p2p<C, L, xf::tile_lines(L, sizeof(C)) ? xf::tile_lines(L, sizeof(C)) : 4>                      \
       <<<c.xf_grid, xf::kThreads, c.xf_smem, st>>>((const C *) in, pp, (const C *) c.xf_tw, c.xf_lgnxb, y0, NY, c.NZ, c.ny_loc)
@@ -309,6 +314,7 @@ static void xfft_fwd(Ctx &c, void *out, cudaStream_t st) {
   }
   const int y0 = c.xf_dma ? 0 : c.y0, NY = c.xf_dma ? c.ny_loc : c.N;
   if (c.xf_mixed) { xfm_fwd(c, out, pp, y0, NY, st); c.launches++; return; }
+  if (c.xf_wide) { xfw_fwd(c, out, pp, y0, NY, st); c.launches++; return; }
 #define OP(L)                                                                                                   \
   xf::k_xfft_fwd_p2p<C, L, xf::tile_lines(L, sizeof(C)) ? xf::tile_lines(L, sizeof(C)) : 4>                      \
       <<<c.xf_grid, xf::kThreads, c.xf_smem, st>>>(pp, (C *) out, (const C *) c.xf_tw, c.xf_lgnxb, y0, NY, c.NZ, c.ny_loc)

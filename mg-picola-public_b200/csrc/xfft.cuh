@@ -74,6 +74,14 @@ __host__ __device__ constexpr int tile_lines(int lgn, int cbytes) {
   return (((size_t) tk << lgn) * cbytes > 200 * 1024) ? 0 : tk;
 }
 
+// wide tiles for the one-CTA-per-SM configuration of multi-rank runs (at most 128 KB): twice the run length on the
+// exchange side (256 bytes at Nmesh 512, 128 at 1024 in double).  Opt-in (MGP_XFFT_WIDE=1, xfft_wide.cu).
+__host__ __device__ constexpr int tile_lines_wide(int lgn, int cbytes) {
+  int tk = 32;
+  while (tk > 4 && ((size_t) tk << lgn) * cbytes > 128 * 1024) tk >>= 1;
+  return (((size_t) tk << lgn) * cbytes > 200 * 1024) ? 0 : tk;
+}
+
 // k-tiles of a line are laid so that the runs of TK values the exchange side moves start on 128-byte lines of the
 // owner's buffer [xl][ky][kz]: row (xl, ky) starts ((ky * NZ) mod A) elements past a line (A = elements per 128 bytes,
 // NY * NZ * xl being a multiple of A), so tile kt of that row covers kz in [kt * TK - off, kt * TK - off + TK)

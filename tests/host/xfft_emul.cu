@@ -174,6 +174,11 @@ int main() {
   // row against the 128-byte lines of the owner's buffer)
   CASE_LIB(double2, 9, 8, 8, 257, td);
   CASE_LIB(double2, 10, 8, 8, 513, td);
+  // the wide-tile instances (xfft_wide.cu)
+  bad += run_case<double2, 8, tile_lines_wide(8, 16)>(2, 2, 129, 256, td);
+  bad += run_case<double2, 9, tile_lines_wide(9, 16)>(8, 8, 17, 256, td);
+  bad += run_case<double2, 10, tile_lines_wide(10, 16)>(4, 4, 9, 256, td);
+  bad += run_case<float2, 9, tile_lines_wide(9, 8)>(2, 2, 33, 256, tf);
   // other tile widths and thread counts than the library's
   bad += run_case<double2, 5, 8>(1, 2, 3, 64, td);
   bad += run_case<double2, 6, 4>(2, 2, 5, 96, td);

@@ -10,7 +10,11 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 
 for N in 512 1024; do
   PROBE_ONLY=0,1,2,3,4,8,9 timeout 120 $TR tools/exchange_probe.py $N 8 2>&1 | grep -E "N=|rror"
 done | tee gpurun_out/n8_exchange.txt
+for N in 512 1024; do
+  MGP_XFFT_WIDE=1 PROBE_ONLY=1,2,8 timeout 120 $TR tools/exchange_probe.py $N 8 2>&1 | grep -E "N=|rror"
+done | tee gpurun_out/n8_exchange_wide.txt
 B="bench.py --gpus 8 --steps 5 --warmup 3 --no-e2e --no-cpu-baseline"
+MGP_XFFT_WIDE=1 timeout 120 $TR $B --nmesh 512 > gpurun_out/n8_bench_512_wide.json 2> gpurun_out/n8_bench_512_wide.err
 for v in "1 0 1" "1 0 2" "0 0 1" "1 1 1"; do set -- $v
   MGP_XFFT=$1 MGP_XFFT_DMA=$2 MGP_XFFT_CPS=$3 timeout 120 $TR $B --nmesh 512 > gpurun_out/n8_bench_512_xf$1_dma$2_cps$3.json 2> gpurun_out/n8_bench_512_xf$1_dma$2_cps$3.err
 done
