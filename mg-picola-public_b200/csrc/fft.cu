@@ -676,6 +676,7 @@ void fft_c2r_block(Ctx &c, int block);
 void fft_debug_exchange(Ctx &c, int which, int reps, float *ms) {
   REQUIRE(c.slab && c.p2p, MGP_ERR_STATE, "exchange probe: needs the peer-memory slab path");
   REQUIRE(which == 0 || which >= 3 || c.xf_on, MGP_ERR_STATE, "exchange probe: fused x-transform is off");
+  REQUIRE((which != 6 && which != 7) || c.xf_dma, MGP_ERR_STATE, "exchange probe: the staging slots exist only with MGP_XFFT_DMA=1");
   const int N = c.N, NZ = c.NZ, nxb = c.nx, nyl = c.ny_loc;
   void *g = c.grid[1];
   PeerPtrs pp;
