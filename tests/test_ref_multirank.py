@@ -54,3 +54,26 @@ def test_ranks_reproduce_the_one_rank_run(tmp_path, variant, model, lcdm_growth,
         for r, (p, _, _) in enumerate(parts):                                   # slab ownership after the final MoveParticles
             slab = (p[:, 0].astype(np.float64) * N / box).astype(np.int64)
             assert ((slab // (N // K)) == r).all()
+
+
+def test_uneven_slabs_match_the_library_slab_rule(tmp_path):
+    """16 planes on 3 ranks (6 + 6 + 4, the FFTW-MPI block distribution): what each rank of the reference actually holds
+    after its MoveParticles is what the library's host-side slab helpers say (mg-picola-public_b200/slab.py, the rule
+    mgp_create and the migration kernels implement), and the run reproduces the one-rank run bit for bit."""
+    if not mprun.available("lcdm"):
+        pytest.skip("oracle/_ref/*_mp not built (needs /root/reference at build time)")
+    from mgpicola_b200 import slab
+    N, box, K = 16, 100.0, 3
+    one, pk1 = _run(tmp_path, "lcdm", "fofr", 1, N, 3, 1)
+    parts, pk = _run(tmp_path, "lcdm", "fofr", K, N, 3, 1)
+    assert pk == pk1
+    ids = np.concatenate([p[2] for p in parts])
+    pos = np.concatenate([p[0] for p in parts])
+    o, o1 = np.argsort(ids), np.argsort(one[0][2])
+    assert np.array_equal(pos[o].view(np.uint32), one[0][0][o1].view(np.uint32))
+    for r, (p, _, _) in enumerate(parts):
+        nx, x0, _, _ = slab.layout(N, N, K, r)
+        planes = (p[:, 0].astype(np.float64) * N / box).astype(np.int64)
+        assert planes.min() >= x0 and planes.max() < x0 + nx
+        assert (slab.owner_of(p[:, 0], N, box, K) == r).all()
+    assert [slab.layout(N, N, K, r)[:2] for r in range(K)] == [(6, 0), (6, 6), (4, 12)]
