@@ -97,3 +97,31 @@ def test_single_gpu_suite_on_the_slab_path(require_gpu, xfft, dma, select):
         cmd += ["-k", select]
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("N,gb,knob", [(320, 8, "MGP_XFFT_MIXED"), (400, 8, "MGP_XFFT_MIXED"), (320, 4, "MGP_XFFT_MIXED"),
+                                       (128, 8, "MGP_XFFT_WIDE"), (256, 8, "MGP_XFFT_WIDE"), (256, 4, "MGP_XFFT_WIDE")])
+def test_experimental_instances_match_numpy(mgp, require_gpu, monkeypatch, N, gb, knob):
+    """The mixed-radix (Nmesh = 320, 400) and wide-tile instances of the fused kernel: host-emulated
+    (tests/test_xfft_host.py), first GPU run pending -- opt-in with MGP_TEST_EXPERIMENTAL=1 until then."""
+    if os.environ.get("MGP_TEST_EXPERIMENTAL", "0") != "1":
+        pytest.skip("first GPU run pending: set MGP_TEST_EXPERIMENTAL=1")
+    monkeypatch.setenv("MGP_FORCE_SLAB", "1")
+    monkeypatch.setenv("MGP_XFFT", "1")
+    monkeypatch.setenv("MGP_XFFT_DMA", "0")
+    monkeypatch.setenv(knob, "1")
+    pm = mgp.PM(N, N, 100.0, grid_bytes=gb)
+    rng = np.random.default_rng(N + gb)
+    tol = 2e-13 if gb == 8 else 2e-5
+    x = rng.standard_normal((N, N, N))
+    g = np.zeros((N + 1, N, 2 * (N // 2 + 1)), pm.gdtype)
+    g[:N, :, :N] = x
+    pm.upload_grid(mgp.GRID_DENSITY, g)
+    pm.fft_r2c(mgp.GRID_DENSITY)
+    k = pm.download_grid_k(mgp.GRID_DENSITY)
+    ref = np.fft.rfftn(x.astype(pm.gdtype).astype(np.float64))
+    assert np.abs(k - ref).max() / np.abs(ref).max() < tol
+    pm.fft_c2r(mgp.GRID_DENSITY)
+    r = pm.download_grid(mgp.GRID_DENSITY)[:N, :, :N]
+    assert np.abs(r / float(N) ** 3 - x).max() / np.abs(x).max() < tol
+    pm.close()

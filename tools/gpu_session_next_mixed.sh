@@ -4,6 +4,7 @@
 #   2. two ranks: exchange pieces, whole-step bench with and without it
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
+MGP_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_slab_fused.py -x -q -m gpu -k experimental 2>&1 | tail -5 | tee gpurun_out/mx_experimental_tests.txt
 python - <<'PY' 2>&1 | tee gpurun_out/mx_parity.txt
 import os, sys, numpy as np
 sys.path.insert(0, ".")
