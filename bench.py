@@ -508,7 +508,7 @@ def cpu_reference_ranks(args, sample_nmesh):
         wd = tempfile.mkdtemp(prefix="mgp_refmp_")
         pf = write_paramfile(wd, N, box, args.model, nsteps, lcdm_growth=0 if use_sd else 1)
         # bounded: a 6-step run at 128^3 takes ~20 s on 4 ranks; a box that cannot give the ranks their cores falls back
-        rc, out, errs = mprun.run([mprun.exe_path(variant), pf], K, scratch_mb=mprun.scratch_mb_for(N), timeout=150)
+        rc, out, errs = mprun.run([mprun.exe_path(variant), pf], K, scratch_mb=mprun.scratch_mb_for(N), timeout=90)
         m = re.search(r"TimeStepping\s+([0-9.]+)", out or "")
         if rc != 0 or not m:
             sys.stderr.write("multi-rank reference run failed (rc %s): %s\n" % (rc, " | ".join(e[-200:] for e in errs if e.strip())))
