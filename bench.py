@@ -362,7 +362,8 @@ def run_ours(args):
     own = {k: phases.get(k, 0.0) for k in ("PtoMesh", "MtoParticles", "Forces", "ComputeFifthForce", "Kick", "Drift", "Sort", "Pofk", "SDField", "SDAssign")}
     dom = max(("PtoMesh", "MtoParticles"), key=lambda k: own.get(k, 0.0))
     ach = kern_bytes[dom] / (own[dom] * 1e-3) / 1e9 if own.get(dom) else None
-    kname = {"PtoMesh": ["k_deposit_atomic", "k_deposit_tile", "k_deposit_rowseg"][args.deposit_mode], "MtoParticles": "k_gather"}[dom]
+    kname = {"PtoMesh": ["k_deposit_atomic", "k_deposit_tile", "k_deposit_rowseg", "k_deposit_scatter"][args.deposit_mode],
+             "MtoParticles": "k_gather_rows" if args.deposit_mode == 3 else "k_gather"}[dom]
     traffic = None          # DRAM bytes per launch of that kernel from the committed ncu --set full capture (same command, 256^3)
     try:
         if N == 256 and world == 1:

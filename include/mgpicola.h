@@ -48,7 +48,10 @@ enum mgp_model {
 enum mgp_deposit_mode {
   MGP_DEPOSIT_ATOMIC = 0,    /* cell-sorted particles, warp-aggregated global reductions */
   MGP_DEPOSIT_TILE = 1,      /* cell-sorted particles, shared-memory tile accumulation */
-  MGP_DEPOSIT_DETERMINISTIC = 2  /* cell-sorted, per-cell ordered gather: bitwise reproducible */
+  MGP_DEPOSIT_DETERMINISTIC = 2, /* cell-sorted, per-cell ordered gather: bitwise reproducible */
+  MGP_DEPOSIT_ROWS = 3       /* per-step row bins (index list, records not moved); one warp owns one target row of a
+                                shared-memory tile, the tile is written by one bulk copy (TMA); MtoParticles reads the
+                                force rows from shared-memory tiles fetched by bulk copies */
 };
 
 enum mgp_grid_id {

@@ -21,7 +21,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmgpicola_cuda.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "mgpicola.h")
 
 MODEL_NONE, MODEL_FOFR, MODEL_DGP, MODEL_GEFF = 0, 1, 2, 3
-DEPOSIT_ATOMIC, DEPOSIT_TILE, DEPOSIT_DETERMINISTIC = 0, 1, 2
+DEPOSIT_ATOMIC, DEPOSIT_TILE, DEPOSIT_DETERMINISTIC, DEPOSIT_ROWS = 0, 1, 2, 3
 GRID_DENSITY, GRID_FORCE_X, GRID_FORCE_Y, GRID_FORCE_Z, GRID_MG_ONE, GRID_MG_TWO, GRID_SD_DELTA1, GRID_SD_DELTA2 = range(8)
 FIELD_D, FIELD_dDdy, FIELD_ddDddy, FIELD_deltaD = range(4)     # proto.h:155-158
 

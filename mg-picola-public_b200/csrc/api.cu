@@ -23,7 +23,7 @@ static Ctx *create(const mgp_config *cfg) {
   REQUIRE(cfg->grid_bytes == 4 || cfg->grid_bytes == 8, MGP_ERR_INVALID, "mgp_create: grid_bytes must be 4 or 8");
   REQUIRE(cfg->nranks >= 1 && cfg->rank >= 0 && cfg->rank < cfg->nranks, MGP_ERR_INVALID, "mgp_create: bad rank/nranks");
   REQUIRE(cfg->model >= MGP_MODEL_NONE && cfg->model <= MGP_MODEL_GEFF, MGP_ERR_INVALID, "mgp_create: unknown model");
-  REQUIRE(cfg->deposit_mode >= 0 && cfg->deposit_mode <= 2, MGP_ERR_INVALID, "mgp_create: unknown deposit_mode");
+  REQUIRE(cfg->deposit_mode >= 0 && cfg->deposit_mode <= 3, MGP_ERR_INVALID, "mgp_create: unknown deposit_mode");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   REQUIRE(e == cudaSuccess && ndev > 0, MGP_ERR_CUDA,
@@ -36,6 +36,10 @@ static Ctx *create(const mgp_config *cfg) {
   try {
     c.cfg = *cfg;
     c.cfg.nccl_unique_id = nullptr;
+    if (const char *dm = getenv("MGP_DEPOSIT_MODE")) {            // developer / test knob: every context uses this strategy
+      const int m = atoi(dm);
+      if (m >= 0 && m <= 3) c.cfg.deposit_mode = m;
+    }
     c.N = cfg->nmesh; c.NZ = cfg->nmesh / 2 + 1;
     c.P = cfg->nranks; c.rank = cfg->rank;
     c.gbytes = cfg->grid_bytes;
@@ -136,7 +140,7 @@ static void destroy(Ctx *cp) {
 // spatial locality, which the Lagrangian / last-sorted order keeps for several steps.
 static void ensure_order(Ctx &c) {
   if (!c.cfg.sort_particles || c.sorted) return;
-  const bool need_exact = c.cfg.deposit_mode != MGP_DEPOSIT_ATOMIC;
+  const bool need_exact = c.cfg.deposit_mode == MGP_DEPOSIT_TILE || c.cfg.deposit_mode == MGP_DEPOSIT_DETERMINISTIC;
   if (need_exact || c.drifts_since_sort >= c.cfg.sort_particles) particles_sort(c);
 }
 
@@ -153,6 +157,7 @@ static void move_particles(Ctx &c) {
 static void ptomesh(Ctx &c, const mgp_step_scalars *s) {
   if (c.cfg.scale_dependent) sd_drop(c);
   ensure_order(c);
+  if (c.cfg.deposit_mode == MGP_DEPOSIT_ROWS) rows_bin(c);   // the per-step row bins (timed as Sort, not as PtoMesh)
   if (needs_mg_arrays(c) && !c.slab) {
     // CopyDensityArray (mg.h:381) without the copy: deposit straight into mgarray_two and transform
     // out of place into P3D, which leaves delta(x) in mgarray_two exactly as the reference has it
@@ -455,6 +460,7 @@ int mgp_mtoparticles(mgp_ctx *ctx, double sumDxyz[3]) {
   REQUIRE(sumDxyz != nullptr, MGP_ERR_INVALID, "mgp_mtoparticles: sumDxyz is NULL");
   gather_forces(c, sumDxyz);
   c.forces_live = false;
+  rows_prefill(c, needs_mg_arrays(c) && !c.slab ? MGP_GRID_MG_TWO : MGP_GRID_DENSITY);
   API_END
 }
 

@@ -127,6 +127,15 @@ struct Ctx {
   uint32_t *key[2] = {nullptr, nullptr};
   uint32_t *perm[2] = {nullptr, nullptr};
   uint32_t *row_start = nullptr;   // (nx*N + 1) offsets into the sorted particle list
+  // per-step bins (rows.cu): particle indices grouped by the (x-plane, y-row, z-chunk) of their cell; the records stay where they are
+  uint32_t *bin_perm = nullptr;    // [cap]
+  uint32_t *bin_start = nullptr;   // [nbins + 2] offsets into bin_perm; bin = (x-plane, y-row, z-chunk)
+  int bin_zc = 0, bin_nc = 1;      // cells per z-chunk, chunks per row
+  size_t nbins = 0;
+  int prefilled_grid = -1;
+  void *bin_scan_temp = nullptr;
+  size_t bin_scan_bytes = 0;
+  bool bins_valid = false;         // bins describe the current positions and storage order
   void *cub_temp = nullptr;
   size_t cub_temp_bytes = 0;
   int key_zshift = 0;         // cell key drops this many low z bits (0 = full cell sort)
@@ -237,6 +246,15 @@ void particles_after_drift(Ctx &c);
 void deposit_density(Ctx &c, int grid_id);
 void gather_forces(Ctx &c, double sumD[3]);
 void deposit_rsd(Ctx &c, int grid_id, int axis, double vnorm, double dDdy, double dD2dy);
+// rows.cu
+void rows_alloc(Ctx &c);
+void rows_free(Ctx &c);
+void rows_bin(Ctx &c);
+void rows_prefill(Ctx &c, int grid_id);
+void deposit_rows(Ctx &c, int grid_id);
+bool deposit_rows_supported(const Ctx &c);
+bool gather_rows_supported(const Ctx &c);
+unsigned gather_rows(Ctx &c);       // returns the number of per-block partial sums left in c.d_red
 // fft.cu
 void fft_setup(Ctx &c);
 void fft_teardown(Ctx &c);

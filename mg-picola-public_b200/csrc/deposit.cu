@@ -16,28 +16,12 @@
 //     2 x (TY+1) rows, warp-aggregated shared atomics, one global reduction per touched tile value.
 //   ATOMIC (MGP_DEPOSIT_ATOMIC): one thread per particle, warp-aggregated global reductions.
 #include "common.cuh"
+#include "cic.cuh"
 #include "reduce.cuh"
 
 namespace mgp {
 
 // ------------------------------------------------------------------ helpers
-
-struct Cic {
-  unsigned ix, iy, iz;     // cell (y,z wrapped; x global)
-  double dx, dy, dz, tx, ty, tz;
-};
-
-__device__ __forceinline__ Cic cic_of(const float4 p, double scale, unsigned N, double W) {
-  Cic q;
-  const double X = (double) p.x * scale, Y = (double) p.y * scale, Z = (double) p.z * scale;
-  q.ix = (unsigned) X; q.iy = (unsigned) Y; q.iz = (unsigned) Z;
-  q.dx = X - (double) q.ix; q.dy = Y - (double) q.iy; q.dz = Z - (double) q.iz;
-  q.tx = 1.0 - q.dx; q.ty = 1.0 - q.dy; q.tz = 1.0 - q.dz;
-  q.dy *= W; q.ty *= W;
-  if (q.iy >= N) q.iy = 0;
-  if (q.iz >= N) q.iz = 0;
-  return q;
-}
 
 template <typename T>
 __global__ void k_fill(T *g, size_t n, T v) {
@@ -249,6 +233,7 @@ static void deposit_t(Ctx &c, int gid) {
   const double W = r * r * r;     // pow((double)Nmesh/(double)Nsample, 3)
   const int single = c.P == 1;
   int mode = c.cfg.deposit_mode;
+  if (mode == MGP_DEPOSIT_ROWS) mode = MGP_DEPOSIT_ATOMIC;   // only reached when the row tile does not fit (deposit_density)
   if (!c.sorted) mode = MGP_DEPOSIT_ATOMIC;      // TILE / DETERMINISTIC need row_start of the current order
   if (mode == MGP_DEPOSIT_DETERMINISTIC && !c.exact_cell_order) mode = MGP_DEPOSIT_ATOMIC;
   const size_t n = c.np;
@@ -379,6 +364,7 @@ void deposit_rsd(Ctx &c, int grid_id, int axis, double vnorm, double dDdy, doubl
 }
 
 void deposit_density(Ctx &c, int grid_id) {
+  if (c.cfg.deposit_mode == MGP_DEPOSIT_ROWS && deposit_rows_supported(c)) { deposit_rows(c, grid_id); return; }
   if (c.gbytes == 4) deposit_t<float>(c, grid_id); else deposit_t<double>(c, grid_id);
 }
 
@@ -422,20 +408,25 @@ k_gather(size_t n, const float4 *__restrict__ pA, const T *__restrict__ fx, cons
 }
 
 void gather_forces(Ctx &c, double sumD[3]) {
+  static const bool rows_env = !(getenv("MGP_GATHER_ROWS") && atoi(getenv("MGP_GATHER_ROWS")) == 0);     // developer knob
+  const bool use_rows = rows_env && c.cfg.deposit_mode == MGP_DEPOSIT_ROWS && c.np && gather_rows_supported(c);
+  if (use_rows) rows_bin(c);                       // normally still valid from PtoMesh
   PhaseTimer t(c, PH_MTOP);
   const size_t n = c.np;
-  const unsigned g = grid_for(n, 256, 8);
+  unsigned g = grid_for(n, 256, 8);
   reduce_alloc(c, (size_t) g * 3 + 16);
-  double *res = c.d_red + (size_t) g * 3;
   const double scale = (double) c.N / c.cfg.box;
-  if (c.gbytes == 4)
+  if (use_rows)
+    g = gather_rows(c);
+  else if (c.gbytes == 4)
     k_gather<float><<<g, 256, 0, c.stream>>>(n, c.pA, (const float *) c.grid[1], (const float *) c.grid[2],
                                              (const float *) c.grid[3], c.disp, c.cap, c.N, c.NZ, c.x0, scale, c.d_red);
   else
     k_gather<double><<<g, 256, 0, c.stream>>>(n, c.pA, (const double *) c.grid[1], (const double *) c.grid[2],
                                               (const double *) c.grid[3], c.disp, c.cap, c.N, c.NZ, c.x0, scale, c.d_red);
+  double *res = c.d_red + (size_t) g * 3;
   k_final_reduce<<<1, 256, 0, c.stream>>>(c.d_red, (int) g, 3, 3, 1.0, res);
-  c.launches += 2;
+  c.launches += use_rows ? 1 : 2;
   allreduce_sum(c, res, 3);
   CK(cudaMemcpyAsync(c.h_red, res, 3 * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
   CK(cudaStreamSynchronize(c.stream));

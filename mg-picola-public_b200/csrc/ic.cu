@@ -422,6 +422,7 @@ void ic_init_particles(Ctx &c, double Di, double Di2, double dDdy, double dD2dy)
   CK(cudaStreamSynchronize(c.stream));
   c.np = nloc;
   c.sorted = false;
+  c.bins_valid = false;
   c.drifts_since_sort = 1 << 30;
   c.have_disp = false;
   c.ic_ready = false;      // disp[] / pA2 scratch is reused from here on

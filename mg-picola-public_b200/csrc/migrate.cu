@@ -181,7 +181,7 @@ void particles_migrate(Ctx &c) {
   c.sd_req_valid = false;
   const size_t ntot = n + nrecv, newn = n + nrecv - nsend;
   static const bool compact_env = !(getenv("MGP_COMPACT") && atoi(getenv("MGP_COMPACT")) == 0);
-  const bool exact_needed = c.cfg.deposit_mode != MGP_DEPOSIT_ATOMIC;
+  const bool exact_needed = c.cfg.deposit_mode == MGP_DEPOSIT_TILE || c.cfg.deposit_mode == MGP_DEPOSIT_DETERMINISTIC;
   const bool sort_due = !c.cfg.sort_particles || c.drifts_since_sort >= c.cfg.sort_particles;
   if (compact_env && !exact_needed && !sort_due && c.cfg.sort_particles) {
     // hole compaction: leavers' slots below the new count are refilled from above it
@@ -194,12 +194,14 @@ void particles_migrate(Ctx &c) {
     c.np = newn;
     c.np_after_sort = SIZE_MAX;
     c.sorted = false;
+    c.bins_valid = false;
     return;
   }
   // the leavers are still in place; the sort that follows drops them (ownership is recomputed there)
   c.np = ntot;
   c.np_after_sort = newn;
   c.sorted = false;
+  c.bins_valid = false;
   c.drifts_since_sort = 1 << 30;
 }
 

@@ -47,6 +47,7 @@ void particles_alloc(Ctx &c) {
                                   (int64_t) cap, 0, 32, c.stream);
   CK(cudaMalloc(&c.cub_temp, c.cub_temp_bytes));
   reduce_alloc(c, 8192);
+  rows_alloc(c);
   CK(cudaMalloc(&c.d_flag, 16 * sizeof(int)));
   CK(cudaMallocHost(&c.h_flag, 16 * sizeof(int)));
 
@@ -75,6 +76,7 @@ void particles_free(Ctx &c) {
   cudaFree(c.pA); cudaFree(c.pB); cudaFree(c.pC); cudaFree(c.pE); cudaFree(c.disp);
   cudaFree(c.pA2); cudaFree(c.pB2); cudaFree(c.pC2); cudaFree(c.pE2);
   for (int i = 0; i < 2; i++) { cudaFree(c.key[i]); cudaFree(c.perm[i]); }
+  rows_free(c);
   cudaFree(c.row_start); cudaFree(c.cub_temp); cudaFree(c.bucket_start); cudaFree(c.stage);
   for (int i = 0; i < 2; i++) if (c.stage_ev[i]) cudaEventDestroy(c.stage_ev[i]);
   if (c.copy_stream) cudaStreamDestroy(c.copy_stream);
@@ -168,6 +170,7 @@ void particles_upload(Ctx &c, uint64_t n, const float *pos, const float *vel, co
   CK(cudaEventDestroy(copied));
   c.np = n;
   c.sorted = false;
+  c.bins_valid = false;
   c.drifts_since_sort = 1 << 30;
   c.np_after_sort = SIZE_MAX;
   c.have_disp = false;
@@ -379,6 +382,7 @@ void particles_sort(Ctx &c) {
   }
   if (c.np_after_sort != SIZE_MAX) { c.np = c.np_after_sort; c.np_after_sort = SIZE_MAX; }   // leavers dropped
   c.sorted = true;
+  c.bins_valid = false;    // the records moved
   c.drifts_since_sort = 0;
   c.have_disp = false;   // Disp was in the old order
   c.sd_req_valid = false;                                  // ... and so were the scale-dependent per-particle fields
@@ -483,6 +487,7 @@ void particles_drift(Ctx &c, double dyyy, double dD, double dD2, const double su
 
 void particles_after_drift(Ctx &c) {
   c.sorted = false;
+  c.bins_valid = false;
   if (c.drifts_since_sort < (1 << 30)) c.drifts_since_sort++;
   c.have_disp = false;
 }

@@ -332,6 +332,7 @@ static void sd_ensure_particles(Ctx &c) {
   c.launches++;
   c.np = nloc;
   c.sorted = false;
+  c.bins_valid = false;
   c.drifts_since_sort = 1 << 30;
   c.sd_req_valid = false;
   c.sd_lagrangian_only = true;
@@ -536,6 +537,7 @@ void sd_init_particles(Ctx &c) {
   CK(cudaStreamSynchronize(c.stream));
   c.sd_lagrangian_only = false;
   c.sorted = false;
+  c.bins_valid = false;
   c.drifts_since_sort = 1 << 30;
   c.have_disp = false;
 }

@@ -19,9 +19,16 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
+def _port():
+    """One rendezvous port per pytest-xdist worker: the tiny problems of this file can share the GPUs, so several tests
+    may run at once (pytest -n 4)."""
+    w = os.environ.get("PYTEST_XDIST_WORKER", "gw0")
+    return 29517 + 7 * int("".join(ch for ch in w if ch.isdigit()) or 0)
+
+
 def _run(world, tmp, nmesh, steps, model, gb, mode, extra=(), env=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
-           "--master-port", "29517", os.path.join(ROOT, "tests", "mgpu_worker.py"), "--nmesh", str(nmesh), "--steps", str(steps),
+           "--master-port", str(_port()), os.path.join(ROOT, "tests", "mgpu_worker.py"), "--nmesh", str(nmesh), "--steps", str(steps),
            "--model", model, "--gb", str(gb), "--mode", str(mode), "--out", str(tmp)] + list(extra)
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, **(env or {})))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
