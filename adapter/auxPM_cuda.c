@@ -116,10 +116,17 @@ void initialize_ffts(void) {
 #ifdef SCALEDEPENDENT
   cfg.scale_dependent = 1;
 #endif
-  cfg.rank = ThisTask; cfg.nranks = NTask; cfg.device = 0;
+  cfg.rank = ThisTask; cfg.nranks = NTask;
   {
+    /* one GPU per rank: rank modulo the visible devices unless MGP_DEVICE names one (ranks of one node; with several
+       nodes set MGP_DEVICE to the node-local rank, e.g. from OMPI_COMM_WORLD_LOCAL_RANK) */
+    const int ndev = mgp_device_count();
     const char *e = getenv("MGP_DEVICE");
-    if (e) cfg.device = atoi(e);
+    cfg.device = e ? atoi(e) : (ndev > 0 ? ThisTask % ndev : 0);
+    if (NTask > 1 && Nmesh % NTask != 0) {
+      if (ThisTask == 0) printf("[mgpicola-cuda] NTask = %d does not divide Nmesh = %d: the CUDA library needs equal slabs\n", NTask, Nmesh);
+      MPI_Abort(MPI_COMM_WORLD, 1);
+    }
   }
   static char nccl_id[128];
   if (NTask > 1) {

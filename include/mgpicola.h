@@ -128,6 +128,8 @@ typedef struct mgp_step_scalars {
 
 const char *mgp_last_error(void);
 int mgp_version(void);
+/* CUDA devices visible to this process (0 when there is none): lets a multi-rank driver pick rank % count by default. */
+int mgp_device_count(void);
 /* fills 128 bytes with a fresh ncclUniqueId (rank 0 calls this and broadcasts it) */
 int mgp_nccl_unique_id(void *out128);
 

@@ -68,6 +68,7 @@ def load_library(path=None):
         raise ImportError("libmgpicola_cuda.so not built at %s -- run `python -c 'import __graft_entry__ as g; g.build()'`" % p)
     L = C.CDLL(p)
     L.mgp_last_error.restype = C.c_char_p
+    L.mgp_device_count.restype = C.c_int
     L.mgp_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
     L.mgp_destroy.argtypes = [C.c_void_p]
     L.mgp_nccl_unique_id.argtypes = [C.c_void_p]

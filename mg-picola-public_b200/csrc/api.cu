@@ -15,6 +15,8 @@ static const char *kPhaseNames[PH_COUNT] = {"MoveParticles", "PtoMesh", "FFT", "
 
 static bool needs_mg_arrays(const Ctx &c) { return c.cfg.model == MGP_MODEL_FOFR || c.cfg.model == MGP_MODEL_DGP; }
 
+static void destroy(Ctx *cp);
+
 static Ctx *create(const mgp_config *cfg) {
   REQUIRE(cfg != nullptr, MGP_ERR_INVALID, "mgp_create: cfg is NULL");
   REQUIRE(cfg->nmesh >= 2 && cfg->nmesh % 2 == 0, MGP_ERR_INVALID, "mgp_create: Nmesh must be even and >= 2");
@@ -105,7 +107,7 @@ static Ctx *create(const mgp_config *cfg) {
     fft_setup(c);
     CK(cudaStreamSynchronize(c.stream));
   } catch (...) {
-    delete cp;   // leaks device memory of a half-built context only on a fatal configuration error
+    destroy(cp);   // frees whatever the half-built context holds (every free below tolerates a null handle)
     throw;
   }
   return cp;
@@ -115,7 +117,7 @@ static void destroy(Ctx *cp) {
   if (!cp) return;
   Ctx &c = *cp;
   cudaSetDevice(c.cfg.device);
-  cudaStreamSynchronize(c.stream);
+  if (c.stream) cudaStreamSynchronize(c.stream);
   fft_teardown(c);
   particles_free(c);
   sd_free(c);
@@ -127,8 +129,9 @@ static void destroy(Ctx *cp) {
   cudaFree(c.pofk_bins_d); cudaFree(c.pofk_sinc_d); cudaFree(c.pofk_out_d); cudaFree(c.nu_tab_d);
   if (c.pofk_out_h) cudaFreeHost(c.pofk_out_h);
   if (c.comm) ncclCommDestroy(c.comm);
-  for (int d = 0; d < 4; d++) { cudaEventDestroy(c.ev[d][0]); cudaEventDestroy(c.ev[d][1]); }
-  cudaStreamDestroy(c.stream);
+  for (int d = 0; d < 4; d++) { if (c.ev[d][0]) cudaEventDestroy(c.ev[d][0]); if (c.ev[d][1]) cudaEventDestroy(c.ev[d][1]); }
+  if (c.stream) cudaStreamDestroy(c.stream);
+  cudaGetLastError();      // a teardown of a half-built context may have touched null handles
   delete cp;
 }
 
@@ -279,7 +282,12 @@ static void *grid_ptr(Ctx &c, int id) {
 extern "C" {
 
 const char *mgp_last_error(void) { return g_last_error.c_str(); }
-int mgp_version(void) { return 100; }
+int mgp_version(void) { return 200; }
+
+int mgp_device_count(void) {
+  int n = 0;
+  return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
 
 int mgp_nccl_unique_id(void *out128) {
   API_BEGIN
@@ -352,13 +360,9 @@ int mgp_download_particles(mgp_ctx *ctx, float *pos, float *vel, float *D, float
 int mgp_download_disp(mgp_ctx *ctx, float *disp) {
   API_BEGIN
   CTX(ctx);
+  REQUIRE(disp != nullptr, MGP_ERR_INVALID, "mgp_download_disp: NULL");
   REQUIRE(c.have_disp, MGP_ERR_STATE, "mgp_download_disp: no displacements available");
-  std::vector<float> tmp(c.np);
-  for (int a = 0; a < 3; a++) {
-    CK(cudaMemcpyAsync(tmp.data(), c.disp + (size_t) a * c.cap, c.np * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
-    CK(cudaStreamSynchronize(c.stream));
-    for (size_t i = 0; i < c.np; i++) disp[3 * i + a] = tmp[i];
-  }
+  copy_soa3(c, c.disp, c.np, disp, true);
   API_END
 }
 
@@ -376,17 +380,11 @@ int mgp_ic_download(mgp_ctx *ctx, float *za, float *lpt) {
   CTX(ctx);
   REQUIRE(c.ic_ready, MGP_ERR_STATE, "mgp_ic_download: call mgp_ic_generate first");
   const size_t n = (size_t) c.npl * c.cfg.nsample * c.cfg.nsample;
-  std::vector<float> tmp(n);
   for (int f = 0; f < 2; f++) {
     float *dst = f == 0 ? za : lpt;
     if (!dst) continue;
-    const float *src = f == 0 ? c.disp : (const float *) c.pA2;
-    for (int a = 0; a < 3; a++) {
-      CK(cudaMemcpyAsync(tmp.data(), src + (size_t) a * c.cap, n * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
-      CK(cudaStreamSynchronize(c.stream));
-      const double m = c.ic_means[3 * f + a];
-      for (size_t i = 0; i < n; i++) dst[3 * i + a] = (float) ((double) tmp[i] - m);   // ZA -= sumdis (2LPT.c:1501-1508)
-    }
+    float *src = f == 0 ? c.disp : (float *) c.pA2;
+    copy_soa3(c, src, n, dst, true, &c.ic_means[3 * f]);       // ZA -= sumdis (2LPT.c:1501-1508)
   }
   API_END
 }
@@ -412,12 +410,7 @@ int mgp_upload_disp(mgp_ctx *ctx, const float *disp) {
   API_BEGIN
   CTX(ctx);
   REQUIRE(disp != nullptr, MGP_ERR_INVALID, "mgp_upload_disp: NULL");
-  std::vector<float> tmp(c.np);
-  for (int a = 0; a < 3; a++) {
-    for (size_t i = 0; i < c.np; i++) tmp[i] = disp[3 * i + a];
-    CK(cudaMemcpyAsync(c.disp + (size_t) a * c.cap, tmp.data(), c.np * sizeof(float), cudaMemcpyHostToDevice, c.stream));
-    CK(cudaStreamSynchronize(c.stream));
-  }
+  copy_soa3(c, c.disp, c.np, const_cast<float *>(disp), false);
   c.have_disp = true;
   API_END
 }

@@ -238,6 +238,7 @@ void particles_free(Ctx &c);
 void particles_upload(Ctx &c, uint64_t n, const float *pos, const float *vel, const float *D, const float *D2, const uint64_t *id);
 void particles_download(Ctx &c, float *pos, float *vel, float *D, float *D2, uint64_t *id);
 void particles_sort(Ctx &c);
+void copy_soa3(Ctx &c, float *dev_soa, size_t n, float *host_aos, bool to_host, const double *sub_mean = nullptr);
 void particles_kick(Ctx &c, double A, double dda, double ddD, double ddD2, const double sumD[3], double sumV[3]);
 void particles_drift(Ctx &c, double dyyy, double dD, double dD2, const double sumV[3]);
 void particles_migrate(Ctx &c);

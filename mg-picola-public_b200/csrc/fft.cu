@@ -243,8 +243,12 @@ static void xfft_setup(Ctx &c) {
   }
   c.xf_on = true;
   {
-    const char *w = getenv("MGP_XFFT_WIDE");       // wide tiles (twice the run length on the exchange side), opt-in
-    if (w && atoi(w) != 0 && xfw_prepare(c)) c.xf_wide = true;
+    // wide tiles (128 KB, twice the run length on the exchange side): on 8 GPUs at 1024^3 the fused kernels move 565 GB/s
+    // per direction instead of 374 - 475 (profiles/r02_exchange_8gpu.md) and the step drops from 67.5 to 61.9 ms; default
+    // from Nmesh = 1024 on several ranks, MGP_XFFT_WIDE = 0 / 1 overrides
+    const char *w = getenv("MGP_XFFT_WIDE");
+    const bool want = w ? atoi(w) != 0 : (c.P > 1 && c.N >= 1024);
+    if (want && xfw_prepare(c)) c.xf_wide = true;
   }
 }
 

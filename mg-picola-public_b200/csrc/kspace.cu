@@ -271,30 +271,58 @@ k_pofk(KL L, const typename Cpx<T>::type *__restrict__ dk, const int *__restrict
   __syncthreads();
   typedef typename Cpx<T>::type C;
   const int N = L.N;
-  KLOOP(e, L) {
-    int i, j, k;
-    kl_decode(L, e, i, j, k);
-    const int d0 = i > N / 2 ? N - i : i, d1 = j > N / 2 ? N - j : j, d2 = k;
-    const long long m = (long long) d0 * d0 + (long long) d1 * d1 + (long long) d2 * d2;
-    const int nk = bin_of_m[m];
-    if (nk >= 0 && nk < nbins) {
-      const double gz = (d2 == 0) ? 1.0 : ((2 * d2 == N) ? 2.0 / 3.14159265358979323846 : sinc[d2]);
-      const double gc = sinc[d0] * sinc[d1] * gz;
-      const double g2 = gc * gc;
-      const double corr = 1.0 / (g2 * g2) * norm;          // 1/pow(gx*gy*gz, 4) * fftw_norm_fac
-      const C v = dk[e];
-      const double p = ((double) v.x * (double) v.x + (double) v.y * (double) v.y) * corr;
-      const double w = (d2 == 0 || 2 * d2 == N) ? 1.0 : 2.0;
-      const double kmag = sqrt((double) m);
-      atomicAdd(&sb[nk], w * p);
-      atomicAdd(&sb[nbins + nk], w * kmag);
-      atomicAdd(&sb[2 * nbins + nk], w);
-      if (RSD) {
-        // mu2 = d[2]*d[2]/kmag/kmag; the (0,0,0) mode has mu2 = 0 (compute_pofk.c:601-602)
-        const double mu2 = m == 0 ? 0.0 : (double) ((long long) d2 * d2) / kmag / kmag;
-        atomicAdd(&sb[3 * nbins + nk], w * p * mu2);
-        atomicAdd(&sb[4 * nbins + nk], w * p * mu2 * mu2);
+  // Neighbouring modes fall into the same few bins: the lanes of a warp are summed per distinct bin with shuffles and
+  // ONE lane adds the total, instead of 32 lanes fighting over one shared-memory address (atomicAdd on a shared double is
+  // a compare-and-swap loop on this part).
+  const size_t nround = (L.total + 31) / 32 * 32;
+  const unsigned lane = threadIdx.x & 31;
+  for (size_t e = blockIdx.x * (size_t) blockDim.x + threadIdx.x; e < nround; e += (size_t) gridDim.x * blockDim.x) {
+    int nk = -1;
+    double vp = 0.0, vk = 0.0, vn = 0.0, v2 = 0.0, v4 = 0.0;
+    if (e < L.total) {
+      int i, j, k;
+      kl_decode(L, e, i, j, k);
+      const int d0 = i > N / 2 ? N - i : i, d1 = j > N / 2 ? N - j : j, d2 = k;
+      const long long m = (long long) d0 * d0 + (long long) d1 * d1 + (long long) d2 * d2;
+      nk = bin_of_m[m];
+      if (nk >= nbins) nk = -1;
+      if (nk >= 0) {
+        const double gz = (d2 == 0) ? 1.0 : ((2 * d2 == N) ? 2.0 / 3.14159265358979323846 : sinc[d2]);
+        const double gc = sinc[d0] * sinc[d1] * gz;
+        const double g2 = gc * gc;
+        const double corr = 1.0 / (g2 * g2) * norm;          // 1/pow(gx*gy*gz, 4) * fftw_norm_fac
+        const C v = dk[e];
+        const double p = ((double) v.x * (double) v.x + (double) v.y * (double) v.y) * corr;
+        const double w = (d2 == 0 || 2 * d2 == N) ? 1.0 : 2.0;
+        const double kmag = sqrt((double) m);
+        vp = w * p; vk = w * kmag; vn = w;
+        if (RSD) {
+          // mu2 = d[2]*d[2]/kmag/kmag; the (0,0,0) mode has mu2 = 0 (compute_pofk.c:601-602)
+          const double mu2 = m == 0 ? 0.0 : (double) ((long long) d2 * d2) / kmag / kmag;
+          v2 = vp * mu2; v4 = vp * mu2 * mu2;
+        }
       }
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, nk >= 0);
+    while (todo) {
+      const int b = __shfl_sync(0xffffffffu, nk, __ffs(todo) - 1);
+      const bool mine = nk == b;
+      double a = mine ? vp : 0.0, bk = mine ? vk : 0.0, cn = mine ? vn : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o); bk += __shfl_xor_sync(0xffffffffu, bk, o); cn += __shfl_xor_sync(0xffffffffu, cn, o);
+      }
+      double r2 = 0.0, r4 = 0.0;
+      if (RSD) {
+        r2 = mine ? v2 : 0.0; r4 = mine ? v4 : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { r2 += __shfl_xor_sync(0xffffffffu, r2, o); r4 += __shfl_xor_sync(0xffffffffu, r4, o); }
+      }
+      if (lane == 0) {
+        atomicAdd(&sb[b], a); atomicAdd(&sb[nbins + b], bk); atomicAdd(&sb[2 * nbins + b], cn);
+        if (RSD) { atomicAdd(&sb[3 * nbins + b], r2); atomicAdd(&sb[4 * nbins + b], r4); }
+      }
+      todo &= ~__ballot_sync(0xffffffffu, mine);
     }
   }
   __syncthreads();

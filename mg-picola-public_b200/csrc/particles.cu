@@ -214,6 +214,48 @@ void particles_download(Ctx &c, float *pos, float *vel, float *D, float *D2, uin
   CK(cudaEventDestroy(unpacked));
 }
 
+
+// ------------------------------------------------------------------ [3][cap] device arrays <-> [n][3] host arrays
+
+__global__ void k_soa3_to_aos(size_t n, size_t off, const float *__restrict__ soa, size_t cap, float m0, float m1, float m2,
+                              double d0, double d1, double d2, int sub, float *__restrict__ aos) {
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+    float x = soa[off + i], y = soa[cap + off + i], z = soa[2 * cap + off + i];
+    if (sub) {           // value - mean evaluated in double, stored float (2LPT.c:1501-1508)
+      x = (float) ((double) x - d0); y = (float) ((double) y - d1); z = (float) ((double) z - d2);
+    }
+    aos[3 * i] = x; aos[3 * i + 1] = y; aos[3 * i + 2] = z;
+  }
+}
+
+__global__ void k_aos_to_soa3(size_t n, size_t off, const float *__restrict__ aos, float *__restrict__ soa, size_t cap) {
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+    soa[off + i] = aos[3 * i]; soa[cap + off + i] = aos[3 * i + 1]; soa[2 * cap + off + i] = aos[3 * i + 2];
+  }
+}
+
+// The interleaving runs on the device, chunk by chunk through the staging area; the host side is one contiguous copy
+// per chunk (no per-element host loop, no pageable temporary).
+void copy_soa3(Ctx &c, float *dev_soa, size_t n, float *host_aos, bool to_host, const double *sub_mean) {
+  if (!n) return;
+  const size_t ch = n < kChunk ? n : kChunk;
+  float *st = stage_buffer(c, ch);
+  for (size_t off = 0; off < n; off += ch) {
+    const size_t m = (n - off) < ch ? (n - off) : ch;
+    if (to_host) {
+      k_soa3_to_aos<<<grid_for(m, 256), 256, 0, c.stream>>>(m, off, dev_soa, c.cap, 0.f, 0.f, 0.f, sub_mean ? sub_mean[0] : 0.0,
+                                                           sub_mean ? sub_mean[1] : 0.0, sub_mean ? sub_mean[2] : 0.0,
+                                                           sub_mean != nullptr, st);
+      CK(cudaMemcpyAsync(host_aos + 3 * off, st, m * 12, cudaMemcpyDeviceToHost, c.stream));
+    } else {
+      CK(cudaMemcpyAsync(st, host_aos + 3 * off, m * 12, cudaMemcpyHostToDevice, c.stream));
+      k_aos_to_soa3<<<grid_for(m, 256), 256, 0, c.stream>>>(m, off, st, dev_soa, c.cap);
+    }
+    c.launches++;
+    CK(cudaStreamSynchronize(c.stream));       // the staging chunk is reused
+  }
+}
+
 // ------------------------------------------------------------------ cell keys, sort, permute
 
 // key = ((ix - x0) * N + iy) * N + iz; cell of a position exactly as PtoMesh computes it

@@ -770,20 +770,8 @@ void sd_free(Ctx &c) {
 void sd_copy_field(Ctx &c, int slot, float *host, bool to_host) {
   REQUIRE(slot >= 0 && slot < 4 && c.sdf[slot], MGP_ERR_STATE, "scale-dependent field storage missing");
   if (to_host) sd_materialise(c, slot / 2); else c.sd_res[slot / 2] = -1;
-  std::vector<float> tmp(c.np);
-  for (int a = 0; a < 3; a++) {
-    float *dev = c.sdf[slot] + (size_t) a * c.cap;
-    if (to_host) {
-      if (c.sd_zero[slot]) { for (size_t i = 0; i < c.np; i++) host[3 * i + a] = 0.0f; continue; }
-      CK(cudaMemcpyAsync(tmp.data(), dev, c.np * sizeof(float), cudaMemcpyDeviceToHost, c.stream));
-      CK(cudaStreamSynchronize(c.stream));
-      for (size_t i = 0; i < c.np; i++) host[3 * i + a] = tmp[i];
-    } else {
-      for (size_t i = 0; i < c.np; i++) tmp[i] = host[3 * i + a];
-      CK(cudaMemcpyAsync(dev, tmp.data(), c.np * sizeof(float), cudaMemcpyHostToDevice, c.stream));
-      CK(cudaStreamSynchronize(c.stream));
-    }
-  }
+  if (to_host && c.sd_zero[slot]) memset(host, 0, c.np * 3 * sizeof(float));
+  else copy_soa3(c, c.sdf[slot], c.np, host, to_host);
   if (!to_host) { c.sd_zero[slot] = false; c.sd_set[slot] = true; }
 }
 

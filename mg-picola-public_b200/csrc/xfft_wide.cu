@@ -1,7 +1,7 @@
 // Wide-tile instances of the fused x-transform (xfft.cuh): tiles of up to 128 KB (one CTA per SM, which is how the kernel
-// runs on several ranks anyway), i.e. twice the run length of the default instances on the exchange side.  Opt-in
-// (MGP_XFFT_WIDE=1, read by fft.cu): host-emulated (tests/host/xfft_emul.cu covers these tile widths), not yet timed on
-// a GPU.
+// runs on several ranks anyway), i.e. twice the run length of the default instances on the exchange side.  Default from
+// Nmesh = 1024 on several ranks (fft.cu; MGP_XFFT_WIDE overrides); parity: tests/test_slab_fused.py, host emulation
+// tests/host/xfft_emul.cu.
 #include "common.cuh"
 
 namespace mgp {
@@ -30,8 +30,11 @@ static bool prepare(Ctx &c) {
     int cps_want = c.P > 1 ? 1 : 2;
     if (const char *cps = getenv("MGP_XFFT_CPS")) cps_want = atoi(cps);
     if (cps_want >= 1 && cps_want < occ) occ = cps_want;
+    // on several ranks the kernel is NVLink-bound: a quarter of the SMs left entirely to the 2-D cuFFT kernels of the
+    // other components of a batched transform costs the exchange 5 % and gains the pipeline 7 % (8 x B200, 1024^3:
+    // 8.08 -> 7.52 ms per batch of three, profiles/r02_exchange_8gpu.md)
     const char *tr = getenv("MGP_XFFT_TRIM");
-    long long g = (long long) kSMs * occ - (tr ? atoi(tr) : 1);
+    long long g = (long long) kSMs * occ - (tr ? atoi(tr) : (c.P > 1 ? 38 : 1));
     if (g < 1) g = 1;
     const long long ntiles = (long long) c.ny_loc * xf::tiles_per_line(c.NZ, TK, 128 / (int) sizeof(C));
     c.xf_grid = (int) (ntiles < g ? ntiles : g);

@@ -33,9 +33,11 @@ def _die_with_parent():
         pass
 
 
-def run(cmd, nranks, slot_mb=64, scratch_mb=64, cwd=None, timeout=3600, env=None, rank_env=None):
+def run(cmd, nranks, slot_mb=64, scratch_mb=64, cwd=None, timeout=3600, env=None, rank_env=None, line_cb=None):
     """Runs `cmd` (list) on `nranks` ranks.  Returns (returncode, stdout of rank 0, tail of every rank's stderr).
-    scratch_mb must hold one complex half-spectrum of the mesh: Nmesh^2 (Nmesh/2+1) * 16 bytes (double grids)."""
+    scratch_mb must hold one complex half-spectrum of the mesh: Nmesh^2 (Nmesh/2+1) * 16 bytes (double grids).
+    line_cb(line, t_seconds_since_start): called for every line of rank 0's stdout as it arrives; returning True stops
+    the run (all ranks are killed, returncode 0): bench.py times the reference's iterations this way."""
     import shutil
     # pages appear when touched: the scratch grid in full, of the message slots only what the messages use
     touched = (scratch_mb << 20) + nranks * (8 << 20)
@@ -64,10 +66,23 @@ def run(cmd, nranks, slot_mb=64, scratch_mb=64, cwd=None, timeout=3600, env=None
         # rank 0's stdout can be large: drain it in this thread while polling the others
         import threading
         chunks = []
-        th = threading.Thread(target=lambda: chunks.append(procs[0].stdout.read()), daemon=True)
+        stop = []
+
+        def drain():
+            if line_cb is None:
+                chunks.append(procs[0].stdout.read())
+                return
+            for line in procs[0].stdout:
+                chunks.append(line)
+                if not stop and line_cb(line, time.time() - t0):
+                    stop.append(1)
+        th = threading.Thread(target=drain, daemon=True)
         th.start()
         rc = None
         while True:
+            if stop:
+                rc = 0
+                break
             codes = [p.poll() for p in procs]
             if any(c not in (None, 0) for c in codes):                  # a rank died or aborted: the others wait forever
                 rc = next(c for c in codes if c not in (None, 0))

@@ -101,11 +101,9 @@ def test_single_gpu_suite_on_the_slab_path(require_gpu, xfft, dma, select):
 
 @pytest.mark.parametrize("N,gb,knob", [(320, 8, "MGP_XFFT_MIXED"), (400, 8, "MGP_XFFT_MIXED"), (320, 4, "MGP_XFFT_MIXED"),
                                        (128, 8, "MGP_XFFT_WIDE"), (256, 8, "MGP_XFFT_WIDE"), (256, 4, "MGP_XFFT_WIDE")])
-def test_experimental_instances_match_numpy(mgp, require_gpu, monkeypatch, N, gb, knob):
-    """The mixed-radix (Nmesh = 320, 400) and wide-tile instances of the fused kernel: host-emulated
-    (tests/test_xfft_host.py), first GPU run pending -- opt-in with MGP_TEST_EXPERIMENTAL=1 until then."""
-    if os.environ.get("MGP_TEST_EXPERIMENTAL", "0") != "1":
-        pytest.skip("first GPU run pending: set MGP_TEST_EXPERIMENTAL=1")
+def test_mixed_radix_and_wide_instances_match_numpy(mgp, require_gpu, monkeypatch, N, gb, knob):
+    """The mixed-radix (Nmesh = 320, 400) and wide-tile instances of the fused kernel (host emulation:
+    tests/test_xfft_host.py; first green GPU run: profiles/r02a_experimental.log)."""
     monkeypatch.setenv("MGP_FORCE_SLAB", "1")
     monkeypatch.setenv("MGP_XFFT", "1")
     monkeypatch.setenv("MGP_XFFT_DMA", "0")

@@ -10,7 +10,7 @@ for stage in "$@"; do
   echo "=== stage $stage ($(date +%T))"
   case $stage in
     experimental)      # first GPU run of the mixed-radix / wide-tile instances of the fused x-transform
-      MGP_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_slab_fused.py -q -m gpu -k experimental -p no:cacheprovider \
+      MGP_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_slab_fused.py -q -m gpu -k "mixed_radix_and_wide" -p no:cacheprovider \
         > gpurun_out/${TAG}_experimental.log 2>&1; tail -5 gpurun_out/${TAG}_experimental.log ;;
     tests)             # the whole single-GPU suite
       timeout 1500 python -m pytest tests -x -q -m gpu -p no:cacheprovider > gpurun_out/${TAG}_gpu_tests.log 2>&1
