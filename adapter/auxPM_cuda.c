@@ -238,12 +238,28 @@ static void upload_host_particles(void) {
   g_host_synced = 0;
 }
 
+/* GADGET snapshots are packed on the GPU (mgp_pack_snapshot): Output() never reads P, only NumPart.  The ASCII output of a
+ * build without -DGADGET_STYLE, the FoF hook and MGP_HOST_SNAPSHOT=1 (the previous behaviour) still bring P back. */
+static int gpu_snapshot(void) {
+#if defined(GADGET_STYLE) && !defined(MATCHMAKER_HALOFINDER)
+  static int on = -1;
+  if (on < 0) { const char *e = getenv("MGP_HOST_SNAPSHOT"); on = !(e && atoi(e) != 0); }
+  return on;
+#else
+  return 0;
+#endif
+}
+
 /* called (through the main.c patch) before Output() reads P */
 void mgp_adapter_sync_host(void) {
   int lnx, lx0, lnp, lp0;
   uint64_t np;
-  if (g_host_is_newer) return;
+  if (g_host_is_newer) {
+    if (!gpu_snapshot()) return;
+    upload_host_particles();          /* an output before the first force evaluation: the blocks are packed on the device */
+  }
   ck(mgp_get_layout(g_ctx, &lnx, &lx0, &lnp, &lp0, &np), "mgp_get_layout");
+  if (gpu_snapshot()) { NumPart = (unsigned int) np; return; }
   if (np > g_host_capacity) FatalError((char *) "mgp_adapter_sync_host: more particles than the host buffer holds; increase Buffer");
   const size_t n = (size_t) np;
   float *pos = my_malloc(n * 12), *vel = my_malloc(n * 12), *d1 = my_malloc(n * 12), *d2 = my_malloc(n * 12);
@@ -269,6 +285,47 @@ void mgp_adapter_sync_host(void) {
   }
 #endif
   g_host_synced = 1;
+}
+
+/* called (through the main.c patch) from Output() in place of its three block loops (main.c:936-997) */
+void mgp_adapter_write_gadget_blocks(FILE *fp, double lengthfac, double velfac_times_fac, double dDdy, double dD2dy) {
+  static float *pos = NULL, *vel = NULL;
+  static uint64_t *id = NULL;
+  static size_t cap = 0;
+  static int pinned = 1;
+  if (!gpu_snapshot()) FatalError((char *) "mgp_adapter_write_gadget_blocks: GPU snapshot packing is off in this build");
+  if (g_host_is_newer) upload_host_particles();       /* an output before the first force evaluation */
+  int lnx, lx0, lnp, lp0;
+  uint64_t np;
+  ck(mgp_get_layout(g_ctx, &lnx, &lx0, &lnp, &lp0, &np), "mgp_get_layout");
+  const size_t n = (size_t) np;
+  if (n > cap) {
+    if (pos) { if (pinned) { mgp_free_host(pos); mgp_free_host(vel); mgp_free_host(id); } else { free(pos); free(vel); free(id); } }
+    cap = n + n / 8 + 1024;
+    pos = mgp_alloc_host(cap * 12); vel = mgp_alloc_host(cap * 12); id = mgp_alloc_host(cap * 8);
+    pinned = pos && vel && id;
+    if (!pinned) {                                     /* no pinned memory to be had: pageable buffers work too */
+      if (pos) mgp_free_host(pos);
+      if (vel) mgp_free_host(vel);
+      if (id) mgp_free_host(id);
+      pos = malloc(cap * 12); vel = malloc(cap * 12); id = malloc(cap * 8);
+      if (!pos || !vel || !id) FatalError((char *) "mgp_adapter_write_gadget_blocks: out of host memory");
+    }
+  }
+  ck(mgp_pack_snapshot(g_ctx, lengthfac, velfac_times_fac, sumxyz, dDdy, dD2dy, pos, vel, id), "mgp_pack_snapshot");
+  int dummy = (int) (sizeof(float) * 3 * n);
+  my_fwrite(&dummy, sizeof(dummy), 1, fp);
+  if (n) my_fwrite(pos, sizeof(float), 3 * n, fp);
+  my_fwrite(&dummy, sizeof(dummy), 1, fp);
+  my_fwrite(&dummy, sizeof(dummy), 1, fp);
+  if (n) my_fwrite(vel, sizeof(float), 3 * n, fp);
+  my_fwrite(&dummy, sizeof(dummy), 1, fp);
+#ifdef PARTICLE_ID
+  dummy = (int) (sizeof(unsigned long long) * n);
+  my_fwrite(&dummy, sizeof(dummy), 1, fp);
+  if (n) my_fwrite(id, sizeof(unsigned long long), n, fp);
+  my_fwrite(&dummy, sizeof(dummy), 1, fp);
+#endif
 }
 
 #ifdef SCALEDEPENDENT

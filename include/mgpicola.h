@@ -152,6 +152,18 @@ int mgp_upload_particles(mgp_ctx *ctx, uint64_t n, const float *pos, const float
                          const float *D, const float *D2, const uint64_t *id);
 /* copy back for Output (main.c:792-1061); any pointer may be NULL; arrays sized NumPart */
 int mgp_download_particles(mgp_ctx *ctx, float *pos, float *vel, float *D, float *D2, uint64_t *id);
+/* Output(), main.c:915-997: the three GADGET blocks of this rank's particles, formed on the device exactly as Output()
+ * forms them on the host and copied into the caller's buffers ([numpart][3] floats twice, [numpart] 64-bit IDs):
+ *   pos = (float)(lengthfac * Pos);   vel = (float)(velfac*fac * (Vel - sumxyz + (D dDdy + D2 dD2dy) UseCOLA))
+ * (scale_dependent: the float sum P.dDdy + P.dD2dy of the fields assigned last, which Output() makes FIELD_dDdy first,
+ * main.c:824-825).  Replaces the download of the whole particle store before an output.  The copies overlap the
+ * packing when the buffers are pinned (mgp_alloc_host). */
+int mgp_pack_snapshot(mgp_ctx *ctx, double lengthfac, double velfac_times_fac, const double sumxyz[3], double dDdy,
+                      double dD2dy, float *pos, float *vel, uint64_t *id);
+/* pinned (page-locked, portable) host memory for particle buffers the driver hands to the library; NULL on failure */
+void *mgp_alloc_host(size_t bytes);
+void mgp_free_host(void *p);
+
 /* Disp[3][NumPart] of MtoParticles (auxPM.c:605-630), as [n][3] */
 int mgp_download_disp(mgp_ctx *ctx, float *disp);
 /* the inverse: load Disp[3][NumPart] from the host as [n][3] (a driver that keeps its own Disp, tests) */
@@ -175,6 +187,18 @@ typedef struct mgp_ic_config {
 /* displacement_fields(): delta_k, the six displacement gradients, the 2LPT source, and the ZA / 2LPT
  * displacements read out at the Lagrangian points of this rank's particle planes (13 FFTs) */
 int mgp_ic_generate(mgp_ctx *ctx, const mgp_ic_config *ic);
+/* READICFROMFILE: ReadFilesMakeDisplacementField + AssignDisplacementField (readICfromfile.c:133-215, 533-778).  The
+ * driver keeps reading the RAMSES / GADGET / ASCII files itself and hands every file's positions over:
+ *   begin   density = -1 (580-581)
+ *   add     pos01[n][3] floats in [0, 1): the particles of this rank's slab are CIC-assigned with X = pos * Nmesh and
+ *           W = (Nmesh/Nsample)^3 (ProcessParticlesSingleFile); *taken_total = how many this rank has taken so far
+ *   finish  ghost-plane add, r2c, density *= normfac (the driver passes 1/Nmesh^3 * growth_DLCDM(1) /
+ *           growth_DLCDM(a_init), 642-646), sharp-k filter above Nsample/2 when Nmesh > Nsample (648-680), CIC window
+ *           deconvolution and rescale_by_k2[m] = sqrt(mg_pofk_ratio(k, 1)) [/ sigma8 ratio] at m = |d|^2 (701-778), then the
+ *           2LPT pipeline of mgp_ic_generate on that delta_k.  Continue with mgp_ic_download / mgp_init_particles. */
+int mgp_ic_particles_begin(mgp_ctx *ctx);
+int mgp_ic_particles_add(mgp_ctx *ctx, const float *pos01, uint64_t n, uint64_t *taken_total);
+int mgp_ic_particles_finish(mgp_ctx *ctx, double normfac, const double *rescale_by_k2, size_t n);
 /* ZA[3][NumPart] / LPT[3][NumPart] of displacement_fields() (vars.h:265-270) for this rank's Lagrangian
  * particles, mean-subtracted, as [n][3]; valid between mgp_ic_generate and mgp_init_particles.  For a
  * driver that keeps main.c's own initialisation loop (main.c:257-309) on the host. */
@@ -250,6 +274,15 @@ int mgp_get_step_power_spectrum_total(mgp_ctx *ctx, double *pofk, double *kmean,
 int mgp_compute_rsd_power_spectrum(mgp_ctx *ctx, double vnorm, double dDdy, double dD2dy, double *out_y, double *out_z);
 
 /* ---- grid access (tests, write_grid_to_file auxPM.c:757-813) ---- */
+/* SimplePofk/main.cpp (the reference's stand-alone P(k) estimator) on the particles the context holds: assignment of raw
+ * counts with scheme 1 = NGP, 2 = CIC, 3 = TSC (main.cpp:59-228; x = double(pos_float / boxsize) * ngrid), one transform,
+ * |d_k|^2 / N^6 / window^2 with window = prod sinc(pi k_a / N)^scheme (324-340, 393), bins int(|k| + 0.5), 0 < bin < Nmesh
+ * (391), mean per bin, optional shot noise 1 / Npart (420-424).  pofk, nmodes: Nmesh doubles each; the tool prints
+ * k = (2 i + 1) pi / Box and pofk[i] Box^3 for 1 <= i <= Nmesh / 2.  tsc_as_published = 1 reproduces the tool's TSC as
+ * written (the P_z weight of the three "this y" lines lands on the next z plane, main.cpp:189, 201, 213); 0 = the textbook
+ * stencil.  One rank only; overwrites force grid X. */
+int mgp_simple_pofk(mgp_ctx *ctx, int scheme, int subtract_shotnoise, int tsc_as_published, double *pofk, double *nmodes);
+
 /* local slab incl. ghost plane: (Local_nx+1) * Nmesh * 2*(Nmesh/2+1) values of grid_bytes */
 size_t mgp_grid_local_values(mgp_ctx *ctx);
 int mgp_download_grid(mgp_ctx *ctx, int grid_id, void *host);

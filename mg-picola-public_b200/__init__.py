@@ -79,9 +79,16 @@ def load_library(path=None):
     L.mgp_upload_particles.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mgp_download_particles.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mgp_download_disp.argtypes = [C.c_void_p, C.c_void_p]
+    L.mgp_pack_snapshot.argtypes = [C.c_void_p, C.c_double, C.c_double, dp, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mgp_alloc_host.argtypes = [C.c_size_t]
+    L.mgp_alloc_host.restype = C.c_void_p
+    L.mgp_free_host.argtypes = [C.c_void_p]
     L.mgp_upload_disp.argtypes = [C.c_void_p, C.c_void_p]
     L.mgp_ic_generate.argtypes = [C.c_void_p, C.POINTER(IcConfig)]
     L.mgp_ic_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mgp_ic_particles_begin.argtypes = [C.c_void_p]
+    L.mgp_ic_particles_add.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.mgp_ic_particles_finish.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_size_t]
     L.mgp_init_particles.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]
     L.mgp_seedtable.argtypes = [C.c_uint, C.c_int, C.c_void_p]
     L.mgp_ranlxd1_draw.argtypes = [C.c_ulong, C.c_long]
@@ -104,6 +111,7 @@ def load_library(path=None):
     L.mgp_get_step_power_spectrum.argtypes = [C.c_void_p, dp, dp, dp]
     L.mgp_get_step_power_spectrum_total.argtypes = [C.c_void_p, dp, dp, dp]
     L.mgp_compute_rsd_power_spectrum.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, dp, dp]
+    L.mgp_simple_pofk.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, dp, dp]
     L.mgp_grid_local_values.argtypes = [C.c_void_p]
     L.mgp_grid_local_values.restype = C.c_size_t
     L.mgp_download_grid.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
@@ -231,6 +239,14 @@ class PM:
     def download_raw(self, pos, vel, D, D2, ids):
         self._ck(self.L.mgp_download_particles(self.ctx, pos or None, vel or None, D or None, D2 or None, ids or None))
 
+    def pack_snapshot(self, lengthfac, velfac_times_fac, sumxyz=None, dDdy=0.0, dD2dy=0.0):
+        """The GADGET blocks of Output() (main.c:915-997): (pos [n][3] float32, vel [n][3] float32, id [n] uint64)."""
+        n = self.numpart
+        pos, vel, ids = np.empty((n, 3), np.float32), np.empty((n, 3), np.float32), np.empty(n, np.uint64)
+        sv = (C.c_double * 3)(*(self.sumxyz if sumxyz is None else sumxyz))
+        self._ck(self.L.mgp_pack_snapshot(self.ctx, lengthfac, velfac_times_fac, sv, dDdy, dD2dy, _ptr(pos), _ptr(vel), _ptr(ids)))
+        return pos, vel, ids
+
     def download_disp(self):
         d = np.empty((self.numpart, 3), np.float32)
         self._ck(self.L.mgp_download_disp(self.ctx, _ptr(d)))
@@ -243,6 +259,18 @@ class PM:
         st = None if seedtable is None else np.ascontiguousarray(seedtable, dtype=np.uint32)
         ic = IcConfig(seed, sphere_mode, amplitude_fixed, inverted, pw.ctypes.data, pw.size, None if st is None else st.ctypes.data)
         self._ck(self.L.mgp_ic_generate(self.ctx, C.byref(ic)))
+
+    def ic_from_particles(self, pos01_files, normfac, rescale_by_k2):
+        """READICFROMFILE (readICfromfile.c:533-778): pos01_files = one [n][3] float32 array in [0, 1) per particle file.
+        Returns how many of the particles fell into this rank's slab."""
+        self._ck(self.L.mgp_ic_particles_begin(self.ctx))
+        taken = C.c_uint64(0)
+        for p in pos01_files:
+            p = np.ascontiguousarray(p, dtype=np.float32)
+            self._ck(self.L.mgp_ic_particles_add(self.ctx, _ptr(p), p.shape[0], C.byref(taken)))
+        r = np.ascontiguousarray(rescale_by_k2, dtype=np.float64)
+        self._ck(self.L.mgp_ic_particles_finish(self.ctx, normfac, _ptr(r), r.size))
+        return taken.value
 
     def ic_download(self):
         n = self.local_np * self.Ns * self.Ns
@@ -376,6 +404,14 @@ class PM:
             out["P" + nm] = (oy[i] + oz[i]) / 2.0
             out["err" + nm] = np.abs(oy[i] - oz[i]) / np.sqrt(2.0)
         return out
+
+    def simple_pofk(self, scheme="CIC", subtract_shotnoise=False, tsc_as_published=True):
+        """SimplePofk/main.cpp on the context's particles: (pofk[N], nmodes[N]); k_i = (2 i + 1) pi / Box, P_i = pofk[i] Box^3."""
+        p, n = np.zeros(self.N), np.zeros(self.N)
+        dp = C.POINTER(C.c_double)
+        self._ck(self.L.mgp_simple_pofk(self.ctx, {"NGP": 1, "CIC": 2, "TSC": 3}[scheme], int(subtract_shotnoise), int(tsc_as_published),
+                                        p.ctypes.data_as(dp), n.ctypes.data_as(dp)))
+        return p, n
 
     # ---- grids ----
     def download_grid(self, gid):

@@ -357,6 +357,29 @@ int mgp_download_particles(mgp_ctx *ctx, float *pos, float *vel, float *D, float
   API_END
 }
 
+int mgp_pack_snapshot(mgp_ctx *ctx, double lengthfac, double velfac_times_fac, const double sumxyz[3], double dDdy, double dD2dy,
+                      float *pos, float *vel, uint64_t *id) {
+  API_BEGIN
+  CTX(ctx);
+  REQUIRE(pos && vel && id && sumxyz, MGP_ERR_INVALID, "mgp_pack_snapshot: NULL argument");
+  if (c.cfg.scale_dependent && c.cfg.use_cola) {
+    sd_materialise(c, 1);                                 // a resident merged field -> P.dDdy / P.dD2dy
+    REQUIRE(c.sd_set[2], MGP_ERR_STATE, "mgp_pack_snapshot (scale-dependent): assign FIELD_dDdy first (main.c:824-825)");
+  }
+  particles_snapshot(c, lengthfac, velfac_times_fac, sumxyz, dDdy, dD2dy, pos, vel, id);
+  API_END
+}
+
+void *mgp_alloc_host(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+
+void mgp_free_host(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
 int mgp_download_disp(mgp_ctx *ctx, float *disp) {
   API_BEGIN
   CTX(ctx);
@@ -372,6 +395,30 @@ int mgp_ic_generate(mgp_ctx *ctx, const mgp_ic_config *ic) {
   if (c.cfg.scale_dependent) sd_drop(c);
   c.density_live = false; c.forces_live = false;
   ic_generate(c, ic);
+  API_END
+}
+
+int mgp_ic_particles_begin(mgp_ctx *ctx) {
+  API_BEGIN
+  CTX(ctx);
+  if (c.cfg.scale_dependent) sd_drop(c);
+  c.density_live = false; c.forces_live = false;
+  ic_particles_begin(c);
+  API_END
+}
+
+int mgp_ic_particles_add(mgp_ctx *ctx, const float *pos01, uint64_t n, uint64_t *taken_total) {
+  API_BEGIN
+  CTX(ctx);
+  ic_particles_add(c, pos01, n);
+  if (taken_total) *taken_total = c.ic_ext_taken;
+  API_END
+}
+
+int mgp_ic_particles_finish(mgp_ctx *ctx, double normfac, const double *rescale_by_k2, size_t n) {
+  API_BEGIN
+  CTX(ctx);
+  ic_particles_finish(c, normfac, rescale_by_k2, n);
   API_END
 }
 
@@ -582,6 +629,14 @@ int mgp_compute_rsd_power_spectrum(mgp_ctx *ctx, double vnorm, double dDdy, doub
   API_BEGIN
   CTX(ctx);
   rsd_power_spectrum(c, vnorm, dDdy, dD2dy, out_y, out_z);
+  API_END
+}
+
+int mgp_simple_pofk(mgp_ctx *ctx, int scheme, int subtract_shotnoise, int tsc_as_published, double *pofk, double *nmodes) {
+  API_BEGIN
+  CTX(ctx);
+  REQUIRE(pofk && nmodes, MGP_ERR_INVALID, "mgp_simple_pofk: NULL output");
+  simple_pofk(c, scheme, subtract_shotnoise, tsc_as_published, pofk, nmodes);
   API_END
 }
 

@@ -144,6 +144,8 @@ struct Ctx {
   // initial conditions / scale-dependent growth
   double ic_means[6] = {0, 0, 0, 0, 0, 0};
   bool ic_ready = false;
+  bool ic_ext_open = false;                  // between mgp_ic_particles_begin and _finish (READICFROMFILE)
+  unsigned long long ic_ext_taken = 0;       // external particles that fell into this rank's slab
   void *sd_delta[2] = {nullptr, nullptr};    // delta1_k, delta2_k (cdelta_cdm, cdelta_cdm2; vars.h:272-273)
   bool sd_have_delta = false;
   float *sdf[4] = {nullptr, nullptr, nullptr, nullptr};   // per-particle D, D2, dDdy, dD2dy as [3][cap] (sd.cu)
@@ -238,6 +240,8 @@ void particles_free(Ctx &c);
 void particles_upload(Ctx &c, uint64_t n, const float *pos, const float *vel, const float *D, const float *D2, const uint64_t *id);
 void particles_download(Ctx &c, float *pos, float *vel, float *D, float *D2, uint64_t *id);
 void particles_sort(Ctx &c);
+void particles_snapshot(Ctx &c, double lengthfac, double vfac, const double sumxyz[3], double dDdy, double dD2dy, float *pos,
+                        float *vel, uint64_t *id);
 void copy_soa3(Ctx &c, float *dev_soa, size_t n, float *host_aos, bool to_host, const double *sub_mean = nullptr);
 void particles_kick(Ctx &c, double A, double dda, double ddD, double ddD2, const double sumD[3], double sumV[3]);
 void particles_drift(Ctx &c, double dyyy, double dD, double dD2, const double sumV[3]);
@@ -293,9 +297,15 @@ void pofk_bin_rsd(Ctx &c, int grid_id, double *out5);
 void kspace_nu_add(Ctx &c, const double *nufac_host, size_t n, double cdmfac);
 int pofk_effective_nbins(const Ctx &c);
 
+// simplepofk.cu
+void simple_pofk(Ctx &c, int scheme, int subtract_shotnoise, int slip, double *pofk, double *nmodes);
+
 // ic.cu
 void ic_generate(Ctx &c, const mgp_ic_config *ic);
 void ic_init_particles(Ctx &c, double Di, double Di2, double dDdy, double dD2dy);
+void ic_particles_begin(Ctx &c);
+void ic_particles_add(Ctx &c, const float *pos01, uint64_t n);
+void ic_particles_finish(Ctx &c, double normfac, const double *rescale_by_k2, size_t n);
 void ic_seedtable(unsigned seed, int N, unsigned *out);
 double ic_ranlxd1_draw(unsigned long seed, long n);
 

@@ -310,17 +310,96 @@ k_ic_particles(size_t nloc, int ns, int p0, const float *__restrict__ za, const 
   }
 }
 
-// ------------------------------------------------------------------ host orchestration
+
+// ------------------------------------------------------------------ READICFROMFILE (readICfromfile.c:133-215, 533-778)
+
+// ProcessParticlesSingleFile (readICfromfile.c:133-215): external particles with coordinates in [0, 1), X = pos * Nmesh,
+// only those of this rank's slab, CIC with W = (Nmesh/Nsample)^3 onto a grid that started at -1.
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_ic_assign_unit(size_t n, const float *__restrict__ pos, T *__restrict__ grid, int N, int NZ, int nx, int x0, int single_rank,
+                 double W, unsigned long long *__restrict__ taken) {
+  unsigned long long mine = 0;
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+    double X = (double) pos[3 * i];
+    const int ixx = (int) (X * (double) N) - x0;
+    if (ixx >= nx || ixx < 0) continue;
+    mine++;
+    X *= (double) N;
+    const double Y = (double) pos[3 * i + 1] * (double) N, Z = (double) pos[3 * i + 2] * (double) N;
+    unsigned ix = (unsigned) X, iy = (unsigned) Y, iz = (unsigned) Z;
+    const double dx = X - (double) ix, dz = Z - (double) iz, tx = 1.0 - dx, tz = 1.0 - dz;
+    double dy = Y - (double) iy, ty = 1.0 - dy;
+    dy *= W; ty *= W;
+    ix -= (unsigned) x0;
+    if (iy >= (unsigned) N) iy = 0;
+    if (iz >= (unsigned) N) iz = 0;
+    unsigned ix1 = ix + 1;
+    if (single_rank && ix1 == (unsigned) nx) ix1 = 0;          // one rank: the ghost plane is plane 0
+    const unsigned iy1 = iy + 1 >= (unsigned) N ? 0 : iy + 1, iz1 = iz + 1 >= (unsigned) N ? 0 : iz + 1;
+    const size_t rz = (size_t) 2 * NZ;
+    T *r00 = grid + ((size_t) ix * N + iy) * rz, *r01 = grid + ((size_t) ix * N + iy1) * rz;
+    T *r10 = grid + ((size_t) ix1 * N + iy) * rz, *r11 = grid + ((size_t) ix1 * N + iy1) * rz;
+    atomicAdd(r00 + iz, (T) (tx * ty * tz)); atomicAdd(r00 + iz1, (T) (tx * ty * dz));
+    atomicAdd(r01 + iz, (T) (tx * dy * tz)); atomicAdd(r01 + iz1, (T) (tx * dy * dz));
+    atomicAdd(r10 + iz, (T) (dx * ty * tz)); atomicAdd(r10 + iz1, (T) (dx * ty * dz));
+    atomicAdd(r11 + iz, (T) (dx * dy * tz)); atomicAdd(r11 + iz1, (T) (dx * dy * dz));
+  }
+  if (mine) atomicAdd(taken, mine);
+}
 
 template <typename T>
-static void ic_generate_t(Ctx &c, const mgp_ic_config *ic) {
+__global__ void k_ic_fill(T *g, size_t n, T v) {
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) g[i] = v;
+}
+
+// delta_k of the external particles -> the delta_k the 2LPT pipeline starts from: normalisation and growth to z = 0
+// (readICfromfile.c:642-646), sharp-k filter at the Nyquist frequency of the particle grid when Nmesh > Nsample (648-680),
+// CIC window deconvolution and the LCDM -> MG rescaling of AssignDisplacementField (701-778; rescale[m] at m = |d|^2)
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_ic_delta_ext(KL L, const typename Cpx<T>::type *__restrict__ p3d, const double *__restrict__ rescale, int nsample,
+               double normfac, typename Cpx<T>::type *__restrict__ dk) {
+  typedef typename Cpx<T>::type C;
+  const int N = L.N;
+  const double PI = 3.14159265358979323846;
+  KLOOP(e, L) {
+    int i, j, k;
+    kl_decode(L, e, i, j, k);
+    const int d0 = i > N / 2 ? i - N : i, d1 = j > N / 2 ? j - N : j, d2 = k;
+    const long long m = (long long) d0 * d0 + (long long) d1 * d1 + (long long) d2 * d2;
+    C out; out.x = (T) 0; out.y = (T) 0;
+    const bool cut = N > nsample && sqrt((double) m) > (double) (nsample / 2);
+    if (m != 0 && !cut) {
+      double gc = 1.0;
+      const int d[3] = {d0, d1, d2};
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+        if (d[a] != 0) gc *= sin((PI * d[a]) / (double) N) / ((PI * d[a]) / (double) N);
+      gc = (1.0 / gc) * (1.0 / gc);                        // pow(1.0 / grid_corr, 2.0)
+      const C v = p3d[e];
+      // density *= normfac in the grid's precision (644-646), then * grid_corr * rescale_fac in double (748-749)
+      const T re = (T) ((double) v.x * normfac), im = (T) ((double) v.y * normfac);
+      const double rf = rescale[m];
+      out.x = (T) (((double) re * gc) * rf); out.y = (T) (((double) im * gc) * rf);     // P3D * grid_corr * rescale_fac, left to right
+    }
+    dk[e] = out;
+  }
+}
+
+// ------------------------------------------------------------------ host orchestration
+
+// ext_rescale != nullptr: delta_k comes from the density of external particles (grid 0 holds their transformed density)
+template <typename T>
+static void ic_generate_t(Ctx &c, const mgp_ic_config *ic, const double *ext_rescale = nullptr, double ext_normfac = 0.0) {
   typedef typename Cpx<T>::type C;
   const int N = c.N, ns = c.cfg.nsample;
   const KL L = layout_of(c);
   const size_t nloc = (size_t) c.npl * ns * ns;
   REQUIRE(nloc <= c.cap, MGP_ERR_BUFFER, "mgp_ic_generate: particle capacity too small");
   const size_t mmax = (size_t) 3 * (N / 2) * (N / 2) + 1;
-  REQUIRE(ic->power_by_k2 != nullptr && ic->n_power >= mmax, MGP_ERR_INVALID,
+  const double *table = ext_rescale ? ext_rescale : ic->power_by_k2;
+  REQUIRE(table != nullptr && (ext_rescale || ic->n_power >= mmax), MGP_ERR_INVALID,
           "mgp_ic_generate: power_by_k2 must hold 3 (Nmesh/2)^2 + 1 entries");
 
   // scratch: delta_k lives in mgarray_one when the model has one, else in a temporary grid
@@ -331,13 +410,14 @@ static void ic_generate_t(Ctx &c, const mgp_ic_config *ic) {
   c.grid[MGP_GRID_MG_ONE] = dk;           // so that the FFT helpers can address it by id
 
   std::vector<unsigned> seeds;
-  if (ic->seedtable) seeds.assign(ic->seedtable, ic->seedtable + (size_t) N * N);
+  if (ext_rescale) seeds.assign(1, 0u);
+  else if (ic->seedtable) seeds.assign(ic->seedtable, ic->seedtable + (size_t) N * N);
   else make_seedtable(ic->seed, N, seeds);
   unsigned *d_seed = nullptr; double *d_pow = nullptr;
   CK(cudaMalloc(&d_seed, seeds.size() * sizeof(unsigned)));
   CK(cudaMalloc(&d_pow, mmax * sizeof(double)));
   CK(cudaMemcpyAsync(d_seed, seeds.data(), seeds.size() * sizeof(unsigned), cudaMemcpyHostToDevice, c.stream));
-  CK(cudaMemcpyAsync(d_pow, ic->power_by_k2, mmax * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+  CK(cudaMemcpyAsync(d_pow, table, mmax * sizeof(double), cudaMemcpyHostToDevice, c.stream));
 
   C *f[3] = {(C *) c.grid[1], (C *) c.grid[2], (C *) c.grid[3]};
   T *fr[3] = {(T *) c.grid[1], (T *) c.grid[2], (T *) c.grid[3]};
@@ -345,8 +425,11 @@ static void ic_generate_t(Ctx &c, const mgp_ic_config *ic) {
   const unsigned gk = grid_for(L.total, 256), gr = grid_for(c.grid_vals, 256);
 
   CK(cudaMemsetAsync(dk, 0, c.grid_bytes(), c.stream));
-  k_ic_delta<T><<<(unsigned) (((size_t) N * N + 127) / 128), 128, 0, c.stream>>>(L, d_seed, d_pow, ns, c.cfg.box, ic->sphere_mode,
-                                                                               ic->amplitude_fixed, ic->inverted, dk);
+  if (ext_rescale)
+    k_ic_delta_ext<T><<<grid_for(L.total, 256), 256, 0, c.stream>>>(L, (const C *) c.grid[MGP_GRID_DENSITY], d_pow, ns, ext_normfac, dk);
+  else
+    k_ic_delta<T><<<(unsigned) (((size_t) N * N + 127) / 128), 128, 0, c.stream>>>(L, d_seed, d_pow, ns, c.cfg.box, ic->sphere_mode,
+                                                                                 ic->amplitude_fixed, ic->inverted, dk);
   c.launches++;
   // second-order source from the six gradients
   for (int pass = 0; pass < 2; pass++) {
@@ -407,6 +490,56 @@ static void ic_generate_t(Ctx &c, const mgp_ic_config *ic) {
 void ic_generate(Ctx &c, const mgp_ic_config *ic) {
   REQUIRE(ic != nullptr, MGP_ERR_INVALID, "mgp_ic_generate: config is NULL");
   if (c.gbytes == 4) ic_generate_t<float>(c, ic); else ic_generate_t<double>(c, ic);
+}
+
+// ReadFilesMakeDisplacementField (readICfromfile.c:533-700) in three calls: begin (grid = -1), add (one per particle file),
+// finish (halo, r2c, normalisation, filter, deconvolution, then the same 2LPT pipeline as the Gaussian branch)
+void ic_particles_begin(Ctx &c) {
+  if (c.gbytes == 4) k_ic_fill<float><<<grid_for(c.grid_vals, 256), 256, 0, c.stream>>>((float *) c.grid[0], c.grid_vals, -1.0f);
+  else k_ic_fill<double><<<grid_for(c.grid_vals, 256), 256, 0, c.stream>>>((double *) c.grid[0], c.grid_vals, -1.0);
+  c.launches++;
+  c.ic_ext_taken = 0;
+  c.ic_ext_open = true;
+  c.density_live = false;
+}
+
+void ic_particles_add(Ctx &c, const float *pos01, uint64_t n) {
+  REQUIRE(c.ic_ext_open, MGP_ERR_STATE, "mgp_ic_particles_add: call mgp_ic_particles_begin first");
+  REQUIRE(pos01 != nullptr || n == 0, MGP_ERR_INVALID, "mgp_ic_particles_add: NULL");
+  if (!n) return;
+  const double r = (double) c.N / (double) c.cfg.nsample;
+  const double W = r * r * r;
+  const size_t chunk = (size_t) 1 << 24;
+  float *d_pos = nullptr;
+  unsigned long long *d_cnt = nullptr, h_cnt = 0;
+  CK(cudaMalloc(&d_pos, (n < chunk ? n : chunk) * 3 * sizeof(float)));
+  CK(cudaMalloc(&d_cnt, sizeof(unsigned long long)));
+  CK(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), c.stream));
+  for (uint64_t off = 0; off < n; off += chunk) {
+    const size_t m = (size_t) ((n - off) < chunk ? (n - off) : chunk);
+    CK(cudaMemcpyAsync(d_pos, pos01 + 3 * off, m * 3 * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+    if (c.gbytes == 4)
+      k_ic_assign_unit<float><<<grid_for(m, 256), 256, 0, c.stream>>>(m, d_pos, (float *) c.grid[0], c.N, c.NZ, c.nx, c.x0, c.P == 1, W, d_cnt);
+    else
+      k_ic_assign_unit<double><<<grid_for(m, 256), 256, 0, c.stream>>>(m, d_pos, (double *) c.grid[0], c.N, c.NZ, c.nx, c.x0, c.P == 1, W, d_cnt);
+    c.launches++;
+    CK(cudaStreamSynchronize(c.stream));            // the staging buffer is reused (and pos01 may be pageable)
+  }
+  CK(cudaMemcpy(&h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost));
+  CK(cudaFree(d_pos)); CK(cudaFree(d_cnt));
+  c.ic_ext_taken += h_cnt;
+}
+
+void ic_particles_finish(Ctx &c, double normfac, const double *rescale_by_k2, size_t n) {
+  REQUIRE(c.ic_ext_open, MGP_ERR_STATE, "mgp_ic_particles_finish: call mgp_ic_particles_begin first");
+  const size_t mmax = (size_t) 3 * (c.N / 2) * (c.N / 2) + 1;
+  REQUIRE(rescale_by_k2 != nullptr && n >= mmax, MGP_ERR_INVALID, "mgp_ic_particles_finish: rescale_by_k2 must hold 3 (Nmesh/2)^2 + 1 entries");
+  c.ic_ext_open = false;
+  halo_add_density(c, MGP_GRID_DENSITY);            // ghost plane -> right neighbour's plane 0, "+ 1" (readICfromfile.c:630-637)
+  fft_r2c(c, MGP_GRID_DENSITY);
+  mgp_ic_config ic;
+  memset(&ic, 0, sizeof(ic));
+  if (c.gbytes == 4) ic_generate_t<float>(c, &ic, rescale_by_k2, normfac); else ic_generate_t<double>(c, &ic, rescale_by_k2, normfac);
 }
 
 void ic_init_particles(Ctx &c, double Di, double Di2, double dDdy, double dD2dy) {

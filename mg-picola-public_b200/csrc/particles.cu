@@ -215,6 +215,88 @@ void particles_download(Ctx &c, float *pos, float *vel, float *D, float *D2, uin
 }
 
 
+// ------------------------------------------------------------------ snapshot blocks (Output, main.c:915-997)
+
+// The three GADGET blocks of this rank's particles exactly as Output() forms them:
+//   pos[k] = (float)(lengthfac * Pos[k])                                                              (main.c:946)
+//   vel[k] = (float)(velfac * fac * (Vel[k] - sumxyz[k] + (D[k] dDdy + D2[k] dD2dy) * UseCOLA))        (main.c:966-967)
+//   SCALEDEPENDENT:                 ... + (P.dDdy[k] + P.dD2dy[k]) * UseCOLA   with the float sum      (main.c:962-963)
+//   id                                                                                                (main.c:985)
+// double arithmetic without contraction, in C's association order, so that the floats are the reference's.
+template <int SD>
+__global__ void __launch_bounds__(256)
+k_snapshot(size_t n, size_t off, const float4 *__restrict__ pA, const float4 *__restrict__ pB, const float4 *__restrict__ pC,
+           const float2 *__restrict__ pE, const float *__restrict__ f1, const float *__restrict__ f2, size_t cap,
+           double lengthfac, double vfac, double s0, double s1, double s2, double dDdy, double dD2dy, int usecola,
+           float *__restrict__ pos, float *__restrict__ vel, unsigned long long *__restrict__ id) {
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+    const size_t j = off + i;
+    const float4 a = pA[j], b = pB[j];
+    pos[3 * i] = (float) __dmul_rn(lengthfac, (double) a.x);
+    pos[3 * i + 1] = (float) __dmul_rn(lengthfac, (double) a.y);
+    pos[3 * i + 2] = (float) __dmul_rn(lengthfac, (double) a.z);
+    double l0, l1, l2;
+    if (SD) {
+      const float g0 = f2 ? f2[j] : 0.0f, g1 = f2 ? f2[cap + j] : 0.0f, g2 = f2 ? f2[2 * cap + j] : 0.0f;
+      l0 = (double) __fmul_rn(__fadd_rn(f1[j], g0), (float) usecola);
+      l1 = (double) __fmul_rn(__fadd_rn(f1[cap + j], g1), (float) usecola);
+      l2 = (double) __fmul_rn(__fadd_rn(f1[2 * cap + j], g2), (float) usecola);
+    } else {
+      const float4 d = pC[j];
+      const float2 e = pE[j];
+      l0 = __dmul_rn(__dadd_rn(__dmul_rn((double) d.x, dDdy), __dmul_rn((double) d.w, dD2dy)), (double) usecola);
+      l1 = __dmul_rn(__dadd_rn(__dmul_rn((double) d.y, dDdy), __dmul_rn((double) e.x, dD2dy)), (double) usecola);
+      l2 = __dmul_rn(__dadd_rn(__dmul_rn((double) d.z, dDdy), __dmul_rn((double) e.y, dD2dy)), (double) usecola);
+    }
+    vel[3 * i] = (float) __dmul_rn(vfac, __dadd_rn(__dsub_rn((double) b.x, s0), l0));
+    vel[3 * i + 1] = (float) __dmul_rn(vfac, __dadd_rn(__dsub_rn((double) b.y, s1), l1));
+    vel[3 * i + 2] = (float) __dmul_rn(vfac, __dadd_rn(__dsub_rn((double) b.z, s2), l2));
+    id[i] = ((unsigned long long) __float_as_uint(b.w) << 32) | (unsigned long long) __float_as_uint(a.w);
+  }
+}
+
+// Packs chunk by chunk into the staging area; chunk c + 1 is packed while chunk c crosses PCIe (asynchronous when the host
+// buffers are pinned, e.g. from mgp_alloc_host).
+void particles_snapshot(Ctx &c, double lengthfac, double vfac, const double sumxyz[3], double dDdy, double dD2dy, float *pos,
+                        float *vel, uint64_t *id) {
+  const size_t n = c.np;
+  if (!n) return;
+  const size_t ch = n < kChunk ? n : kChunk;
+  float *base = stage_buffer(c, ch);
+  const size_t rec = ch * (12 * sizeof(float) + sizeof(uint64_t));
+  cudaEvent_t drained[2] = {c.stage_ev[0], c.stage_ev[1]};
+  cudaEvent_t packed;
+  CK(cudaEventCreateWithFlags(&packed, cudaEventDisableTiming));
+  const bool sd = c.cfg.scale_dependent != 0;
+  int it = 0;
+  for (size_t off = 0; off < n; off += ch, it++) {
+    const int b = it & 1;
+    float *st = (float *) ((char *) base + (size_t) b * rec);
+    float *s_pos = st, *s_vel = st + 3 * ch;
+    unsigned long long *s_id = (unsigned long long *) (st + 12 * ch);
+    const size_t m = (n - off) < ch ? (n - off) : ch;
+    if (it >= 2) CK(cudaStreamWaitEvent(c.stream, drained[b], 0));          // buffer b copied out
+    if (sd)
+      k_snapshot<1><<<grid_for(m, 256), 256, 0, c.stream>>>(m, off, c.pA, c.pB, nullptr, nullptr, c.sdf[2],
+                                                           c.sd_zero[3] ? nullptr : c.sdf[3], c.cap, lengthfac, vfac, sumxyz[0],
+                                                           sumxyz[1], sumxyz[2], dDdy, dD2dy, c.cfg.use_cola, s_pos, s_vel, s_id);
+    else
+      k_snapshot<0><<<grid_for(m, 256), 256, 0, c.stream>>>(m, off, c.pA, c.pB, c.pC, (const float2 *) c.pE, nullptr, nullptr, c.cap,
+                                                           lengthfac, vfac, sumxyz[0], sumxyz[1], sumxyz[2], dDdy, dD2dy,
+                                                           c.cfg.use_cola, s_pos, s_vel, s_id);
+    c.launches++;
+    CK(cudaEventRecord(packed, c.stream));
+    CK(cudaStreamWaitEvent(c.copy_stream, packed, 0));
+    CK(cudaMemcpyAsync(pos + 3 * off, s_pos, m * 12, cudaMemcpyDeviceToHost, c.copy_stream));
+    CK(cudaMemcpyAsync(vel + 3 * off, s_vel, m * 12, cudaMemcpyDeviceToHost, c.copy_stream));
+    CK(cudaMemcpyAsync(id + off, s_id, m * 8, cudaMemcpyDeviceToHost, c.copy_stream));
+    CK(cudaEventRecord(drained[b], c.copy_stream));
+  }
+  CK(cudaStreamSynchronize(c.copy_stream));
+  CK(cudaStreamSynchronize(c.stream));
+  CK(cudaEventDestroy(packed));
+}
+
 // ------------------------------------------------------------------ [3][cap] device arrays <-> [n][3] host arrays
 
 __global__ void k_soa3_to_aos(size_t n, size_t off, const float *__restrict__ soa, size_t cap, float m0, float m1, float m2,

@@ -610,3 +610,129 @@ def rsd_velocity(vel, D, D2, axis, use_cola, dDdy, dD2dy, scale_dependent=False)
     if scale_dependent:
         return (v + (D[:, axis] + D2[:, axis]).astype(np.float32)).astype(np.float32).astype(np.float64)
     return v.astype(np.float64) + (D[:, axis].astype(np.float64) * dDdy + D2[:, axis].astype(np.float64) * dD2dy)
+
+
+# ----------------------------------------------------------------------------- SimplePofk (post-processing tool)
+
+def simple_pofk(pos, ngrid, box, scheme="CIC", subtract_shotnoise=False):
+    """SimplePofk/main.cpp restated (the reference's stand-alone P(k) estimator; the only user of NGP and TSC):
+    positions as GADGET floats, x = double(pos_float / boxsize) (main.cpp:259-261); assignment add_to_grid_NGP / _CIC /
+    _TSC (59-228) of raw counts (no mean subtraction, no normalisation); complex 3-D transform; per mode
+    |d_k|^2 / N^6 / window^2 with window = prod_a sinc(pi k_a / N) to the power 1 / 2 / 3 (324-340, 393); bin
+    int(|k| + 0.5) for 0 < bin < N (391); mean per bin, optional shot noise 1 / Npart (420-424).
+    TSC reproduces the tool as written, including its three `izneighN` where the weight PZ belongs to `izneighP`
+    (main.cpp:189, 201, 213: the "010", "110", "210" lines).  Returns (pofk[N], nmodes[N]); the tool prints
+    k = (2 i + 1) pi / boxsize and pofk[i] * boxsize^3 for 1 <= i <= N / 2 (436-444).
+    PARITY UNPINNED against a compiled SimplePofk: the tool needs FFTW's complex 3-D plan and OpenMP, which the image does
+    not have; this restatement is what the CUDA path is checked against."""
+    N = int(ngrid)
+    p = np.asarray(pos, dtype=np.float32)
+    x = (p.astype(np.float64) / np.float64(box))
+    X = x * N
+    I = X.astype(np.int64)
+    Dd = X - I
+    I = np.where(I >= N, I - N, I)
+    grid = np.zeros((N, N, N))                      # grid[ix, iy, iz]; the tool stores ix fastest, P(k) does not care
+
+    def add(ix, iy, iz, w):
+        np.add.at(grid, (ix, iy, iz), w)
+    ix, iy, iz = I[:, 0], I[:, 1], I[:, 2]
+    if scheme == "NGP":
+        add(ix, iy, iz, np.ones(len(p)))
+        power = 1
+    elif scheme == "CIC":
+        nb = [np.where(I[:, a] + 1 >= N, I[:, a] + 1 - N, I[:, a] + 1) for a in range(3)]
+        T, Dw = 1.0 - Dd, Dd
+        for ax, wx in ((ix, T[:, 0]), (nb[0], Dw[:, 0])):
+            for ay, wy in ((iy, T[:, 1]), (nb[1], Dw[:, 1])):
+                for az, wz in ((iz, T[:, 2]), (nb[2], Dw[:, 2])):
+                    add(ax, ay, az, wx * wy * wz)
+        power = 2
+    elif scheme == "TSC":
+        Tw = 0.75 - Dd * Dd
+        Nw = 0.5 * (0.5 + Dd) * (0.5 + Dd)
+        Pw = 0.5 * (0.5 - Dd) * (0.5 - Dd)
+        nN = [np.where(I[:, a] + 1 >= N, I[:, a] + 1 - N, I[:, a] + 1) for a in range(3)]
+        nP = [np.where(I[:, a] - 1 < 0, I[:, a] - 1 + N, I[:, a] - 1) for a in range(3)]
+        cx = ((nP[0], Pw[:, 0]), (ix, Tw[:, 0]), (nN[0], Nw[:, 0]))
+        cy = ((nP[1], Pw[:, 1], "P"), (iy, Tw[:, 1], "T"), (nN[1], Nw[:, 1], "N"))
+        for ax, wx in cx:
+            for ay, wy, ytag in cy:
+                # the z triple: previous, this, next -- except that on the "this y" lines the previous-z weight lands on next z
+                zP = nN[2] if ytag == "T" else nP[2]
+                add(ax, ay, zP, wx * wy * Pw[:, 2])
+                add(ax, ay, iz, wx * wy * Tw[:, 2])
+                add(ax, ay, nN[2], wx * wy * Nw[:, 2])
+        power = 3
+    else:
+        raise ValueError(scheme)
+    dk = np.fft.fftn(grid)
+    k1 = np.arange(N)
+    kk = np.where(k1 < N // 2, k1, k1 - N)
+    ii, jj, ll = np.meshgrid(kk, kk, kk, indexing="ij")
+    kind = (np.sqrt((ii * ii + jj * jj + ll * ll).astype(np.float64)) + 0.5).astype(np.int64)
+    fac = np.pi / N
+
+    def sinc(k):
+        a = k * fac
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return np.where(k != 0, np.sin(a) / np.where(k != 0, a, 1.0), 1.0)
+    w = (sinc(ii) * sinc(jj) * sinc(ll)) ** power
+    val = (dk.real ** 2 + dk.imag ** 2) * (1.0 / float(N) ** 3) ** 2 / (w * w)
+    sel = (kind < N) & (kind > 0)
+    pofk = np.bincount(kind[sel], weights=val[sel], minlength=N).astype(np.float64)
+    nmodes = np.bincount(kind[sel], minlength=N).astype(np.float64)
+    good = nmodes > 0
+    pofk[good] /= nmodes[good]
+    if subtract_shotnoise:
+        pofk -= 1.0 / float(len(p))
+    return pofk, nmodes
+
+
+# ----------------------------------------------------------------------------- READICFROMFILE
+
+def readic_delta_k(pos01_files, nmesh, nsample, normfac, rescale_by_k2, grid_dtype=np.float64):
+    """ReadFilesMakeDisplacementField + AssignDisplacementField restated for one task (readICfromfile.c:133-215,
+    533-778): CIC of the external particles (coordinates in [0, 1), X = pos * Nmesh, W = (Nmesh/Nsample)^3) onto a grid
+    that starts at -1, the ghost plane folded onto plane 0 (630-637), r2c, density *= normfac (642-646), sharp-k filter
+    above Nsample/2 when Nmesh > Nsample (648-680), and cdelta_cdm = P3D * grid_corr * rescale_fac with the CIC window
+    grid_corr = prod_a (sin(pi d_a / N) / (pi d_a / N))^-2 (724-750).  Returns delta_k [N][N][N/2+1]; mode 0 is 0.
+    PARITY UNPINNED against a compiled -DREADICFROMFILE build (it needs particle files of an external code); checked
+    piecewise: the deposit is PtoMesh's (pinned), the transform is pinned, the rest is pointwise."""
+    N = int(nmesh)
+    W = (float(nmesh) / float(nsample)) ** 3
+    dens = np.full((N + 1, N, N), -1.0)
+    for pos in pos01_files:
+        p = np.asarray(pos, dtype=np.float32).astype(np.float64) * float(N)
+        I = p.astype(np.uint32).astype(np.int64)
+        D = p - I
+        T = 1.0 - D
+        ix = I[:, 0]
+        iy = np.where(I[:, 1] >= N, 0, I[:, 1])
+        iz = np.where(I[:, 2] >= N, 0, I[:, 2])
+        iy1 = np.where(iy + 1 >= N, 0, iy + 1)
+        iz1 = np.where(iz + 1 >= N, 0, iz + 1)
+        Dy, Ty = D[:, 1] * W, T[:, 1] * W
+        for ax, wx in ((ix, T[:, 0]), (ix + 1, D[:, 0])):
+            for ay, wy in ((iy, Ty), (iy1, Dy)):
+                for az, wz in ((iz, T[:, 2]), (iz1, D[:, 2])):
+                    np.add.at(dens, (ax, ay, az), wx * wy * wz)
+    dens[0] += dens[N] + 1.0                                   # the slice from the left task: density += temp + 1
+    g = dens[:N].astype(grid_dtype)
+    dk = np.fft.rfftn(g.astype(np.float64)).astype(np.complex64 if grid_dtype == np.float32 else np.complex128)
+    dk = (dk * normfac).astype(dk.dtype)
+    k1 = np.arange(N)
+    d0 = np.where(k1 > N // 2, k1 - N, k1)
+    dd0, dd1, dd2 = np.meshgrid(d0, d0, np.arange(N // 2 + 1), indexing="ij")
+    m = dd0 * dd0 + dd1 * dd1 + dd2 * dd2
+    if nmesh > nsample:
+        dk = np.where(np.sqrt(m.astype(np.float64)) > float(nsample // 2), 0.0, dk)
+
+    def sinc(d):
+        a = PI * d / float(N)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return np.where(d != 0, np.sin(a) / np.where(d != 0, a, 1.0), 1.0)
+    gc = (1.0 / (sinc(dd0) * sinc(dd1) * sinc(dd2))) ** 2
+    out = (dk.astype(np.complex128) * gc) * np.asarray(rescale_by_k2, dtype=np.float64)[m]
+    out[0, 0, 0] = 0.0
+    return out

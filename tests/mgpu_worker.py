@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--ic", action="store_true", help="generate the golden-fixture ICs on the ranks instead of stepping")
     ap.add_argument("--sd", action="store_true", help="scale-dependent run of tests/golden/sd_fofr.npz on the ranks")
     ap.add_argument("--merged", action="store_true")
+    ap.add_argument("--sort-interval", type=int, default=1, help="sort_particles of the context (>= 3: the hole compaction of "
+                    "MoveParticles runs between sorts)")
     a = ap.parse_args()
     import torch
     import mgpicola_b200 as mgp
@@ -49,7 +51,7 @@ def main():
         N, box, om = int(g["N"]), float(g["box"]), float(g["omega"])
         nid = mdist.share_from_rank0(mgp.nccl_unique_id)
         pm = mgp.PM(N, N, box, omega=om, model=mgp.MODEL_FOFR, include_screening=1, grid_bytes=a.gb, scale_dependent=1, buffer=2.5,
-                    rank=rank, nranks=world, device=local, nccl_id=nid)
+                    rank=rank, nranks=world, device=local, nccl_id=nid, deposit_mode=a.mode, sort_particles=a.sort_interval)
         c = g["pofk_cfg"]
         pm.set_pofk(int(c[0]), int(c[1]), int(c[2]), float(c[3]), float(c[4]))
         pm.ic_generate(g["power_by_k2"], seed=int(g["seed"]))            # keeps delta1_k / delta2_k, transposed slabs
@@ -84,7 +86,7 @@ def main():
     nid = mdist.share_from_rank0(mgp.nccl_unique_id)
     mid = {"lcdm": mgp.MODEL_NONE, "fofr": mgp.MODEL_FOFR, "dgp": mgp.MODEL_DGP}[a.model]
     pm = mgp.PM(N, N, box, omega=om, model=mid, include_screening=1, grid_bytes=a.gb, deposit_mode=a.mode, buffer=2.5,
-                rank=rank, nranks=world, device=local, nccl_id=nid)
+                rank=rank, nranks=world, device=local, nccl_id=nid, sort_particles=a.sort_interval)
     pm.set_pofk(16, 0, 1, 0.0, 0.0)
     pm.upload_particles(pos[mine], vel[mine], D[mine], D2[mine], ids[mine])
     pks = []

@@ -132,10 +132,7 @@ def test_driver_on_ranks_matches_cpu_reference_on_ranks(require_gpu, tmp_path, v
     (adapter/_build/MG_PICOLA_CUDA_<v>_mp, ranks = processes of the multi-process MPI stand-in, NCCL id handed round
     with MPI_Bcast) against the unmodified CPU reference on the same number of ranks: every P(k) file, and per rank
     the snapshot file -- the SAME particle IDs on the same rank (slab ownership, auxPM.c:151-153) at positions within
-    the single-GPU tolerance.
-    Written after this round's last GPU slot: opt-in (MGP_TEST_MULTIRANK_DRIVER=1) until it has had its first run."""
-    if os.environ.get("MGP_TEST_MULTIRANK_DRIVER", "0") != "1":
-        pytest.skip("first GPU run pending: set MGP_TEST_MULTIRANK_DRIVER=1")
+    the single-GPU tolerance.  Every rank takes GPU `rank % device count` by itself (adapter/auxPM_cuda.c)."""
     import torch
     if torch.cuda.device_count() < ranks:
         pytest.skip("needs %d GPUs" % ranks)
@@ -149,8 +146,7 @@ def test_driver_on_ranks_matches_cpu_reference_on_ranks(require_gpu, tmp_path, v
             pytest.skip("%s not built (needs /root/reference at build time)" % exe[kind])
         wd = str(tmp_path / kind)
         pf = bench.write_paramfile(wd, N, box, model, nsteps, lcdm_growth=lcdm_growth)
-        rc, so, errs = mprun.run([exe[kind], pf], ranks, scratch_mb=mprun.scratch_mb_for(N), timeout=900, cwd=wd,
-                                 rank_env=(lambda r: {"MGP_DEVICE": str(r)}) if kind == "gpu" else None)
+        rc, so, errs = mprun.run([exe[kind], pf], ranks, scratch_mb=mprun.scratch_mb_for(N), timeout=900, cwd=wd)
         assert rc == 0, (kind, rc, so[-2000:], errs)
         out[kind] = os.path.join(wd, "output")
     shot = (box / N) ** 3

@@ -98,6 +98,35 @@ def test_slab_decomposed_steps_match_oracle(require_gpu, tmp_path, world, model,
         assert int(r["launches"]) > 20
 
 
+@pytest.mark.parametrize("world,mode,compact", [(2, 0, "1"), (2, 0, "0"), (2, 3, "1"), (8, 0, "1")])
+def test_migration_between_sorts_matches_oracle(require_gpu, tmp_path, world, mode, compact):
+    """The production particle path: sort_particles = 4 and the ATOMIC (or ROWS) deposit, five steps, so that MoveParticles
+    closes the holes of the leavers by compaction (k_compact_lists / k_compact_move, MGP_COMPACT = 1) on the steps between
+    two sorts -- unsorted order, shrinking counts, stale row offsets -- and, with MGP_COMPACT = 0, through a full sort
+    every time.  Same oracle comparison as the sorted path: IDs a permutation, ownership, positions, velocities, P(k)."""
+    if _ngpu() < world:
+        pytest.skip("needs %d GPUs" % world)
+    from mgpicola_b200 import slab
+    N, steps, box = 32, 5, 100.0
+    ranks = _run(world, tmp_path, N, steps, "fofr", 8, mode, extra=["--sort-interval", "4"], env={"MGP_COMPACT": compact})
+    pos, vel, pks = _oracle(N, steps, "fofr")
+    all_ids = np.concatenate([r["id"] for r in ranks])
+    assert np.array_equal(np.sort(all_ids), np.arange(N ** 3, dtype=np.uint64))
+    for k, r in enumerate(ranks):
+        assert (slab.owner_of(r["pos"][:, 0], N, box, world) == k).all()
+        ids = r["id"].astype(np.int64)
+        dp = np.abs(r["pos"].astype(np.float64) - pos[ids])
+        dp = np.minimum(dp, box - dp)
+        assert dp.max() < 5e-5 * box / N
+        assert np.abs(r["vel"] - vel[ids]).max() < 2e-5 * np.abs(vel).max()
+        for it in range(steps):
+            p, kk, n = r["pks"][it]
+            assert np.array_equal(n, pks[it][2])                     # mode counts: exact
+            good = n > 0
+            rel = np.abs(p[good] - pks[it][0][good]) / (np.abs(pks[it][0][good]) + (box / N) ** 3)
+            assert rel.max() < 1e-9                                  # mass conservation shows here first
+
+
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_distributed_ic_matches_reference(require_gpu, tmp_path, world):
     """displacement_fields() on P slabs (transposed k-space, distributed FFTs, displacement halos) ==
@@ -127,7 +156,8 @@ def test_scale_dependent_run_on_slabs(require_gpu, tmp_path, world, merged):
         pytest.skip("needs %d GPUs" % world)
     g = dict(np.load(os.path.join(ROOT, "tests", "golden", "sd_fofr.npz")))
     N, box = int(g["N"]), float(g["box"])
-    ranks = _run(world, tmp_path, N, 0, "fofr", 8, 0, extra=["--sd"] + (["--merged"] if merged else []))
+    # merged: the production settings as well (no sort on most steps, hole compaction, request lists rebuilt per order)
+    ranks = _run(world, tmp_path, N, 0, "fofr", 8, 0, extra=["--sd"] + (["--merged", "--sort-interval", "4"] if merged else []))
     assert np.array_equal(np.concatenate([r["id0"] for r in ranks]), g["id0"])
     dp = np.abs(np.concatenate([r["pos0"] for r in ranks]).astype(np.float64) - g["pos0"])
     assert np.minimum(dp, box - dp).max() < 1e-5
