@@ -385,7 +385,10 @@ static void sd_assign_t(Ctx &c, int fieldtype, int order, const double *g1, cons
   double mean[3] = {0, 0, 0};
   // N == Nsample: the lattice sum is the k = 0 mode of the transform, which k_sd_field set to zero; the
   // reference subtracts the FFT's rounding noise (|mean| ~ 1e-17 of the rms).  Skipped in merged mode.
-  const bool skip_mean = merged && (N % ns == 0);
+  // N == 2 Nsample: the sub-lattice sum aliases the modes with every component a multiple of Nsample = N/2, which are
+  // self-conjugate and therefore real in k-space, so that i k / k^2 times them drops out of the c2r: zero as well.
+  // Any other ratio (N = 3 Nsample ...) aliases modes the second-order field does populate: the mean is computed.
+  const bool skip_mean = merged && (N == ns || N == 2 * ns);
   if (!skip_mean) {
     PhaseTimer t(c, PH_SDASSIGN);
     const unsigned gp = grid_for(nloc ? nloc : 1, 256, 8);

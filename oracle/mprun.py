@@ -1,4 +1,4 @@
-"""Launcher of the multi-process MPI stand-in (oracle/shim/shim_mpi_mp.c): starts `nranks` copies of a reference
+"""Launcher of the multi-process MPI stand-in (standins/shim_mpi_mp.c): starts `nranks` copies of a reference
 executable built with it (oracle/_ref/MG_PICOLA_<variant>_mp), all mapping one zero-filled file under /dev/shm.
 
 TEST INFRASTRUCTURE ONLY: the CPU baseline of bench.py (the reference's multi-rank path on the box's host cores) and a

@@ -1,5 +1,5 @@
 """ctypes driver for oracle/_ref/libmgpicola_ref_<variant>.so -- the UNMODIFIED reference sources
-compiled against the stand-ins of oracle/shim (see oracle/Makefile).
+compiled against the stand-ins of standins (see oracle/Makefile).
 
 TEST INFRASTRUCTURE ONLY.  Used to (a) pin oracle/pm_oracle.py against the reference's own code,
 (b) generate the committed fixtures in tests/golden/ (oracle/make_golden.py) and (c) time the

@@ -1,7 +1,7 @@
 /*
  * Stand-in for <fftw3.h> (+ the fftw_mpi_* slab API in fftw3-mpi.h).
  * TEST INFRASTRUCTURE ONLY: lets the unmodified reference compile without FFTW
- * (SURVEY.md section 0).  Backed by oracle/shim/shim_fft.c, a self-contained
+ * (SURVEY.md section 0).  Backed by standins/shim_fft.c, a self-contained
  * CPU FFT.  Semantics reproduced: unnormalised transforms, in-place padded
  * r2c/c2r layout [x][y][2*(n2/2+1)], c2r = c2c over x,y then c2r over z with the
  * imaginary parts of the kz = 0 and kz = n2/2 inputs ignored (FFTW behaviour).

@@ -1,6 +1,6 @@
 /*
  * Multi-process stand-in for <mpi.h>: the ranks are processes started by oracle/mprun.py that share one
- * memory segment (oracle/shim/shim_mpi_mp.c).  TEST INFRASTRUCTURE ONLY.  Differs from the serial header
+ * memory segment (standins/shim_mpi_mp.c).  TEST INFRASTRUCTURE ONLY.  Differs from the serial header
  * (../include/mpi.h) in one thing: a datatype carries its KIND as well as its size, because reductions over
  * several ranks must know whether 4 bytes are an int or a float.
  *

@@ -1,4 +1,4 @@
-"""The multi-process MPI stand-in (oracle/shim/shim_mpi_mp.c + shim_fft_mp.c, started by oracle/mprun.py) runs the
+"""The multi-process MPI stand-in (standins/shim_mpi_mp.c + shim_fft_mp.c, started by oracle/mprun.py) runs the
 UNMODIFIED reference driver on several ranks -- x-slabs, halo exchanges, hop-by-hop particle migration, the
 request / response exchange of the SCALEDEPENDENT displacement fields.  Pinned here against the one-rank run of the same
 executable: in double precision every rank count must reproduce it bit for bit (reductions add in rank order, the
