@@ -500,7 +500,6 @@ int mgp_mtoparticles(mgp_ctx *ctx, double sumDxyz[3]) {
   REQUIRE(sumDxyz != nullptr, MGP_ERR_INVALID, "mgp_mtoparticles: sumDxyz is NULL");
   gather_forces(c, sumDxyz);
   c.forces_live = false;
-  rows_prefill(c, needs_mg_arrays(c) && !c.slab ? MGP_GRID_MG_TWO : MGP_GRID_DENSITY);
   API_END
 }
 

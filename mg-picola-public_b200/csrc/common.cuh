@@ -132,7 +132,6 @@ struct Ctx {
   uint32_t *bin_start = nullptr;   // [nbins + 2] offsets into bin_perm; bin = (x-plane, y-row, z-chunk)
   int bin_zc = 0, bin_nc = 1;      // cells per z-chunk, chunks per row
   size_t nbins = 0;
-  int prefilled_grid = -1;
   void *bin_scan_temp = nullptr;
   size_t bin_scan_bytes = 0;
   bool bins_valid = false;         // bins describe the current positions and storage order
@@ -255,7 +254,6 @@ void deposit_rsd(Ctx &c, int grid_id, int axis, double vnorm, double dDdy, doubl
 void rows_alloc(Ctx &c);
 void rows_free(Ctx &c);
 void rows_bin(Ctx &c);
-void rows_prefill(Ctx &c, int grid_id);
 void deposit_rows(Ctx &c, int grid_id);
 bool deposit_rows_supported(const Ctx &c);
 bool gather_rows_supported(const Ctx &c);

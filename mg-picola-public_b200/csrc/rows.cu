@@ -225,13 +225,6 @@ k_deposit_tiles(const float4 *__restrict__ pA, const uint32_t *__restrict__ perm
   tma::wait_all();
 }
 
-void rows_prefill(Ctx &c, int grid_id) {
-  static const bool on = getenv("MGP_DEBUG_EARLYFILL") != nullptr;
-  if (!on || c.gbytes != 8 || c.cfg.deposit_mode != MGP_DEPOSIT_ROWS) return;
-  k_fill_rows<<<grid_for(c.grid_vals, 256), 256, 0, c.stream>>>((double *) c.grid[grid_id], c.grid_vals, -1.0);
-  c.prefilled_grid = grid_id;
-}
-
 bool deposit_rows_supported(const Ctx &c) { return c.bin_perm != nullptr && c.gbytes == 8; }
 
 void deposit_rows(Ctx &c, int grid_id) {
@@ -247,13 +240,8 @@ void deposit_rows(Ctx &c, int grid_id) {
     CK(cudaFuncSetAttribute(k_deposit_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
     attr_sm = sm;
   }
-  // timing experiment: the fill of this call was issued long ago (rows_prefill), its dirty lines have left L2
-  const bool nofill = c.prefilled_grid == grid_id;
-  c.prefilled_grid = -1;
-  if (!nofill) {
-    k_fill_rows<<<grid_for(c.grid_vals, 256), 256, 0, c.stream>>>(grid, c.grid_vals, -1.0);
-    c.launches++;
-  }
+  k_fill_rows<<<grid_for(c.grid_vals, 256), 256, 0, c.stream>>>(grid, c.grid_vals, -1.0);
+  c.launches++;
   if (!c.np) return;
   static int occ = 0;             // host-side query: once (the launch sits right behind a host synchronisation)
   static size_t occ_sm = 0;

@@ -23,7 +23,7 @@ for stage in "$@"; do
       tail -c 3000 gpurun_out/${TAG}_bench_${BNAME:-default}.json; tail -3 gpurun_out/${TAG}_bench_${BNAME:-default}.err ;;
     benchmodes)        # deposit strategies at $NMESH (device step only)
       for m in ${MODES:-0 2}; do
-        timeout 400 python bench.py --nmesh ${NMESH:-512} --steps 8 --warmup 4 --no-e2e --no-cpu-baseline --deposit-mode $m $BARGS \
+        timeout 400 python bench.py --nmesh ${NMESH:-512} --steps 8 --warmup 4 --no-e2e --no-cpu-baseline --no-parity --deposit-mode $m $BARGS \
           > gpurun_out/${TAG}_bench_${NMESH:-512}_mode$m.json 2> gpurun_out/${TAG}_bench_${NMESH:-512}_mode$m.err
         python - <<PY
 import json
@@ -36,11 +36,11 @@ PY
       done ;;
     launches)          # ncu launch list of one bench step (shares, not absolutes)
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c ${NCU_C:-400} --csv --log-file gpurun_out/${TAG}_launches.csv \
-        python bench.py --nmesh ${NMESH:-512} --steps 1 --warmup 1 --no-e2e --no-cpu-baseline ${BARGS} > gpurun_out/${TAG}_launches.log 2>&1
+        python bench.py --nmesh ${NMESH:-512} --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-parity ${BARGS} > gpurun_out/${TAG}_launches.log 2>&1
       tail -2 gpurun_out/${TAG}_launches.log ;;
     ncufull)           # ncu --set full of the kernels matching $KREGEX
       timeout 900 ncu --set full --clock-control none --import-source on -k "regex:${KREGEX}" -s ${NCU_S:-0} -c ${NCU_C:-6} -f -o gpurun_out/${TAG}_${NCU_NAME:-prof} \
-        python bench.py --nmesh ${NMESH:-512} --steps 1 --warmup 1 --no-e2e --no-cpu-baseline ${BARGS} > gpurun_out/${TAG}_ncufull.log 2>&1
+        python bench.py --nmesh ${NMESH:-512} --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-parity ${BARGS} > gpurun_out/${TAG}_ncufull.log 2>&1
       tail -2 gpurun_out/${TAG}_ncufull.log ;;
     mgpu_tests)        # multi-GPU parity on $NG GPUs, several tests at a time (tiny problems share the GPUs)
       timeout ${MGPU_TIMEOUT:-900} python -m pytest tests/test_multi_gpu.py -q -m gpu -p no:cacheprovider -n ${XDIST:-4} ${K:+-k "$K"} \
