@@ -93,7 +93,7 @@ struct Ctx {
   // x-transform fused with the slab exchange (xfft.cuh): power-of-two Nmesh on the peer-memory path
   bool xf_on = false;
   int xf_lgn = 0, xf_lgnxb = 0;                // log2 Nmesh, log2 Local_nx
-  bool xf_wide = false;                        // wide-tile instances (xfft_wide.cu; opt-in MGP_XFFT_WIDE=1)
+  bool xf_wide = false;                        // wide-tile instances (xfft_wide.cu; default from Nmesh = 1024 on several ranks)
   bool xf_mixed = false;                       // Nmesh = 2^a 3^b 5^c instance (xfft_mixed.cu; opt-in MGP_XFFT_MIXED=1)
   void *xf_tw = nullptr;                       // twiddle tables of the passes (complex, grid precision)
   int xf_tk = 0, xf_grid = 0;                  // lines per tile, persistent grid size

@@ -200,8 +200,8 @@ static void xfft_setup(Ctx &c) {
   int lgn = 0;
   while ((1 << lgn) < c.N) lgn++;
   if ((1 << lgn) != c.N) {
-    // mesh sizes with factors 3 and 5 (the 2- and 4-GPU weak-scaling meshes 320 and 400): mixed-radix instances,
-    // opt-in until they have been timed on a GPU
+    // mesh sizes with factors 3 and 5 (320, 400, 640, 800): mixed-radix instances, parity-checked on the GPU
+    // (tests/test_slab_fused.py) but never timed on several ranks: opt-in
     const char *mx = getenv("MGP_XFFT_MIXED");
     if (mx && atoi(mx) != 0 && xfm_supported(c.N) && xfm_prepare(c)) { c.xf_mixed = true; c.xf_on = true; }
     return;

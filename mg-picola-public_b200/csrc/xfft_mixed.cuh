@@ -4,7 +4,7 @@
 // reversal absorbed by the exchange side, runs aligned to 128-byte lines); what changes is that strides are no longer
 // powers of two (constant divisions instead of shifts), that the radix set gains 5 and 3, and that the owner of an x-plane
 // is x / nxb.  OPT-IN (MGP_XFFT_MIXED=1): verified on the CPU by tests/host/xfft_mixed_emul.cu (thread-by-thread
-// emulation against a direct DFT), not yet timed on a GPU; the default for these sizes stays cuFFT's 1-D plan + the
+// emulation against a direct DFT), parity-checked on the GPU (tests/test_slab_fused.py), not yet timed on several ranks; the default for these sizes stays cuFFT's 1-D plan + the
 // transpose kernels.
 #pragma once
 

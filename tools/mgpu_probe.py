@@ -17,7 +17,7 @@ if world > 1:
     ids = [mgp.nccl_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
     nid = ids[0]
-N = int(sys.argv[1]) if len(sys.argv) > 1 else bench.WEAK_NMESH[world]
+N = int(sys.argv[1]) if len(sys.argv) > 1 else bench.DEFAULT_NMESH
 use_sd = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 box = bench.box_for(N)
 cos = cosmology.LCDM(bench.OMEGA, bench.Z_INIT)
