@@ -588,6 +588,74 @@ void mgp_adapter_drift(double dyyy, double deltaD, double deltaD2) {
   ck(mgp_drift(g_ctx, dyyy, deltaD, deltaD2, sumxyz), "mgp_drift");
 }
 
+#ifdef LIGHTCONE
+/* called (through adapter/lightcone_c.patch) from Drift_Lightcone in place of its particle loop (lightcone.c:392-471): the
+ * scalars, the exit-time tables and flag_replicates stay in lightcone.c, the rows come back in the layout Output_Lightcone
+ * (lightcone.c:482-565, unchanged) writes to the replicate files */
+void mgp_adapter_drift_lightcone(double A, double AFF, double dyyy, double da1, double da2, double dv1, double dv2,
+                                 double Rcomov_old, double Rcomov_new, double boundary, double lengthfac, double velfac_times_fac,
+                                 int ntab, const double *AL_tab, const double *da1_tab, const double *da2_tab, const double *dyyy_tab) {
+  static uint64_t cap = 4096;
+  if (g_host_is_newer) upload_host_particles();
+  const int nall = (Nrep_neg_x + Nrep_pos_x + 1) * (Nrep_neg_y + Nrep_pos_y + 1) * (Nrep_neg_z + Nrep_pos_z + 1);
+  int *ijk = my_malloc(sizeof(int) * 3 * (nall > 0 ? nall : 1)), *coords = my_malloc(sizeof(int) * (nall > 0 ? nall : 1));
+  int nrep = 0;
+  for (int i = -Nrep_neg_x; i <= Nrep_pos_x; i++)                              /* the order of lightcone.c:411-413 */
+    for (int j = -Nrep_neg_y; j <= Nrep_pos_y; j++)
+      for (int k = -Nrep_neg_z; k <= Nrep_pos_z; k++) {
+        const int coord = ((i + Nrep_neg_max[0]) * (Nrep_neg_max[1] + Nrep_pos_max[1] + 1) + (j + Nrep_neg_max[1])) *
+                              (Nrep_neg_max[2] + Nrep_pos_max[2] + 1) + (k + Nrep_neg_max[2]);
+        if (repflag[coord] == 0) { ijk[3 * nrep] = i; ijk[3 * nrep + 1] = j; ijk[3 * nrep + 2] = k; coords[nrep] = coord; nrep++; }
+      }
+  mgp_lightcone_step ls;
+  memset(&ls, 0, sizeof(ls));
+  ls.A = A; ls.AFF = AFF; ls.dyyy = dyyy; ls.da1 = da1; ls.da2 = da2; ls.dv1 = dv1; ls.dv2 = dv2;
+  for (int a = 0; a < 3; a++) ls.sumxyz[a] = sumxyz[a];
+  ls.rcomov_old = Rcomov_old; ls.rcomov_new = Rcomov_new;
+  ls.origin[0] = Origin_x; ls.origin[1] = Origin_y; ls.origin[2] = Origin_z;
+  ls.boundary = boundary; ls.lengthfac = lengthfac; ls.velfac_times_fac = velfac_times_fac;
+  ls.ntab = ntab; ls.al_tab = AL_tab; ls.da1_tab = da1_tab; ls.da2_tab = da2_tab; ls.dyyy_tab = dyyy_tab;
+  ls.nrep = nrep; ls.rep_ijk = ijk;
+  uint64_t *count = my_malloc(sizeof(uint64_t) * (nrep > 0 ? nrep : 1));
+  float *block = NULL;
+  for (;;) {
+    block = malloc(sizeof(float) * 6 * cap * (size_t) (nrep > 0 ? nrep : 1));
+    if (!block) FatalError((char *) "mgp_adapter_drift_lightcone: out of host memory for the lightcone block");
+    const int rc = mgp_drift_lightcone(g_ctx, &ls, cap, block, count);
+    if (rc == MGP_OK) break;
+    free(block);
+    if (rc != MGP_ERR_BUFFER) ck(rc, "mgp_drift_lightcone");
+    uint64_t most = 0;                                                         /* nothing moved: size the block and repeat */
+    for (int r = 0; r < nrep; r++) if (count[r] > most) most = count[r];
+    cap = most + most / 8 + 16;
+  }
+  unsigned int *pc = (unsigned int *) calloc(nall > 0 ? nall : 1, sizeof(unsigned int));
+  for (int r = 0; r < nrep; r++) Noutput[coords[r]] += (unsigned int) count[r];
+  /* Output_Lightcone indexes the block with 32-bit arithmetic (lightcone.c:563): hand it slices that stay below 2^32 floats */
+  const uint64_t lim = 0xffffffffull / (6ull * (uint64_t) (nrep > 0 ? nrep : 1));
+  if (cap <= lim) {
+    for (int r = 0; r < nrep; r++) pc[r] = (unsigned int) count[r];
+    Output_Lightcone(pc, (unsigned int) cap, block);
+  } else {
+    float *slice = malloc(sizeof(float) * 6 * lim * (size_t) nrep);
+    if (!slice) FatalError((char *) "mgp_adapter_drift_lightcone: out of host memory for the output slice");
+    for (uint64_t done = 0;; done += lim) {
+      int any = 0;
+      for (int r = 0; r < nrep; r++) {
+        const uint64_t left = count[r] > done ? count[r] - done : 0, take = left < lim ? left : lim;
+        pc[r] = (unsigned int) take;
+        if (take) { memcpy(slice + 6 * lim * (size_t) r, block + 6 * (cap * (size_t) r + done), sizeof(float) * 6 * take); any = 1; }
+      }
+      if (!any) break;
+      Output_Lightcone(pc, (unsigned int) lim, slice);
+    }
+    free(slice);
+  }
+  free(pc); free(block);
+  my_free(count); my_free(ijk); my_free(coords);
+}
+#endif
+
 void mgp_adapter_finish(void) {
   if (g_ctx) mgp_destroy(g_ctx);
   g_ctx = NULL;

@@ -252,6 +252,40 @@ int mgp_kick(mgp_ctx *ctx, double A, double dda, double ddDddy, double ddD2ddy,
  * when scale_dependent: P.dDdy / P.dD2dy hold the per-particle increments) */
 int mgp_drift(mgp_ctx *ctx, double dyyy, double deltaD, double deltaD2, const double sumxyz[3]);
 
+/* ---- lightcone (-DLIGHTCONE; lightcone.c:265-474) ---- */
+/* Drift_Lightcone: the drift of one step, done replicate by replicate so that every particle image that leaves the
+ * shrinking lightcone during [A, AFF] is written out at its interpolated exit position.  The scalar part stays on the
+ * host exactly as in lightcone.c:294-347 (set_lightcone, flag_replicates and the file writers are host C too); the
+ * particle loop (392-471) runs here.  Not available with scale_dependent (the reference refuses that build, Makefile:279). */
+typedef struct mgp_lightcone_step {
+  double A, AFF;             /* scale factor at the start / end of the drift */
+  double dyyy;               /* Sq(A, AFF, AF) (or the StdDA variants, lightcone.c:302-308) */
+  double da1, da2;           /* growth_D(AFF) - Di, growth_D2(AFF) - Di2 (310-311) */
+  double dv1, dv2;           /* growth_dDdy(AF), growth_dD2dy(AF) (315-316) */
+  double sumxyz[3];          /* mean velocity left by Kick */
+  double rcomov_old, rcomov_new;   /* Light / Hubble * SphiStd(A, 1), ... (AFF, 1) (286-287) */
+  double origin[3];          /* Origin_x, Origin_y, Origin_z */
+  double boundary;           /* 20 Mpc/h (283): a larger Delta_Pos component is the reference's FatalError (403-407) */
+  double lengthfac;          /* UnitLength_in_cm / 3.085678e24 */
+  double velfac_times_fac;   /* UnitVelocity_in_cm_per_s / 1e5 * Hubble / AF */
+  /* the exit-time lookup tables of lightcone.c:326-347: ntab nodes AL_tab (increasing) with da1_tab = growth_D(AL) - Di,
+   * da2_tab = growth_D2(AL) - Di2, dyyy_tab = Sq(A, AL, AF); the library builds gsl_interp_cspline's natural cubic
+   * splines through them (349-357) and evaluates them at every exit time */
+  int ntab;
+  const double *al_tab, *da1_tab, *da2_tab, *dyyy_tab;
+  /* replicates with repflag == 0 (flag_replicates, lightcone.c:62-189), as offsets (i, j, k) in the order of the
+   * reference's triple loop (411-413): rep_ijk[3 r .. 3 r + 2] */
+  int nrep;
+  const int *rep_ijk;
+} mgp_lightcone_step;
+/* how many particle images leave the lightcone in this step, per listed replicate (count[nrep]); changes nothing */
+int mgp_lightcone_count(mgp_ctx *ctx, const mgp_lightcone_step *ls, uint64_t *count);
+/* the drift itself: Pos = periodic_wrap(Pos + Delta_Pos) for every particle (468-470) and, for every image that leaves,
+ * one row {x, y, z [Mpc/h], vx, vy, vz [km/s]} of six floats at block[(r * cap + slot) * 6] exactly as lightcone.c:447-453
+ * forms it -- the layout Output_Lightcone (482-565) reads with blockmaxlen = cap.  count[r] = rows of replicate r.
+ * MGP_ERR_BUFFER (nothing moved) when a replicate needs more than cap rows: size cap from mgp_lightcone_count. */
+int mgp_drift_lightcone(mgp_ctx *ctx, const mgp_lightcone_step *ls, uint64_t cap, float *block, uint64_t *count);
+
 /* ---- P(k) (compute_pofk.c:71-271) ---- */
 int mgp_set_pofk_config(mgp_ctx *ctx, const mgp_pofk_config *pc);
 /* bins the k-space density currently in MGP_GRID_DENSITY; arrays sized mgp_pofk_nbins() */

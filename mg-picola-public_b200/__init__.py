@@ -49,6 +49,15 @@ class PofkConfig(C.Structure):
                 ("kmin", C.c_double), ("kmax", C.c_double)]
 
 
+class LightconeStep(C.Structure):
+    """mgp_lightcone_step (include/mgpicola.h): the host scalars and tables of Drift_Lightcone (lightcone.c:281-347)."""
+    _fields_ = [("A", C.c_double), ("AFF", C.c_double), ("dyyy", C.c_double), ("da1", C.c_double), ("da2", C.c_double),
+                ("dv1", C.c_double), ("dv2", C.c_double), ("sumxyz", C.c_double * 3), ("rcomov_old", C.c_double),
+                ("rcomov_new", C.c_double), ("origin", C.c_double * 3), ("boundary", C.c_double), ("lengthfac", C.c_double),
+                ("velfac_times_fac", C.c_double), ("ntab", C.c_int), ("al_tab", C.c_void_p), ("da1_tab", C.c_void_p),
+                ("da2_tab", C.c_void_p), ("dyyy_tab", C.c_void_p), ("nrep", C.c_int), ("rep_ijk", C.c_void_p)]
+
+
 class StepScalars(C.Structure):
     _fields_ = [("a", C.c_double), ("phi_crit", C.c_double), ("coupling", C.c_double), ("massterm2", C.c_double),
                 ("dgp_fac0", C.c_double), ("rsmooth", C.c_double), ("geff", C.c_double), ("compute_pofk", C.c_int),
@@ -105,6 +114,8 @@ def load_library(path=None):
     L.mgp_get_displacements.argtypes = [C.c_void_p, C.POINTER(StepScalars), dp]
     L.mgp_kick.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, dp, dp]
     L.mgp_drift.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, dp]
+    L.mgp_lightcone_count.argtypes = [C.c_void_p, C.POINTER(LightconeStep), C.c_void_p]
+    L.mgp_drift_lightcone.argtypes = [C.c_void_p, C.POINTER(LightconeStep), C.c_uint64, C.c_void_p, C.c_void_p]
     L.mgp_set_pofk_config.argtypes = [C.c_void_p, C.POINTER(PofkConfig)]
     L.mgp_pofk_nbins.argtypes = [C.c_void_p]
     L.mgp_compute_power_spectrum.argtypes = [C.c_void_p, dp, dp, dp]
@@ -366,6 +377,35 @@ class PM:
     def Drift(self, dyyy, deltaD, deltaD2, sumxyz=None):
         sv = (C.c_double * 3)(*(self.sumxyz if sumxyz is None else sumxyz))
         self._ck(self.L.mgp_drift(self.ctx, dyyy, deltaD, deltaD2, sv))
+
+    # ---- lightcone (lightcone.c:265-474) ----
+    def _lightcone_step(self, sc, reps, sumxyz):
+        keep = [np.ascontiguousarray(sc[k], dtype=np.float64) for k in ("al_tab", "da1_tab", "da2_tab", "dyyy_tab")]
+        reps = np.ascontiguousarray(reps, dtype=np.int32).reshape(-1, 3)
+        ls = LightconeStep(sc["A"], sc["AFF"], sc["dyyy"], sc["da1"], sc["da2"], sc["dv1"], sc["dv2"],
+                           (C.c_double * 3)(*(self.sumxyz if sumxyz is None else sumxyz)), sc["rcomov_old"], sc["rcomov_new"],
+                           (C.c_double * 3)(*sc["origin"]), sc.get("boundary", 20.0), sc["lengthfac"], sc["velfac_times_fac"],
+                           keep[0].size, keep[0].ctypes.data, keep[1].ctypes.data, keep[2].ctypes.data, keep[3].ctypes.data,
+                           reps.shape[0], reps.ctypes.data if reps.size else None)
+        return ls, (keep, reps)
+
+    def lightcone_count(self, sc, reps, sumxyz=None):
+        """How many particle images leave the lightcone in the step described by `sc`, per replicate of `reps`."""
+        ls, keep = self._lightcone_step(sc, reps, sumxyz)
+        cnt = np.zeros(max(ls.nrep, 1), np.uint64)
+        self._ck(self.L.mgp_lightcone_count(self.ctx, C.byref(ls), _ptr(cnt)))
+        return cnt[:ls.nrep]
+
+    def Drift_Lightcone(self, sc, reps, sumxyz=None, cap=None):
+        """The particle loop of Drift_Lightcone: drifts the particles and returns [rows of replicate r, float32 [count][6]]."""
+        ls, keep = self._lightcone_step(sc, reps, sumxyz)
+        if cap is None:
+            c0 = self.lightcone_count(sc, reps, sumxyz)
+            cap = int(c0.max()) if c0.size else 0
+        cnt = np.zeros(max(ls.nrep, 1), np.uint64)
+        block = np.zeros((max(ls.nrep, 1), max(cap, 1), 6), np.float32)
+        self._ck(self.L.mgp_drift_lightcone(self.ctx, C.byref(ls), cap, _ptr(block), _ptr(cnt)))
+        return [block[r, :int(cnt[r])].copy() for r in range(ls.nrep)]
 
     # ---- P(k) ----
     def set_pofk(self, nbins, bintype, subtract_shotnoise, kmin, kmax):

@@ -544,6 +544,20 @@ int mgp_drift(mgp_ctx *ctx, double dyyy, double deltaD, double deltaD2, const do
   API_END
 }
 
+int mgp_lightcone_count(mgp_ctx *ctx, const mgp_lightcone_step *ls, uint64_t *count) {
+  API_BEGIN
+  CTX(ctx);
+  lightcone_count(c, ls, count);
+  API_END
+}
+
+int mgp_drift_lightcone(mgp_ctx *ctx, const mgp_lightcone_step *ls, uint64_t cap, float *block, uint64_t *count) {
+  API_BEGIN
+  CTX(ctx);
+  lightcone_drift(c, ls, cap, block, count);
+  API_END
+}
+
 int mgp_assign_displacement_field(mgp_ctx *ctx, int fieldtype, int lpt_order, const double *growth_by_k2, size_t n) {
   API_BEGIN
   CTX(ctx);

@@ -298,6 +298,10 @@ int pofk_effective_nbins(const Ctx &c);
 // simplepofk.cu
 void simple_pofk(Ctx &c, int scheme, int subtract_shotnoise, int slip, double *pofk, double *nmodes);
 
+// lightcone.cu
+void lightcone_count(Ctx &c, const mgp_lightcone_step *ls, uint64_t *count);
+void lightcone_drift(Ctx &c, const mgp_lightcone_step *ls, uint64_t cap, float *block, uint64_t *count);
+
 // ic.cu
 void ic_generate(Ctx &c, const mgp_ic_config *ic);
 void ic_init_particles(Ctx &c, double Di, double Di2, double dDdy, double dD2dy);

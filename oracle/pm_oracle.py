@@ -736,3 +736,81 @@ def readic_delta_k(pos01_files, nmesh, nsample, normfac, rescale_by_k2, grid_dty
     out = (dk.astype(np.complex128) * gc) * np.asarray(rescale_by_k2, dtype=np.float64)[m]
     out[0, 0, 0] = 0.0
     return out
+
+
+# ----------------------------------------------------------------------------- lightcone (-DLIGHTCONE)
+
+def cspline_coeffs(x, y):
+    """Coefficient array of gsl_interp_cspline (natural cubic spline; GSL interpolation/cspline.c, a third-party
+    dependency absent from the reference tree -- its published construction): c[0] = c[n-1] = 0, the interior from the
+    symmetric tridiagonal system h_i c_i + 2 (h_i + h_{i+1}) c_{i+1} + h_{i+1} c_{i+2} = 3 (dy_{i+1}/h_{i+1} - dy_i/h_i).
+    Call sites: lightcone.c:349-357."""
+    x = np.asarray(x, np.float64)
+    y = np.asarray(y, np.float64)
+    n = x.size
+    c = np.zeros(n)
+    if n < 3:
+        return c
+    h = np.diff(x)
+    dy = np.diff(y)
+    off = h[1:].copy()
+    diag = 2.0 * (h[1:] + h[:-1])
+    g = 3.0 * (dy[1:] / h[1:] - dy[:-1] / h[:-1])
+    m = n - 2
+    for i in range(1, m):
+        w = off[i - 1] / diag[i - 1]
+        diag[i] -= w * off[i - 1]
+        g[i] -= w * g[i - 1]
+    c[m] = g[m - 1] / diag[m - 1]
+    for i in range(m - 2, -1, -1):
+        c[i + 1] = (g[i] - off[i] * c[i + 2]) / diag[i]
+    return c
+
+
+def cspline_eval(x, y, c, v):
+    """gsl_spline_eval of the cubic spline (cspline.c: b = dy/dx - dx (c[i+1] + 2 c[i]) / 3, d = (c[i+1] - c[i]) / (3 dx),
+    y = y[i] + t (b + t (c[i] + t d))); interval x[i] <= v < x[i+1], the last one for v = x[n-1]."""
+    v = np.asarray(v, np.float64)
+    i = np.clip(np.searchsorted(x, v, side="right") - 1, 0, x.size - 2)
+    dx = x[i + 1] - x[i]
+    dy = y[i + 1] - y[i]
+    b = dy / dx - dx * (c[i + 1] + 2.0 * c[i]) / 3.0
+    d = (c[i + 1] - c[i]) / (3.0 * dx)
+    t = v - x[i]
+    return y[i] + t * (b + t * (c[i] + t * d))
+
+
+def drift_lightcone(pos, vel, D, D2, sumxyz, box, use_cola, A, AFF, dyyy, da1, da2, dv1, dv2, rcomov_old, rcomov_new,
+                    origin, reps, al_tab, da1_tab, da2_tab, dyyy_tab, lengthfac, velfac_times_fac, boundary=20.0):
+    """The particle loop of Drift_Lightcone (lightcone.c:392-471) for the replicates `reps` ([nrep][3] offsets with
+    repflag == 0, in the order of the triple loop 411-413).  Returns (new positions float32, [rows of replicate r as
+    float32 [count][6], in particle order], exceeded) with exceeded = True where the reference calls FatalError (403-407)."""
+    P = pos.astype(np.float64)
+    V = vel.astype(np.float64) - np.asarray(sumxyz, np.float64)[None, :]
+    Dd = D.astype(np.float64)
+    D2d = D2.astype(np.float64)
+    uc = float(use_cola)
+    dpos = V * dyyy + uc * (Dd * da1 + D2d * da2)                               # 398-400
+    exceeded = bool(np.any(dpos > boundary))                                    # 403
+    al_tab = np.asarray(al_tab, np.float64)
+    tabs = [np.asarray(t, np.float64) for t in (da1_tab, da2_tab, dyyy_tab)]
+    cs = [cspline_coeffs(al_tab, t) for t in tabs]
+    org = np.asarray(origin, np.float64)
+    rows = []
+    for (i, j, k) in np.asarray(reps, np.int64).reshape(-1, 3):
+        shift = np.array([i * box, j * box, k * box], np.float64)
+        X = P - org[None, :] + shift[None, :]                                   # 420-422
+        ro2 = X[:, 0] * X[:, 0] + X[:, 1] * X[:, 1] + X[:, 2] * X[:, 2]
+        Xn = X + dpos
+        rn2 = Xn[:, 0] * Xn[:, 0] + Xn[:, 1] * Xn[:, 1] + Xn[:, 2] * Xn[:, 2]
+        sel = np.nonzero((ro2 <= rcomov_old * rcomov_old) & (rn2 > rcomov_new * rcomov_new))[0]   # 425, 434
+        ro, rn = np.sqrt(ro2[sel]), np.sqrt(rn2[sel])
+        AL = A + (AFF - A) * ((rcomov_old - ro) / ((rn - ro) - (rcomov_new - rcomov_old)))        # 440
+        t1, t2, ty = (cspline_eval(al_tab, tabs[q], cs[q], AL) for q in range(3))
+        out = np.empty((sel.size, 6), np.float32)
+        x = P[sel] + V[sel] * ty[:, None] + uc * (Dd[sel] * t1[:, None] + D2d[sel] * t2[:, None]) + shift[None, :]   # 447-449
+        out[:, :3] = (lengthfac * x).astype(np.float32)
+        out[:, 3:] = (velfac_times_fac * (V[sel] + (Dd[sel] * dv1 + D2d[sel] * dv2) * uc)).astype(np.float32)     # 451-453
+        rows.append(out)
+    newpos = periodic_wrap((P + dpos).astype(np.float32), box)                  # 468-470
+    return newpos, rows, exceeded

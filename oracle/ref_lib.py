@@ -28,6 +28,7 @@ VARIANT_FLAGS = {
     "dgp": dict(scaledependent=False, single=False),
     "dgp_sd": dict(scaledependent=True, single=False),
     "fofrnu": dict(scaledependent=True, single=False),
+    "lcdm_lc": dict(scaledependent=False, single=False),     # -DLIGHTCONE -DUNFORMATTED, no GADGET_STYLE
 }
 
 
@@ -109,7 +110,9 @@ class RefLib:
                      StdDA=C.c_int, fullT=C.c_int, timeStep_global=C.c_int, NoutputStart_global=C.c_int,
                      Box=C.c_double, Buffer=C.c_double, Omega=C.c_double, aexp_global=C.c_double, fofr0=C.c_double,
                      nfofr=C.c_double, Rsmooth_global=C.c_double, rcH0_DGP=C.c_double, pofk_kmin=C.c_double,
-                     pofk_kmax=C.c_double, nLPT=C.c_double, NumPart=C.c_uint, TotNumPart=C.c_ulonglong)
+                     pofk_kmax=C.c_double, nLPT=C.c_double, NumPart=C.c_uint, TotNumPart=C.c_ulonglong,
+                     Origin_x=C.c_double, Origin_y=C.c_double, Origin_z=C.c_double, Nrep_neg_x=C.c_int, Nrep_neg_y=C.c_int,
+                     Nrep_neg_z=C.c_int, Nrep_pos_x=C.c_int, Nrep_pos_y=C.c_int, Nrep_pos_z=C.c_int)
         for k, v in kw.items():
             self._g(k, types[k]).value = v
 
@@ -337,6 +340,43 @@ class RefLib:
         P["Vel"][:n] = vel
         P["ID"][:n] = ids
         return dict(A=A, Di=L.growth_D(A), Di2=L.growth_D2(A))
+
+    # ---- LIGHTCONE build ----
+    def lightcone_scalars(self, A, AFF, AF, Di, Di2, ntab=1000):
+        """The host part of Drift_Lightcone (lightcone.c:281-347) evaluated with the reference's own functions: what
+        the C adapter hands to mgp_drift_lightcone.  StdDA = 0 (COLA)."""
+        L = self.lib
+        for name, nargs in (("SphiStd", 2), ("Sq", 3)):
+            f = getattr(L, name)
+            f.restype = C.c_double
+            f.argtypes = [C.c_double] * nargs
+        light = self.get("Light", C.c_double)
+        hub = self.get("Hubble", C.c_double)
+        al = np.array([(i * (AFF - A)) / (ntab - 1.0) + A for i in range(ntab)])
+        return dict(A=A, AFF=AFF, dyyy=L.Sq(A, AFF, AF), da1=L.growth_D(AFF) - Di, da2=L.growth_D2(AFF) - Di2,
+                    dv1=L.growth_dDdy(AF), dv2=L.growth_dD2dy(AF),
+                    rcomov_old=light / hub * L.SphiStd(A, 1.0), rcomov_new=light / hub * L.SphiStd(AFF, 1.0),
+                    al_tab=al, da1_tab=np.array([L.growth_D(a) - Di for a in al]),
+                    da2_tab=np.array([L.growth_D2(a) - Di2 for a in al]), dyyy_tab=np.array([L.Sq(A, a, AF) for a in al]),
+                    lengthfac=self.get("UnitLength_in_cm", C.c_double) / 3.085678e24,
+                    velfac_times_fac=self.get("UnitVelocity_in_cm_per_s", C.c_double) / 1.0e5 * (hub / AF), boundary=20.0)
+
+    def lightcone_replicates(self):
+        """Offsets (i, j, k) of the replicates with repflag == 0 in the order of the loops of lightcone.c:411-413, and
+        their `coord` (file number = coord * NTask + ThisTask, lightcone.c:509); valid after flag_replicates."""
+        g = lambda n: self.get(n, C.c_int)
+        nmax = (C.c_int * 3).in_dll(self.lib, "Nrep_neg_max"), (C.c_int * 3).in_dll(self.lib, "Nrep_pos_max")
+        dims = [nmax[0][a] + nmax[1][a] + 1 for a in range(3)]
+        flags = C.POINTER(C.c_int).in_dll(self.lib, "repflag")
+        reps, coords = [], []
+        for i in range(-g("Nrep_neg_x"), g("Nrep_pos_x") + 1):
+            for j in range(-g("Nrep_neg_y"), g("Nrep_pos_y") + 1):
+                for k in range(-g("Nrep_neg_z"), g("Nrep_pos_z") + 1):
+                    coord = ((i + nmax[0][0]) * dims[1] + (j + nmax[0][1])) * dims[2] + (k + nmax[0][2])
+                    if flags[coord] == 0:
+                        reps.append((i, j, k))
+                        coords.append(coord)
+        return np.array(reps, np.int32).reshape(-1, 3), coords
 
     def get_displacements(self):
         """GetDisplacements() as compiled (MEMORY_MODE: allocates and frees its own grids)."""

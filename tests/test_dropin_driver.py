@@ -180,3 +180,45 @@ def test_driver_on_ranks_matches_cpu_reference_on_ranks(require_gpu, tmp_path, v
         edge = np.abs(xs / (N // ranks) - np.round(xs / (N // ranks))) * (N // ranks)
         assert (edge < 2 * tol * N / box).all()
     assert moved.sum() <= 4
+
+
+@pytest.mark.gpu
+def test_lightcone_driver_matches_cpu_reference(require_gpu, tmp_path):
+    """-DLIGHTCONE -DUNFORMATTED build: the reference's driver with Drift_Lightcone's particle loop served by
+    mgp_drift_lightcone (adapter/lightcone_c.patch) against the unmodified reference on a whole lightcone run (three
+    ordinary steps down to the redshift the cone starts at, four lightcone steps to z = 0, 125 replicates).  Every image
+    the reference writes must be written by the CUDA build too, replicate file by replicate file, at the same exit
+    position and velocity; the info file (lightcone.c:570-646) must agree."""
+    from scipy.spatial import cKDTree
+    import lightcone_case as lcc
+    N, box = 32, 100.0
+    runs = {}
+    for kind in ("cpu", "gpu"):
+        wd = str(tmp_path / kind)
+        pf = lcc.write_lightcone_paramfile(wd, N, box, 0.06, 3, 4)
+        r = subprocess.run([_exe(kind, "lcdm_lc"), pf], capture_output=True, text=True, cwd=wd, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        runs[kind] = os.path.join(wd, "output")
+    info_c = np.loadtxt(os.path.join(runs["cpu"], "bench_lightcone.info"), comments="#").reshape(-1, 8)
+    info_g = np.loadtxt(os.path.join(runs["gpu"], "bench_lightcone.info"), comments="#").reshape(-1, 8)
+    assert np.array_equal(info_c[:, :7], info_g[:, :7])                    # file numbers and slice corners
+    assert info_c[:, 7].sum() > 50000
+    # a particle within float rounding of the cone's surface may leave one step earlier or later, or start just outside
+    assert np.all(np.abs(info_c[:, 7] - info_g[:, 7]) <= 2 + 1e-3 * info_c[:, 7])
+    files_c = sorted(f for f in os.listdir(runs["cpu"]) if "_lightcone." in f and not f.endswith(".info"))
+    files_g = sorted(f for f in os.listdir(runs["gpu"]) if "_lightcone." in f and not f.endswith(".info"))
+    assert set(files_c) ^ set(files_g) <= {f for f in set(files_c) | set(files_g)
+                                            if info_c[int(f.rsplit(".", 1)[1]), 7] + info_g[int(f.rsplit(".", 1)[1]), 7] <= 2}
+    total = unmatched = 0
+    for f in sorted(set(files_c) & set(files_g)):
+        a, b = lcc.read_lightcone_file(os.path.join(runs["cpu"], f)), lcc.read_lightcone_file(os.path.join(runs["gpu"], f))
+        n = int(f.rsplit(".", 1)[1])
+        assert a.shape[0] == info_c[n, 7] and b.shape[0] == info_g[n, 7]      # Noutput bookkeeping (lightcone.c:456)
+        if a.shape[0] == 0 or b.shape[0] == 0:
+            unmatched += a.shape[0]
+            continue
+        d, j = cKDTree(b[:, :3].astype(np.float64)).query(a[:, :3].astype(np.float64))
+        good = (d < 3e-5 * box / N * 20) & (np.abs(a[:, 3:] - b[j, 3:]).max(axis=1) < 3e-4 * np.abs(a[:, 3:]).max() * 10)
+        total += a.shape[0]
+        unmatched += int((~good).sum())
+    assert total > 50000 and unmatched <= 5 + 2e-4 * total, (total, unmatched)
