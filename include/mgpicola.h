@@ -286,6 +286,35 @@ int mgp_lightcone_count(mgp_ctx *ctx, const mgp_lightcone_step *ls, uint64_t *co
  * MGP_ERR_BUFFER (nothing moved) when a replicate needs more than cap rows: size cap from mgp_lightcone_count. */
 int mgp_drift_lightcone(mgp_ctx *ctx, const mgp_lightcone_step *ls, uint64_t cap, float *block, uint64_t *count);
 
+/* ---- FoF halo finder on the fly (-DMATCHMAKER_HALOFINDER; mm_main.c:129-385, mm_fof.c) ---- */
+/* what main.c:834-868 hands to MatchMaker(), as numbers */
+typedef struct mgp_fof_config {
+  double norm_pos;           /* lengthfac: code positions -> Mpc/h */
+  double norm_vel;           /* Hubble / A / A: code velocities -> comoving dx/dt in km/s (main.c:866) */
+  double boxsize;            /* Box * lengthfac */
+  double dx_extra;           /* mm_dx_extra_mpc * lengthfac: width of the strip shared with the left neighbour */
+  double b_fof;              /* mm_linking_length, in units of the mean inter-particle distance */
+  int np_min;                /* mm_min_npart_halo */
+  double mass_part;          /* particle mass in 1e10 Msun/h (main.c:853) */
+  double dDdy, dD2dy;        /* growth_dDdy(A), growth_dD2dy(A): the LPT velocity added back (mm_main.c:301-303, 327);
+                                ignored when scale_dependent: P.dDdy / P.dD2dy must then hold FIELD_dDdy (main.c:831-832) */
+} mgp_fof_config;
+/* FoFHalo of mm_common.h:115-128, field for field (write_halos() of mm_snap_io.c takes an array of these) */
+typedef struct mgp_fof_halo {
+  int np;
+  float m_halo;
+  float x_avg[3], x_rms[3], v_avg[3], v_rms[3], lam[3];
+  float b, c;
+  float ea[3], eb[3], ec[3];
+} mgp_fof_halo;
+/* picola_to_matchmaker_particles + fof_get_halos for this rank's slab: particles translated and ordered by x, the strip
+ * x <= dx_extra handed to the left neighbour, friends-of-friends groups (x open, y and z periodic, linking length
+ * b_fof * Box / Nsample), groups the left neighbour also found given up, and the properties of every group with at least
+ * np_min members.  *n_halos = halos of this rank; they stay in the context until the next call. */
+int mgp_fof_find(mgp_ctx *ctx, const mgp_fof_config *cfg, uint64_t *n_halos);
+/* the halos of the last mgp_fof_find, by decreasing np (fof_get_halos returns them in that order, mm_fof.c:459) */
+int mgp_fof_get(mgp_ctx *ctx, mgp_fof_halo *out);
+
 /* ---- P(k) (compute_pofk.c:71-271) ---- */
 int mgp_set_pofk_config(mgp_ctx *ctx, const mgp_pofk_config *pc);
 /* bins the k-space density currently in MGP_GRID_DENSITY; arrays sized mgp_pofk_nbins() */

@@ -58,6 +58,18 @@ class LightconeStep(C.Structure):
                 ("da2_tab", C.c_void_p), ("dyyy_tab", C.c_void_p), ("nrep", C.c_int), ("rep_ijk", C.c_void_p)]
 
 
+class FofConfig(C.Structure):
+    """mgp_fof_config (include/mgpicola.h): what main.c:834-868 hands to MatchMaker()."""
+    _fields_ = [("norm_pos", C.c_double), ("norm_vel", C.c_double), ("boxsize", C.c_double), ("dx_extra", C.c_double),
+                ("b_fof", C.c_double), ("np_min", C.c_int), ("mass_part", C.c_double), ("dDdy", C.c_double), ("dD2dy", C.c_double)]
+
+
+# mgp_fof_halo == FoFHalo of mm_common.h:115-128
+FOF_HALO_DTYPE = np.dtype([("np", np.int32), ("m_halo", np.float32), ("x_avg", np.float32, 3), ("x_rms", np.float32, 3),
+                           ("v_avg", np.float32, 3), ("v_rms", np.float32, 3), ("lam", np.float32, 3), ("b", np.float32),
+                           ("c", np.float32), ("ea", np.float32, 3), ("eb", np.float32, 3), ("ec", np.float32, 3)])
+
+
 class StepScalars(C.Structure):
     _fields_ = [("a", C.c_double), ("phi_crit", C.c_double), ("coupling", C.c_double), ("massterm2", C.c_double),
                 ("dgp_fac0", C.c_double), ("rsmooth", C.c_double), ("geff", C.c_double), ("compute_pofk", C.c_int),
@@ -114,6 +126,8 @@ def load_library(path=None):
     L.mgp_get_displacements.argtypes = [C.c_void_p, C.POINTER(StepScalars), dp]
     L.mgp_kick.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, dp, dp]
     L.mgp_drift.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, dp]
+    L.mgp_fof_find.argtypes = [C.c_void_p, C.POINTER(FofConfig), C.POINTER(C.c_uint64)]
+    L.mgp_fof_get.argtypes = [C.c_void_p, C.c_void_p]
     L.mgp_lightcone_count.argtypes = [C.c_void_p, C.POINTER(LightconeStep), C.c_void_p]
     L.mgp_drift_lightcone.argtypes = [C.c_void_p, C.POINTER(LightconeStep), C.c_uint64, C.c_void_p, C.c_void_p]
     L.mgp_set_pofk_config.argtypes = [C.c_void_p, C.POINTER(PofkConfig)]
@@ -377,6 +391,16 @@ class PM:
     def Drift(self, dyyy, deltaD, deltaD2, sumxyz=None):
         sv = (C.c_double * 3)(*(self.sumxyz if sumxyz is None else sumxyz))
         self._ck(self.L.mgp_drift(self.ctx, dyyy, deltaD, deltaD2, sv))
+
+    # ---- FoF halo finder (MatchMaker, mm_main.c / mm_fof.c) ----
+    def MatchMaker(self, norm_pos, norm_vel, boxsize, dx_extra, b_fof, np_min, mass_part, dDdy=0.0, dD2dy=0.0):
+        """The halos of this rank's slab as FoFHalo records (FOF_HALO_DTYPE), by decreasing np."""
+        cfg = FofConfig(norm_pos, norm_vel, boxsize, dx_extra, b_fof, np_min, mass_part, dDdy, dD2dy)
+        n = C.c_uint64()
+        self._ck(self.L.mgp_fof_find(self.ctx, C.byref(cfg), C.byref(n)))
+        out = np.zeros(n.value, FOF_HALO_DTYPE)
+        self._ck(self.L.mgp_fof_get(self.ctx, _ptr(out) if n.value else None))
+        return out
 
     # ---- lightcone (lightcone.c:265-474) ----
     def _lightcone_step(self, sc, reps, sumxyz):

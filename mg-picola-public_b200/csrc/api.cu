@@ -544,6 +544,23 @@ int mgp_drift(mgp_ctx *ctx, double dyyy, double deltaD, double deltaD2, const do
   API_END
 }
 
+int mgp_fof_find(mgp_ctx *ctx, const mgp_fof_config *cfg, uint64_t *n_halos) {
+  API_BEGIN
+  CTX(ctx);
+  fof_find(c, cfg);
+  if (n_halos) *n_halos = c.fof_halos.size();
+  API_END
+}
+
+int mgp_fof_get(mgp_ctx *ctx, mgp_fof_halo *out) {
+  API_BEGIN
+  CTX(ctx);
+  REQUIRE(c.fof_valid, MGP_ERR_STATE, "mgp_fof_get: call mgp_fof_find first");
+  REQUIRE(out != nullptr || c.fof_halos.empty(), MGP_ERR_INVALID, "mgp_fof_get: NULL");
+  if (!c.fof_halos.empty()) memcpy(out, c.fof_halos.data(), c.fof_halos.size() * sizeof(mgp_fof_halo));
+  API_END
+}
+
 int mgp_lightcone_count(mgp_ctx *ctx, const mgp_lightcone_step *ls, uint64_t *count) {
   API_BEGIN
   CTX(ctx);

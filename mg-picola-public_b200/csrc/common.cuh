@@ -193,6 +193,10 @@ struct Ctx {
   int pofk_tab_nbins = 0, pofk_tab_bintype = 0;
   double pofk_tab_kmin = 0, pofk_tab_kmax = 0;
 
+  // FoF halos of the last mgp_fof_find (fof.cu), by decreasing np
+  std::vector<mgp_fof_halo> fof_halos;
+  bool fof_valid = false;
+
   cudaStream_t stream = nullptr;
   ncclComm_t comm = nullptr;
 
@@ -298,6 +302,8 @@ int pofk_effective_nbins(const Ctx &c);
 // simplepofk.cu
 void simple_pofk(Ctx &c, int scheme, int subtract_shotnoise, int slip, double *pofk, double *nmodes);
 
+// fof.cu
+void fof_find(Ctx &c, const mgp_fof_config *cfg);
 // lightcone.cu
 void lightcone_count(Ctx &c, const mgp_lightcone_step *ls, uint64_t *count);
 void lightcone_drift(Ctx &c, const mgp_lightcone_step *ls, uint64_t cap, float *block, uint64_t *count);

@@ -814,3 +814,167 @@ def drift_lightcone(pos, vel, D, D2, sumxyz, box, use_cola, A, AFF, dyyy, da1, d
         rows.append(out)
     newpos = periodic_wrap((P + dpos).astype(np.float32), box)                  # 468-470
     return newpos, rows, exceeded
+
+
+# ----------------------------------------------------------------------------- FoF halo finder (-DMATCHMAKER_HALOFINDER)
+
+FOF_HALO_DTYPE = np.dtype([("np", np.int32), ("m_halo", np.float32), ("x_avg", np.float32, 3), ("x_rms", np.float32, 3),
+                           ("v_avg", np.float32, 3), ("v_rms", np.float32, 3), ("lam", np.float32, 3), ("b", np.float32),
+                           ("c", np.float32), ("ea", np.float32, 3), ("eb", np.float32, 3), ("ec", np.float32, 3)])   # mm_common.h:115-128
+
+
+def fof_translate(pos, vel, D, D2, norm_pos, norm_vel, use_cola, dDdy, dD2dy, scale_dependent=False):
+    """picola_to_matchmaker_particles, mm_main.c:294-338: MatchMaker's float positions (before the x offset) and
+    velocities.  scale_dependent: D / D2 are then P.dDdy / P.dD2dy (float sum, mm_main.c:319)."""
+    npf, nvf = np.float32(norm_pos), np.float32(norm_vel)
+    x = (npf * pos.astype(np.float32)).astype(np.float32)
+    if not use_cola:
+        v = (nvf * vel.astype(np.float32)).astype(np.float32)
+    elif scale_dependent:
+        v = (nvf * (vel.astype(np.float32) + (D.astype(np.float32) + D2.astype(np.float32)))).astype(np.float32)
+    else:
+        v = (np.float64(nvf) * (vel.astype(np.float64) + (D.astype(np.float64) * dDdy + D2.astype(np.float64) * dD2dy))).astype(np.float32)
+    return x, v
+
+
+def fof_link_pairs(x, dfof, lbox):
+    """All pairs (i < j) that get_neighbors (mm_fof.c:112-186) links: dx = |x0 - x1| (NOT periodic: slab coordinates),
+    dy, dz periodic (d > L/2 -> L - d), d2 = dx dx + dy dy + dz dz <= Dfof^2, everything in float."""
+    from scipy.spatial import cKDTree
+    dfof = np.float32(dfof)
+    lb, lh = np.float32(lbox), np.float32(lbox / 2)
+    xd = x.astype(np.float64).copy()
+    L = float(lb)
+    xd[:, 1:] = np.mod(xd[:, 1:], L)
+    xd[:, 1:][xd[:, 1:] >= L] = 0.0
+    span = float(xd[:, 0].max() - xd[:, 0].min()) + 4.0 * float(dfof) + 1.0
+    xd[:, 0] -= xd[:, 0].min()
+    tree = cKDTree(xd, boxsize=[span * 4.0, L, L])                  # x: a period no pair can wrap around
+    cand = tree.query_pairs(float(dfof) * 1.0001 + 1e-6, output_type="ndarray")
+    i, j = cand[:, 0], cand[:, 1]
+    dx = np.abs(x[i, 0] - x[j, 0]).astype(np.float32)
+    dy = np.abs(x[i, 1] - x[j, 1]).astype(np.float32)
+    dz = np.abs(x[i, 2] - x[j, 2]).astype(np.float32)
+    dy = np.where(dy > lh, lb - dy, dy).astype(np.float32)
+    dz = np.where(dz > lh, lb - dz, dz).astype(np.float32)
+    d2 = ((dx * dx + dy * dy).astype(np.float32) + dz * dz).astype(np.float32)
+    ok = (dx <= dfof) & (d2 <= np.float32(dfof * dfof))
+    return i[ok], j[ok]
+
+
+def fof_halo_properties(x, v, ids, boxsize, mass_particle, x_offset):
+    """get_halos (mm_fof.c:468-611) for one group: members `ids` in increasing index order."""
+    L = float(boxsize)
+    n = ids.size
+    h = np.zeros((), FOF_HALO_DTYPE)
+    h["np"] = n
+    h["m_halo"] = n * mass_particle
+    xs, vs = x[ids].astype(np.float64), v[ids].astype(np.float64)
+    x_sum = np.zeros(3)
+    for j in range(n):                                              # running centre of mass decides the image (490-511)
+        for ax in range(3):
+            xx = xs[j, ax]
+            if j > 0:
+                cm = x_sum[ax] / j
+                if 2 * abs(xx - cm) > L:
+                    xx = xx - L if 2 * xx > L else xx + L
+            x_sum[ax] += xx
+    v_sum = np.zeros(3)
+    for j in range(n):
+        v_sum += vs[j]
+    x_avg = (x_sum / n).astype(np.float32)                          # stored as float (512-515)
+    v_avg = (v_sum / n).astype(np.float32)
+    xa, va = x_avg.astype(np.float64), v_avg.astype(np.float64)
+    xw = xs.copy()
+    far = 2 * np.abs(xw - xa[None, :]) > L                          # 527-536
+    xw = np.where(far, np.where(2 * xw > L, xw - L, xw + L), xw)
+    dx, dv = xw - xa[None, :], vs - va[None, :]
+    x_rms, v_rms, lam, inertia = np.zeros(3), np.zeros(3), np.zeros(3), np.zeros((3, 3))
+    for j in range(n):                                              # 539-555, in member order
+        x_rms += dx[j] * dx[j]
+        v_rms += dv[j] * dv[j]
+        inertia += np.outer(dx[j], dx[j])
+        lam[0] += dx[j, 1] * dv[j, 2] - dx[j, 2] * dv[j, 1]
+        lam[1] += dx[j, 2] * dv[j, 0] - dx[j, 0] * dv[j, 2]
+        lam[2] += dx[j, 0] * dv[j, 1] - dx[j, 1] * dv[j, 0]
+    w, e = np.linalg.eigh(inertia)                                  # gsl_eigen_symmv + descending sort (557-568)
+    o = np.argsort(-w, kind="stable")
+    w, e = w[o], e[:, o]
+    if w[0] <= 0:
+        h["b"] = h["c"] = 0
+    else:
+        h["b"], h["c"] = w[1] / w[0], w[2] / w[0]
+        h["ea"], h["eb"], h["ec"] = e[:, 0], e[:, 1], e[:, 2]
+    h["x_rms"] = np.sqrt(x_rms / n)
+    h["v_rms"] = np.sqrt(v_rms / n)
+    h["lam"] = lam
+    xf = x_avg.copy()                                               # wrap the centre of mass (598-603), float arithmetic
+    for ax in range(3):
+        if xf[ax] < 0:
+            xf[ax] = np.float32(np.float64(xf[ax]) + L)
+        elif xf[ax] >= L:
+            xf[ax] = np.float32(np.float64(xf[ax]) - L)
+    xf[0] = np.float32(xf[0] + np.float32(x_offset))
+    h["x_avg"] = xf
+    h["v_avg"] = v_avg
+    return h
+
+
+def fof_halos(tasks, norm_pos, norm_vel, boxsize, dx_extra, b_fof, np_min, mass_part, n_part_1d, use_cola=1, dDdy=0.0,
+              dD2dy=0.0, scale_dependent=False):
+    """MatchMaker (mm_main.c:129-385, mm_fof.c) on NTask = len(tasks) tasks: tasks[t] = dict(pos, vel, D, D2,
+    local_p_start) holds task t's particles (D / D2 = P.dDdy / P.dD2dy when scale_dependent).  Returns per task the
+    FoFHalo records sorted by np (descending), and per task a dict of intermediate results for the tests."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    nt = len(tasks)
+    L = float(boxsize)
+    ipd = np.float32(L / np.float64(float(n_part_1d) ** 3) ** (1.0 / 3.0))        # init_fof, mm_fof.c:83
+    dfof = np.float32(np.float64(ipd) * b_fof)
+    mass_particle = 1.0e10 * mass_part                                             # MATCHMAKER_MASS_FACTOR
+    x_off = [np.float32(t["local_p_start"] * (L / float(n_part_1d))) for t in tasks]                  # mm_main.c:227
+    st = []
+    for r, t in enumerate(tasks):
+        xo_right = x_off[(r + 1) % nt]
+        dxd = np.float32(xo_right - x_off[r])                                       # 236-237
+        if dxd < 0:
+            dxd = np.float32(np.float64(dxd) + L)
+        pos = t["pos"]
+        x1 = (np.float64(norm_pos) * pos[:, 0].astype(np.float64) - np.float64(x_off[r])).astype(np.float32)   # 266-271
+        n_toleft = int(np.count_nonzero(x1.astype(np.float64) <= dx_extra))
+        x, v = fof_translate(pos, t["vel"], t["D"], t["D2"], norm_pos, norm_vel, use_cola, dDdy, dD2dy, scale_dependent)
+        x[:, 0] = x[:, 0] - x_off[r]                                                # 334
+        order = np.argsort(x[:, 0], kind="stable")                                  # qsort by x (360)
+        st.append(dict(x=x[order], v=v[order], order=order, n_dom=pos.shape[0], n_toleft=n_toleft, dx_domain=dxd))
+    for r in range(nt):                                                             # buffer from the right neighbour (363-373)
+        right = st[(r + 1) % nt]
+        bx = right["x"][:right["n_toleft"]].copy()
+        bx[:, 0] = bx[:, 0] + st[r]["dx_domain"]
+        st[r]["xa"] = np.concatenate([st[r]["x"], bx])
+        st[r]["va"] = np.concatenate([st[r]["v"], right["v"][:right["n_toleft"]]])
+    for r in range(nt):                                                             # assign_particles_to_fof (354-400)
+        s = st[r]
+        n = s["xa"].shape[0]
+        i, j = fof_link_pairs(s["xa"], dfof, L)
+        ncomp, lab = connected_components(coo_matrix((np.ones(i.size, np.int8), (i, j)), shape=(n, n)), directed=False)
+        size = np.bincount(lab, minlength=ncomp)
+        has_dom = np.bincount(lab[:s["n_dom"]], minlength=ncomp) > 0               # groups are seeded by in-domain particles only
+        s["lab"], s["in_group"] = lab, (size[lab] >= 2) & has_dom[lab]
+    out, info = [], []
+    for r in range(nt):
+        s, left = st[r], st[(r - 1) % nt]
+        member = s["in_group"].copy()
+        back = left["in_group"][left["n_dom"]:]                                     # my first n_toleft particles as the left task saw them (425-437)
+        member[:s["n_toleft"]] &= ~back
+        lab = s["lab"]
+        cnt = np.bincount(lab[member], minlength=lab.max() + 1)
+        halos = []
+        for g in np.nonzero(cnt >= np_min)[0]:
+            ids = np.nonzero(member & (lab == g))[0]
+            halos.append(fof_halo_properties(s["xa"], s["va"], ids, L, mass_particle, x_off[r]))
+        h = np.array(halos, FOF_HALO_DTYPE) if halos else np.zeros(0, FOF_HALO_DTYPE)
+        h = h[np.argsort(-h["np"], kind="stable")]
+        out.append(h)
+        info.append(dict(n_groups=int(np.count_nonzero(cnt > 0)), n_toleft=s["n_toleft"], n_fromright=s["xa"].shape[0] - s["n_dom"],
+                         dfof=float(dfof), group_sizes=np.sort(cnt[cnt > 0])[::-1]))
+    return out, info

@@ -29,6 +29,7 @@ VARIANT_FLAGS = {
     "dgp_sd": dict(scaledependent=True, single=False),
     "fofrnu": dict(scaledependent=True, single=False),
     "lcdm_lc": dict(scaledependent=False, single=False),     # -DLIGHTCONE -DUNFORMATTED, no GADGET_STYLE
+    "lcdm_mm": dict(scaledependent=False, single=False),     # -DMATCHMAKER_HALOFINDER
 }
 
 

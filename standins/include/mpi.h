@@ -58,5 +58,9 @@ int MPI_Type_match_size(int typeclass, int size, MPI_Datatype *t);
 int MPI_Type_create_struct(int count, const int *blocklengths, const MPI_Aint *offsets,
                            const MPI_Datatype *types, MPI_Datatype *newtype);
 int MPI_Type_commit(MPI_Datatype *t);
+/* MatchMaker (mm_main.c:72, 124; mm_snap_io.c:335): the MPI-1 name of MPI_Type_create_struct, and a gather of unequal pieces */
+int MPI_Type_struct(int count, int *blocklengths, MPI_Aint *offsets, MPI_Datatype *types, MPI_Datatype *newtype);
+int MPI_Gatherv(const void *sendbuf, int scount, MPI_Datatype st, void *recvbuf, const int *rcounts, const int *displs,
+                MPI_Datatype rt, int root, MPI_Comm comm);
 
 #endif

@@ -462,3 +462,64 @@ void gsl_sort(double *data, size_t stride, size_t n) {
   for (size_t i = 0; i < n; i++) data[i * stride] = tmp[i];
   free(tmp);
 }
+
+/* ------------------------------------------------------------------ symmetric eigen-systems (mm_fof.c:548-556) */
+#include <gsl/gsl_eigen.h>
+
+gsl_matrix *gsl_matrix_alloc(size_t n1, size_t n2) {
+  gsl_matrix *m = (gsl_matrix *) malloc(sizeof(gsl_matrix));
+  m->size1 = n1; m->size2 = n2; m->data = (double *) calloc(n1 * n2, sizeof(double));
+  return m;
+}
+void gsl_matrix_free(gsl_matrix *m) { if (m) { free(m->data); free(m); } }
+void gsl_matrix_set(gsl_matrix *m, size_t i, size_t j, double x) { m->data[i * m->size2 + j] = x; }
+double gsl_matrix_get(const gsl_matrix *m, size_t i, size_t j) { return m->data[i * m->size2 + j]; }
+gsl_vector *gsl_vector_alloc(size_t n) {
+  gsl_vector *v = (gsl_vector *) malloc(sizeof(gsl_vector));
+  v->size = n; v->data = (double *) calloc(n, sizeof(double));
+  return v;
+}
+void gsl_vector_free(gsl_vector *v) { if (v) { free(v->data); free(v); } }
+double gsl_vector_get(const gsl_vector *v, size_t i) { return v->data[i]; }
+gsl_eigen_symmv_workspace *gsl_eigen_symmv_alloc(size_t n) {
+  gsl_eigen_symmv_workspace *w = (gsl_eigen_symmv_workspace *) malloc(sizeof(gsl_eigen_symmv_workspace));
+  w->size = n;
+  return w;
+}
+void gsl_eigen_symmv_free(gsl_eigen_symmv_workspace *w) { free(w); }
+
+/* cyclic Jacobi rotations (GSL tridiagonalises and runs implicit QR; eigenvalues agree to rounding, eigenvectors up to
+ * sign and, for degenerate eigenvalues, up to a rotation of the eigen-space: what a comparison may rely on) */
+int gsl_eigen_symmv(gsl_matrix *A, gsl_vector *eval, gsl_matrix *evec, gsl_eigen_symmv_workspace *w) {
+  (void) w;
+  const size_t n = A->size1;
+  double *a = A->data, *v = evec->data;
+  for (size_t i = 0; i < n; i++) for (size_t j = 0; j < n; j++) v[i * n + j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 64; sweep++) {
+    double off = 0.0;
+    for (size_t p = 0; p < n; p++) for (size_t q = p + 1; q < n; q++) off += a[p * n + q] * a[p * n + q];
+    if (off == 0.0) break;
+    for (size_t p = 0; p < n; p++)
+      for (size_t q = p + 1; q < n; q++) {
+        const double apq = a[p * n + q];
+        if (apq == 0.0) continue;
+        const double theta = (a[q * n + q] - a[p * n + p]) / (2.0 * apq);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        for (size_t k = 0; k < n; k++) {           /* A <- A J */
+          const double akp = a[k * n + p], akq = a[k * n + q];
+          a[k * n + p] = c * akp - s * akq; a[k * n + q] = s * akp + c * akq;
+        }
+        for (size_t k = 0; k < n; k++) {           /* A <- J^T A */
+          const double apk = a[p * n + k], aqk = a[q * n + k];
+          a[p * n + k] = c * apk - s * aqk; a[q * n + k] = s * apk + c * aqk;
+        }
+        for (size_t k = 0; k < n; k++) {           /* V <- V J */
+          const double vkp = v[k * n + p], vkq = v[k * n + q];
+          v[k * n + p] = c * vkp - s * vkq; v[k * n + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  for (size_t i = 0; i < n; i++) eval->data[i] = a[i * n + i];
+  return GSL_SUCCESS;
+}

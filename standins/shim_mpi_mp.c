@@ -262,3 +262,24 @@ int MPI_Type_create_struct(int count, const int *blocklengths, const MPI_Aint *o
   return MPI_SUCCESS;
 }
 int MPI_Type_commit(MPI_Datatype *t) { (void) t; return MPI_SUCCESS; }
+
+int MPI_Type_struct(int count, int *blocklengths, MPI_Aint *offsets, MPI_Datatype *types, MPI_Datatype *newtype) {
+  return MPI_Type_create_struct(count, blocklengths, offsets, types, newtype);
+}
+/* every rank learns every count, then rank r's piece travels like a broadcast from r; only the root keeps it */
+int MPI_Gatherv(const void *sendbuf, int scount, MPI_Datatype st, void *recvbuf, const int *rcounts, const int *displs,
+                MPI_Datatype rt, int root, MPI_Comm comm) {
+  (void) rcounts; (void) rt;
+  const size_t sz = MGP_DT_SIZE(st);
+  int *counts = (int *) malloc(sizeof(int) * (size_t) g_size);
+  MPI_Allgather(&scount, 1, MPI_INT, counts, 1, MPI_INT, comm);
+  for (int r = 0; r < g_size; r++) {
+    if (counts[r] == 0) continue;
+    char *tmp = (g_rank == root) ? (char *) recvbuf + (size_t) displs[r] * sz : (char *) malloc((size_t) counts[r] * sz);
+    if (g_rank == r) memcpy(tmp, sendbuf, (size_t) counts[r] * sz);
+    MPI_Bcast(tmp, (int) ((size_t) counts[r] * sz), MPI_BYTE, r, comm);
+    if (g_rank != root) free(tmp);
+  }
+  free(counts);
+  return MPI_SUCCESS;
+}

@@ -25,13 +25,15 @@ def test_library_exports_every_declared_symbol(mgp):
 
 def test_header_compiles_as_c_and_struct_sizes_match(mgp, tmp_path):
     src = tmp_path / "t.c"
-    src.write_text('#include "mgpicola.h"\n#include <stdio.h>\nint main(void){printf("%zu %zu %zu %zu\\n", sizeof(mgp_config), '
-                   'sizeof(mgp_pofk_config), sizeof(mgp_step_scalars), sizeof(mgp_lightcone_step)); return 0;}\n')
+    src.write_text('#include "mgpicola.h"\n#include <stdio.h>\nint main(void){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(mgp_config), '
+                   'sizeof(mgp_pofk_config), sizeof(mgp_step_scalars), sizeof(mgp_lightcone_step), sizeof(mgp_fof_config), '
+                   'sizeof(mgp_fof_halo)); return 0;}\n')
     exe = tmp_path / "t"
     inc = os.path.join(os.path.dirname(mgp.HEADER_PATH))
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", inc, str(src), "-o", str(exe)], check=True)
     sizes = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()]
-    assert sizes == [C.sizeof(mgp.Config), C.sizeof(mgp.PofkConfig), C.sizeof(mgp.StepScalars), C.sizeof(mgp.LightconeStep)]
+    assert sizes == [C.sizeof(mgp.Config), C.sizeof(mgp.PofkConfig), C.sizeof(mgp.StepScalars), C.sizeof(mgp.LightconeStep),
+                     C.sizeof(mgp.FofConfig), mgp.FOF_HALO_DTYPE.itemsize]
 
 
 def test_no_cpu_fallback(mgp):
