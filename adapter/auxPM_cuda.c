@@ -239,9 +239,10 @@ static void upload_host_particles(void) {
 }
 
 /* GADGET snapshots are packed on the GPU (mgp_pack_snapshot): Output() never reads P, only NumPart.  The ASCII output of a
- * build without -DGADGET_STYLE, the FoF hook and MGP_HOST_SNAPSHOT=1 (the previous behaviour) still bring P back. */
+ * build without -DGADGET_STYLE and MGP_HOST_SNAPSHOT=1 (the previous behaviour) still bring P back.  The FoF hook of
+ * main.c:830-872 no longer needs P either (MatchMaker below). */
 static int gpu_snapshot(void) {
-#if defined(GADGET_STYLE) && !defined(MATCHMAKER_HALOFINDER)
+#if defined(GADGET_STYLE)
   static int on = -1;
   if (on < 0) { const char *e = getenv("MGP_HOST_SNAPSHOT"); on = !(e && atoi(e) != 0); }
   return on;
@@ -587,6 +588,75 @@ void mgp_adapter_kick(double A, double dda, double ddDddy, double ddD2ddy) {
 void mgp_adapter_drift(double dyyy, double deltaD, double deltaD2) {
   ck(mgp_drift(g_ctx, dyyy, deltaD, deltaD2, sumxyz), "mgp_drift");
 }
+
+#ifdef MATCHMAKER_HALOFINDER
+/* ------------------------------------------------------------------ FoF halos on the fly (mm_main.c, mm_fof.c)
+ * MatchMaker() keeps its name and its argument (main.c:830-872 is untouched): the parameter block of mm_main.c:144-240 is
+ * filled as before because the reference's writers (mm_snap_io.c, mm_msg.c: compiled unmodified) read it; the particle
+ * translation, the strip exchange, the friends-of-friends search and the halo properties (picola_to_matchmaker_particles,
+ * fof_get_halos) run in the library. */
+#include "mm_common.h"
+
+void MatchMaker(struct PicolaToMatchMakerData data) {
+  static int initialised = 0;
+  if (!initialised) {                                  /* mm_mpi_init: write_halos_root gathers FoFHalo records (mm_snap_io.c:335) */
+    int bc[1] = {(int) sizeof(FoFHalo)};
+    MPI_Aint off[1] = {0};
+    MPI_Datatype ty[1] = {MPI_BYTE};
+    MPI_Type_struct(1, bc, off, ty, &HaloMPI);
+    MPI_Type_commit(&HaloMPI);
+    mm_msg_init();
+    initialised = 1;
+  }
+  mm_msg_printf("\n=========================\n");
+  mm_msg_printf("Powering up MatchMaker (CUDA library)\n");
+  mm_msg_printf("=========================\n\n");
+  Param.output_format = data.output_format; Param.output_pernode = data.output_pernode;
+  Param.dx_extra = data.dx_extra; Param.np_min = data.np_min; Param.b_fof = data.b_fof;
+  Param.n_part_1d = data.n_part_1d;
+  Param.n_part = (lint) data.n_part_1d * (lint) data.n_part_1d * (lint) data.n_part_1d;
+  Param.boxsize = data.boxsize; Param.omega_m = data.omega_m; Param.omega_l = data.omega_l; Param.redshift = data.redshift;
+  Param.norm_vel = data.norm_vel; Param.norm_pos = data.norm_pos; Param.h = data.HubbleParam;
+  Param.NumPart = NumPart; Param.Local_p_start = data.Local_p_start; Param.P = NULL;
+  Param.growth_dDdy = data.growth_dDdy; Param.growth_dD2dy = data.growth_dD2dy;
+  sprintf(Param.OutputDir, "%s", data.OutputDir);
+  sprintf(Param.FileBase, "%s", data.FileBase);
+  Param.mp = data.mass_part;
+  {
+    const double z = Param.redshift;
+    const int zint = (int) z, zfrac = (int) ((z - zint) * 1000);
+    sprintf(Param.output_prefix, "%s/matchmaker_%s_z%d.%03d", Param.OutputDir, Param.FileBase, zint, zfrac);
+  }
+  MPI_Comm_rank(MPI_COMM_WORLD, &(Param.i_node));
+  MPI_Comm_size(MPI_COMM_WORLD, &(Param.n_nodes));
+  Param.i_node_left = (Param.i_node - 1 + Param.n_nodes) % Param.n_nodes;
+  Param.i_node_right = (Param.i_node + 1) % Param.n_nodes;
+  if (Param.dx_extra >= 0.5 * Param.boxsize / (double) Param.n_nodes) {             /* mm_main.c:214-218 */
+    mm_msg_printf("Buffer size might be too big! MatchMaker will not be run!\nReduce it or the number of cores!\n");
+    return;
+  }
+  if (g_host_is_newer) upload_host_particles();
+  mgp_fof_config fc;
+  memset(&fc, 0, sizeof(fc));
+  fc.norm_pos = data.norm_pos; fc.norm_vel = data.norm_vel; fc.boxsize = data.boxsize; fc.dx_extra = data.dx_extra;
+  fc.b_fof = data.b_fof; fc.np_min = data.np_min; fc.mass_part = data.mass_part;
+#ifndef SCALEDEPENDENT
+  {
+    const double A = 1.0 / (1.0 + Param.redshift);                                 /* mm_main.c:300-303 */
+    fc.dDdy = data.growth_dDdy(A); fc.dD2dy = data.growth_dD2dy(A);
+  }
+#endif
+  uint64_t nh = 0;
+  mm_msg_printf("Getting halos\n");
+  ck(mgp_fof_find(g_ctx, &fc, &nh), "mgp_fof_find");
+  if (sizeof(FoFHalo) != sizeof(mgp_fof_halo)) FatalError((char *) "MatchMaker: FoFHalo and mgp_fof_halo differ");
+  FoFHalo *fh = nh ? my_malloc(nh * sizeof(FoFHalo)) : NULL;                        /* write_halos frees it (mm_snap_io.c:300, 337) */
+  ck(mgp_fof_get(g_ctx, (mgp_fof_halo *) fh), "mgp_fof_get");
+  mm_msg_printf("Writing output\n");
+  write_halos((lint) nh, fh);
+  mm_msg_printf("=========================\n\n");
+}
+#endif
 
 #ifdef LIGHTCONE
 /* called (through adapter/lightcone_c.patch) from Drift_Lightcone in place of its particle loop (lightcone.c:392-471): the

@@ -222,3 +222,45 @@ def test_lightcone_driver_matches_cpu_reference(require_gpu, tmp_path):
         total += a.shape[0]
         unmatched += int((~good).sum())
     assert total > 50000 and unmatched <= 5 + 2e-4 * total, (total, unmatched)
+
+
+@pytest.mark.gpu
+def test_matchmaker_driver_matches_cpu_reference(require_gpu, tmp_path):
+    """-DMATCHMAKER_HALOFINDER build: main.c's FoF hook (main.c:830-872) served by mgp_fof_find, the catalogue written by
+    the reference's own mm_snap_io.c.  (a) Exact: the numpy restatement of MatchMaker applied to the positions of the
+    CUDA driver's own snapshot must give the catalogue the CUDA driver wrote -- np, centres, rms radii and axis ratios bit
+    for bit (the snapshot holds the very floats the finder saw; its velocities carry -<Vel>, so velocity moments are
+    compared to that accuracy only).  (b) Against the unmodified reference's run: positions differ by float rounding after
+    ten steps, so a few marginal links differ: the same number of halos and the same mass in them to a per cent."""
+    import bench
+    import fof_case as fc
+    from oracle import pm_oracle as po
+    N, box, nsteps = 64, 100.0, 10
+    runs = {}
+    for kind in ("cpu", "gpu"):
+        wd = str(tmp_path / kind)
+        pf = bench.write_paramfile(wd, N, box, "lcdm", nsteps, extra=fc.MM_TAGS)
+        r = subprocess.run([_exe(kind, "lcdm_mm"), pf], capture_output=True, text=True, cwd=wd, timeout=900)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        runs[kind] = os.path.join(wd, "output")
+    hc = fc.read_halo_file(os.path.join(runs["cpu"], "matchmaker_bench_z0.000.dat"))
+    hg = fc.read_halo_file(os.path.join(runs["gpu"], "matchmaker_bench_z0.000.dat"))
+    assert hc.size > 200
+    # (a) the catalogue of the CUDA run is what MatchMaker gives on the particles of the CUDA run
+    snap = [f for f in os.listdir(runs["gpu"]) if f.startswith("bench_z0p000")]
+    pos, vel, ids = read_gadget(os.path.join(runs["gpu"], snap[0]))
+    zero = np.zeros_like(pos)
+    Hubble = 100.0                                          # HUBBLE * UnitTime_in_s with the units of the parameter file
+    mass_part = 3.0 * bench.OMEGA * Hubble * Hubble * box ** 3 / (8.0 * np.pi * 43.0071 * float(N) ** 3)   # main.c:853
+    out, _ = po.fof_halos([dict(pos=pos, vel=vel, D=zero, D2=zero, local_p_start=0)], 1.0, 1.0, box, 3.0, 0.2, 20, mass_part, N, 0)
+    a, b = fc.canonical(out[0]), fc.canonical(hg)
+    assert a.size == b.size and np.array_equal(a["np"], b["np"])
+    for f in ("x_avg", "x_rms", "b", "c"):
+        assert np.array_equal(a[f].view(np.uint32), b[f].view(np.uint32)), f
+    assert np.allclose(a["m_halo"], b["m_halo"], rtol=1e-4)
+    vscale = np.abs(b["v_rms"]).max()
+    assert np.abs(a["v_avg"] - b["v_avg"]).max() < 2e-3 * vscale and np.abs(a["v_rms"] - b["v_rms"]).max() < 2e-3 * vscale
+    # (b) against the unmodified reference
+    assert abs(hc.size - hg.size) <= 2 + 0.01 * hc.size
+    assert abs(int(hc["np"].sum()) - int(hg["np"].sum())) <= 0.01 * hc["np"].sum()
+    assert abs(int(hc["np"][0]) - int(hg["np"][0])) <= 0.02 * hc["np"][0]
