@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--ic", action="store_true", help="generate the golden-fixture ICs on the ranks instead of stepping")
     ap.add_argument("--sd", action="store_true", help="scale-dependent run of tests/golden/sd_fofr.npz on the ranks")
     ap.add_argument("--merged", action="store_true")
+    ap.add_argument("--fof", action="store_true", help="FoF halo finder on the ranks (tests/fof_case.py particles)")
     ap.add_argument("--sort-interval", type=int, default=1, help="sort_particles of the context (>= 3: the hole compaction of "
                     "MoveParticles runs between sorts)")
     a = ap.parse_args()
@@ -43,6 +44,23 @@ def main():
         pm.init_particles(float(g["Di"]), float(g["Di2"]))
         got = pm.download_particles()
         np.savez(os.path.join(a.out, "rank%d.npz" % rank), p0=pm.local_p_start, npl=pm.local_np, **got)
+        mdist.barrier()
+        pm.close()
+        return
+    if a.fof:
+        import fof_case as fc
+        N, box = a.nmesh, 100.0
+        pos, vel, D, D2 = fc.make_particles(N, box, 3)
+        mine = (np.arange(N ** 3) % world) == rank
+        nid = mdist.share_from_rank0(mgp.nccl_unique_id)
+        pm = mgp.PM(N, N, box, grid_bytes=a.gb, buffer=2.5, rank=rank, nranks=world, device=local, nccl_id=nid, sort_particles=1)
+        pm.upload_particles(pos[mine], vel[mine], D[mine], D2[mine], np.arange(N ** 3, dtype=np.uint64)[mine])
+        pm.MoveParticles()                  # every particle to the rank that owns its slab (auxPM.c:151-153)
+        got = pm.download_particles()
+        c = fc.FOF_DEFAULTS
+        h = pm.MatchMaker(c["norm_pos"], c["norm_vel"], box * c["norm_pos"], c["dx_extra"], c["b_fof"], c["np_min"], c["mass_part"],
+                          c["dDdy"], c["dD2dy"])
+        np.savez(os.path.join(a.out, "rank%d.npz" % rank), halos=h, p0=pm.local_p_start, **got)
         mdist.barrier()
         pm.close()
         return

@@ -171,3 +171,23 @@ def test_scale_dependent_run_on_slabs(require_gpu, tmp_path, world, merged):
     assert np.abs(vel - g["vel1"][ro][ids]).max() < 1e-5 * np.abs(g["vel1"]).max()
     moved = sum(int(((r["id"].astype(np.int64) // (N * N)) // (N // world) != k).sum()) for k, r in enumerate(ranks))
     assert moved > 0, "no particle left its birth slab: the remote fetch was not exercised"
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_halo_finder_on_ranks_matches_oracle(require_gpu, tmp_path, world):
+    """mgp_fof_find on several ranks: the strip x <= dx_extra travels to the left neighbour over NCCL and the "already
+    yours?" flags travel back (mm_main.c:363-373, mm_fof.c:417-437).  Every rank's catalogue must be what the restatement
+    of MatchMaker gives for the same particles on the same number of tasks (pinned to the reference as a 2-rank program in
+    tests/test_fof.py), bit for bit."""
+    if _ngpu() < world:
+        pytest.skip("needs %d GPUs" % world)
+    import fof_case as fc
+    N, box = 32, 100.0
+    ranks = _run(world, tmp_path, N, 0, "lcdm", 8, 0, extra=["--fof"])
+    c = fc.FOF_DEFAULTS
+    tasks = [dict(pos=r["pos"], vel=r["vel"], D=r["D"], D2=r["D2"], local_p_start=int(r["p0"])) for r in ranks]
+    orc, info = po.fof_halos(tasks, c["norm_pos"], c["norm_vel"], box * c["norm_pos"], c["dx_extra"], c["b_fof"], c["np_min"],
+                             c["mass_part"], N, 1, c["dDdy"], c["dD2dy"])
+    assert sum(h.size for h in orc) >= 40 and all(i["n_toleft"] > 0 for i in info)
+    for k, r in enumerate(ranks):
+        fc.assert_same_halos(r["halos"], orc[k], exact_vectors=False)
