@@ -55,6 +55,19 @@ PY
       tail -c 2500 gpurun_out/${TAG}_bench_${NG}gpu_${BNAME:-default}.json; tail -3 gpurun_out/${TAG}_bench_${NG}gpu_${BNAME:-default}.err ;;
     pcie)              # pinned host <-> device copy rates on $NG ranks, alone and together
       timeout 200 $TR $NG tools/pcie_probe.py 2>&1 | grep -E "rank|aggregate|rror" | tee gpurun_out/${TAG}_pcie_${NG}gpu.txt ;;
+    fof_lc)            # section 8(f).4: library tests, the two driver tests (their files kept), then the timing probe
+      timeout 120 python -m pytest tests/test_lightcone.py tests/test_fof.py -q -m gpu -p no:cacheprovider -rA \
+        --basetemp=gpurun_out/${TAG}_tmp_lib > gpurun_out/${TAG}_fof_lc_lib.log 2>&1
+      echo "rc=$?" >> gpurun_out/${TAG}_fof_lc_lib.log; tail -6 gpurun_out/${TAG}_fof_lc_lib.log
+      timeout 90 python -m pytest tests/test_dropin_driver.py -q -m gpu -p no:cacheprovider -rA -k "lightcone_driver or matchmaker_driver" \
+        --basetemp=gpurun_out/${TAG}_tmp_drv > gpurun_out/${TAG}_fof_lc_drv.log 2>&1
+      echo "rc=$?" >> gpurun_out/${TAG}_fof_lc_drv.log; tail -6 gpurun_out/${TAG}_fof_lc_drv.log
+      find gpurun_out/${TAG}_tmp_lib gpurun_out/${TAG}_tmp_drv -type f -size +20M -delete 2>/dev/null
+      timeout 70 python tools/fof_lc_probe.py > gpurun_out/${TAG}_fof_lc_probe.json 2> gpurun_out/${TAG}_fof_lc_probe.err
+      tail -c 1500 gpurun_out/${TAG}_fof_lc_probe.json; tail -3 gpurun_out/${TAG}_fof_lc_probe.err
+      timeout 50 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/${TAG}_fof_lc_launches.csv \
+        python tools/fof_lc_probe.py --n1d 128 --lc-n1d 64 --reps 1 > gpurun_out/${TAG}_fof_lc_launches.log 2>&1
+      tail -2 gpurun_out/${TAG}_fof_lc_launches.log ;;
     smi)
       nvidia-smi --query-gpu=index,name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv | tee gpurun_out/${TAG}_smi.txt
       nvidia-smi topo -m | head -12 | tee -a gpurun_out/${TAG}_smi.txt; nproc | tee -a gpurun_out/${TAG}_smi.txt; free -g | head -2 | tee -a gpurun_out/${TAG}_smi.txt ;;
