@@ -35,17 +35,36 @@ __global__ void k_fof_step(size_t n, F f) {
   for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) f(i);
 }
 
+template <class F>
+__global__ void k_fof_warp_step(size_t n, F f) {      // one warp per index, every lane calls f(i)
+  const size_t w = (blockIdx.x * (size_t) blockDim.x + threadIdx.x) >> 5, nw = ((size_t) gridDim.x * blockDim.x) >> 5;
+  for (size_t i = w; i < n; i += nw) f(i);
+}
+
 struct DeviceBackend {
   Ctx &c;
+  // work arrays are carved out of a few large device allocations (about thirty arrays per call; cudaMalloc and cudaFree
+  // of each would cost more than most of the steps)
   std::vector<void *> owned;
-  explicit DeviceBackend(Ctx &c_) : c(c_) {}
+  char *cur = nullptr;
+  size_t left = 0, chunk;
+  explicit DeviceBackend(Ctx &c_) : c(c_), chunk(std::max((size_t) 32 << 20, (size_t) 48 * (size_t) c_.np)) {}
   ~DeviceBackend() { for (void *q : owned) cudaFree(q); }
 
   template <class T> T *alloc(size_t n) {
-    void *q = nullptr;
-    CK(cudaMalloc(&q, (n ? n : 1) * sizeof(T)));
-    owned.push_back(q);
-    return (T *) q;
+    const size_t bytes = (((n ? n : 1) * sizeof(T)) + 255) & ~(size_t) 255;
+    if (bytes > left) {
+      void *q = nullptr;
+      const size_t sz = std::max(bytes, chunk);
+      CK(cudaMalloc(&q, sz));
+      owned.push_back(q);
+      cur = (char *) q;
+      left = sz;
+    }
+    T *r = (T *) cur;
+    cur += bytes;
+    left -= bytes;
+    return r;
   }
   void zero(void *p, size_t bytes) { if (bytes) CK(cudaMemsetAsync(p, 0, bytes, c.stream)); }
   template <class F> void run(size_t n, F f, int block = 256) {
@@ -53,6 +72,21 @@ struct DeviceBackend {
     k_fof_step<F><<<grid_for(n, block, 64), block, 0, c.stream>>>(n, f);
     CK(cudaGetLastError());
     c.launches++;
+  }
+  template <class F> void run_warp(size_t n, F f) {
+    if (!n) return;
+    k_fof_warp_step<F><<<grid_for(n * 32, 128, 64), 128, 0, c.stream>>>(n, f);
+    CK(cudaGetLastError());
+    c.launches++;
+  }
+  // search cells for n particles: up to 160 per particle (Dfof = 0.2 mean distances needs 125), within a quarter of the
+  // memory that is free once the ~96 bytes per particle of the search itself are set aside
+  size_t max_cells(size_t n) {
+    if (const char *e = getenv("MGP_FOF_MAX_CELLS")) return (size_t) strtoull(e, nullptr, 10);
+    size_t fr = 0, tot = 0;
+    CK(cudaMemGetInfo(&fr, &tot));
+    const size_t need = 96 * n, avail = fr > need ? fr - need : 0;
+    return std::max(n / 8 + 1, std::min(avail / 16, 160 * n + (1u << 20)));
   }
   void scan(unsigned *p, size_t n) {
     size_t tb = 0;

@@ -51,11 +51,13 @@ struct Geometry {
   double boxsize;
   // search cells (the library's own: any cell size >= Dfof finds the same pairs as the reference's cells do)
   int ncx, ncy, ncz;
-  float icx, icy, icz; // 1 / cell size
+  double icx, icy, icz; // 1 / cell size (double: the cell of a coordinate is exact to 1e-12 cells whatever the mesh)
 };
 
-// edge / edge_right: x_offset of this task and of its right neighbour; slab_fraction: Local_nx / Nmesh
-inline Geometry geometry(const mgp_fof_config &cfg, int nsample, float edge, float edge_right, double slab_fraction) {
+// edge / edge_right: x_offset of this task and of its right neighbour; slab_fraction: Local_nx / Nmesh; max_cells: how
+// many search cells the caller can afford (4 bytes each)
+inline Geometry geometry(const mgp_fof_config &cfg, int nsample, float edge, float edge_right, double slab_fraction,
+                         size_t max_cells) {
   Geometry g;
   g.boxsize = cfg.boxsize;
   g.edge = edge;
@@ -67,13 +69,19 @@ inline Geometry geometry(const mgp_fof_config &cfg, int nsample, float edge, flo
   g.d2fof = g.dfof * g.dfof;
   g.lbox = (float) cfg.boxsize;
   g.lbox_half = (float) (cfg.boxsize / 2);
-  // search cells: one mean inter-particle distance, never less than the linking length (with a margin for the rounding
-  // of x * (1 / cell)); y and z tile the periodic box, x covers the slab and its strip and clamps what lies beyond
-  const double cs = std::max((double) g.dfof * 1.001, (double) ipd);
-  g.ncy = g.ncz = std::max(1, (int) std::floor(cfg.boxsize / cs));
-  g.icy = g.icz = (float) ((double) g.ncy / cfg.boxsize);
-  g.ncx = (int) std::floor((cfg.boxsize * slab_fraction + cfg.dx_extra) / cs) + 1;
-  g.icx = (float) (1.0 / cs);
+  // search cells: as close to one linking length as `max_cells` allows (the candidates of a particle are the contents
+  // of 27 cells: at Dfof = 0.2 mean distances a cell of one mean distance holds 125 times the particles a cell of Dfof
+  // does, and the cores of halos are where the pair tests are), never less than the linking length (with a margin);
+  // y and z tile the periodic box, x covers the slab and its strip and clamps what lies beyond
+  double cs = (double) g.dfof * 1.001;
+  for (;;) {
+    g.ncy = g.ncz = std::max(1, (int) std::floor(cfg.boxsize / cs));
+    g.ncx = (int) std::floor((cfg.boxsize * slab_fraction + cfg.dx_extra) / cs) + 1;
+    if ((double) g.ncx * (double) g.ncy * (double) g.ncz <= (double) max_cells || g.ncy == 1) break;
+    cs *= 1.125;
+  }
+  g.icy = g.icz = (double) g.ncy / cfg.boxsize;
+  g.icx = 1.0 / cs;
   return g;
 }
 
@@ -106,8 +114,8 @@ FOF_HD float translate_vel_sd(float vel, float f1, float f2, float norm_vel_f) {
   return FF_MUL(norm_vel_f, FF_ADD(vel, FF_ADD(f1, f2)));
 }
 
-FOF_HD int cell_coord(float x, float inv, int n) {
-  int c = (int) (x * inv);
+FOF_HD int cell_coord(float x, double inv, int n) {
+  int c = (int) ((double) x * inv);
   if (c < 0) c = 0;
   if (c >= n) c = n - 1;
   return c;
@@ -138,11 +146,24 @@ FOF_HD unsigned find_root(Load &&load, unsigned i) {
     i = p;
   }
 }
-template <class Load, class Cas>
-FOF_HD void unite(Load &&load, Cas &&cas, unsigned a, unsigned b) {
+// the same walk with path halving: a particle on the way is re-pointed at its grandparent.  Safe beside concurrent
+// unions: only a particle that is no root (and never will be one again) is written, and only with one of its ancestors.
+template <class Load, class Store>
+FOF_HD unsigned find_root_halving(Load &&load, Store &&store, unsigned i) {
   for (;;) {
-    a = find_root(load, a);
-    b = find_root(load, b);
+    const unsigned p = load(i);
+    if (p == i) return i;
+    const unsigned gp = load(p);
+    if (gp == p) return p;
+    store(i, gp);
+    i = gp;
+  }
+}
+template <class Load, class Store, class Cas>
+FOF_HD void unite(Load &&load, Store &&store, Cas &&cas, unsigned a, unsigned b) {
+  for (;;) {
+    a = find_root_halving(load, store, a);
+    b = find_root_halving(load, store, b);
     if (a == b) return;
     if (a < b) { const unsigned t = a; a = b; b = t; }
     if (cas(a, a, b) == a) return;          // a was still a root: hooked.  Otherwise somebody else hooked it: again
@@ -181,20 +202,28 @@ FOF_HD void jacobi3(double a[9], double w[3], double v[9]) {
   for (int i = 0; i < 3; i++) w[i] = a[i * 3 + i];
 }
 
-// get_halos, mm_fof.c:468-611, for one halo: its np members ids[0 .. np) in increasing index order (= the reference's
-// order: sorted by x, the buffer particles last) of the particle arrays x[3][stride], v[3][stride].
-FOF_HD void halo_properties(const Geometry &g, const float *x, const float *v, size_t stride, const unsigned *ids, int np,
-                            double mass_particle, mgp_fof_halo &h) {
+// get_halos, mm_fof.c:468-611, for one halo of np members.  fetch(j, xx, vv) delivers position and velocity of the j-th
+// member in increasing index order (= the reference's order: sorted by x, the buffer particles last); it is called for
+// j = 0 .. np-1 twice.  On the device a whole warp runs this function for one halo, every lane the same arithmetic: the
+// fetcher has the lanes load 32 members at a time (fof_impl.cuh), the sums stay the sequential ones of the reference.
+template <class Fetch>
+FOF_HD void halo_properties(const Geometry &g, Fetch &&fetch, int np, double mass_particle, mgp_fof_halo &h) {
   const double L = g.boxsize;
   double xs[3] = {0, 0, 0}, vs[3] = {0, 0, 0};
   for (int j = 0; j < np; j++) {                      // centre of mass; the running mean picks the periodic image (490-511)
-    const unsigned ip = ids[j];
+    float xf[3], vf[3];
+    fetch(j, xf, vf);
     for (int ax = 0; ax < 3; ax++) {
-      double xx = (double) x[ax * stride + ip];
-      const double vv = (double) v[ax * stride + ip];
+      double xx = (double) xf[ax];
+      const double vv = (double) vf[ax];
       if (j > 0) {
-        const double cm = FD_DIV(xs[ax], (double) j);
-        if (FD_MUL(2.0, fabs(FD_SUB(xx, cm))) > L) {
+        // the reference's test is 2 |xx - xs / j| > L.  j |xx - xs / j| = |xx j - xs| to a few ulps, and a member is either
+        // near the running mean or a box away from it: only within 2 % of the threshold is the division needed to decide
+        // as the reference does
+        const double dj = (double) j, t2 = FD_MUL(2.0, fabs(FD_SUB(FD_MUL(xx, dj), xs[ax]))), Lj = FD_MUL(L, dj);
+        bool far = t2 > FD_MUL(1.02, Lj);
+        if (!far && !(t2 < FD_MUL(0.98, Lj))) far = FD_MUL(2.0, fabs(FD_SUB(xx, FD_DIV(xs[ax], dj)))) > L;
+        if (far) {
           if (FD_MUL(2.0, xx) > L) xx = FD_SUB(xx, L); else xx = FD_ADD(xx, L);
         }
       }
@@ -206,15 +235,16 @@ FOF_HD void halo_properties(const Geometry &g, const float *x, const float *v, s
   for (int ax = 0; ax < 3; ax++) { xavg[ax] = (float) FD_DIV(xs[ax], (double) np); vavg[ax] = (float) FD_DIV(vs[ax], (double) np); }
   double xr[3] = {0, 0, 0}, vr[3] = {0, 0, 0}, lam[3] = {0, 0, 0}, in[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (int j = 0; j < np; j++) {                      // quantities relative to the centre of mass (519-555)
-    const unsigned ip = ids[j];
+    float xf[3], vf[3];
+    fetch(j, xf, vf);
     double dx[3], dv[3];
     for (int ax = 0; ax < 3; ax++) {
-      double xx = (double) x[ax * stride + ip];
+      double xx = (double) xf[ax];
       if (FD_MUL(2.0, fabs(FD_SUB(xx, (double) xavg[ax]))) > L) {
         if (FD_MUL(2.0, xx) > L) xx = FD_SUB(xx, L); else xx = FD_ADD(xx, L);
       }
       dx[ax] = FD_SUB(xx, (double) xavg[ax]);
-      dv[ax] = FD_SUB((double) v[ax * stride + ip], (double) vavg[ax]);
+      dv[ax] = FD_SUB((double) vf[ax], (double) vavg[ax]);
     }
     for (int ax = 0; ax < 3; ax++) { xr[ax] = FD_ADD(xr[ax], FD_MUL(dx[ax], dx[ax])); vr[ax] = FD_ADD(vr[ax], FD_MUL(dv[ax], dv[ax])); }
     for (int ax = 0; ax < 3; ax++)

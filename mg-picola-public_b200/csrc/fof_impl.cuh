@@ -5,6 +5,7 @@
 // arithmetic.
 #pragma once
 
+#include <algorithm>
 #include <vector>
 
 #include "fof.cuh"
@@ -36,6 +37,7 @@ struct Atom {
 #endif
   }
   static FOF_HD unsigned load(const unsigned *p) { return *(const volatile unsigned *) p; }
+  static FOF_HD void store(unsigned *p, unsigned v) { *(volatile unsigned *) p = v; }
 };
 
 // the particle store as the library keeps it: 16-byte records, or [3][cap] arrays for the
@@ -118,31 +120,31 @@ struct IotaStep {
   FOF_HD void operator()(size_t f) const { parent[f] = (unsigned) f; }
 };
 
-struct LinkStep {         // every pair of friends, each once (the partner with the smaller index), in the 27 cells around
+struct LinkStep {         // every pair of friends, each once: the rest of the own cell and the 13 cells "ahead" of it
   const float4 *packed; const unsigned *start; Geometry g; unsigned *parent;
   FOF_HD static unsigned word(float f) { union { unsigned u; float fl; } w; w.fl = f; return w.u; }
   FOF_HD void operator()(size_t s) const {
     unsigned *par = parent;
     auto load = [par](unsigned i) { return Atom::load(par + i); };
+    auto store = [par](unsigned i, unsigned v) { Atom::store(par + i, v); };
     auto cas = [par](unsigned at, unsigned expect, unsigned desired) { return Atom::cas(par + at, expect, desired); };
     const float4 me = packed[s];
     const unsigned fme = word(me.w);
     const int cx = cell_coord(me.x, g.icx, g.ncx), cy = cell_coord(me.y, g.icy, g.ncy), cz = cell_coord(me.z, g.icz, g.ncz);
-    for (int ox = -1; ox <= 1; ox++) {
+    const unsigned own = ((unsigned) cx * (unsigned) g.ncy + (unsigned) cy) * (unsigned) g.ncz + (unsigned) cz;
+    for (unsigned t = (unsigned) s + 1u, t1 = start[own + 1]; t < t1; t++) {
+      const float4 o = packed[t];
+      if (linked(g, me.x, me.y, me.z, o.x, o.y, o.z)) unite(load, store, cas, fme, word(o.w));
+    }
+    for (int k = 14; k < 27; k++) {                                   // (ox, oy, oz) after (0, 0, 0) in lexicographic order
+      const int ox = k / 9 - 1, oy = (k / 3) % 3 - 1, oz = k % 3 - 1;
       const int x2 = cx + ox;
-      if (x2 < 0 || x2 >= g.ncx) continue;                          // x is open
-      for (int oy = -1; oy <= 1; oy++) {
-        const int y2 = (cy + oy + g.ncy) % g.ncy;
-        for (int oz = -1; oz <= 1; oz++) {
-          const int z2 = (cz + oz + g.ncz) % g.ncz;
-          const unsigned c2 = ((unsigned) x2 * (unsigned) g.ncy + (unsigned) y2) * (unsigned) g.ncz + (unsigned) z2;
-          const unsigned t1 = start[c2 + 1];
-          for (unsigned t = start[c2]; t < t1; t++) {
-            const float4 o = packed[t];
-            const unsigned fo = word(o.w);
-            if (fo < fme && linked(g, me.x, me.y, me.z, o.x, o.y, o.z)) unite(load, cas, fme, fo);
-          }
-        }
+      if (x2 >= g.ncx) continue;                                      // x is open
+      const int y2 = (cy + oy + g.ncy) % g.ncy, z2 = (cz + oz + g.ncz) % g.ncz;
+      const unsigned c2 = ((unsigned) x2 * (unsigned) g.ncy + (unsigned) y2) * (unsigned) g.ncz + (unsigned) z2;
+      for (unsigned t = start[c2], t1 = start[c2 + 1]; t < t1; t++) {
+        const float4 o = packed[t];
+        if (linked(g, me.x, me.y, me.z, o.x, o.y, o.z)) unite(load, store, cas, fme, word(o.w));
       }
     }
   }
@@ -204,11 +206,38 @@ struct SegmentStep {      // where a halo's members start in the list sorted by 
   }
 };
 
-struct PropsStep {
+// member j of a halo for halo_properties.  Device: the 32 lanes of the warp that owns the halo each load one member of
+// the current chunk of 32 (the loads of a chunk are in flight together instead of one dependent pair per member) and
+// hand it round by shuffles; every lane must call with the same j.  Host: a plain lookup.
+struct MemberFetch {
+  const float *x, *v; size_t N; const unsigned *ids; int np;
+  float cx[3], cv[3];
+  FOF_HD void operator()(int j, float xf[3], float vf[3]) {
+#if defined(__CUDA_ARCH__)
+    if ((j & 31) == 0) {
+      const int m = j + (int) (threadIdx.x & 31u);
+      if (m < np) {
+        const unsigned ip = ids[m];
+        for (int a = 0; a < 3; a++) { cx[a] = x[a * N + ip]; cv[a] = v[a * N + ip]; }
+      }
+    }
+    for (int a = 0; a < 3; a++) { xf[a] = __shfl_sync(0xffffffffu, cx[a], j & 31); vf[a] = __shfl_sync(0xffffffffu, cv[a], j & 31); }
+#else
+    const unsigned ip = ids[j];
+    for (int a = 0; a < 3; a++) { xf[a] = x[a * N + ip]; vf[a] = v[a * N + ip]; }
+#endif
+  }
+};
+
+struct PropsStep {        // one warp (device) / one call (host) per halo
   Geometry g; const float *x, *v; size_t N; const unsigned *members, *seg, *cnt; double mass_particle; mgp_fof_halo *out;
   FOF_HD void operator()(size_t h) const {
     mgp_fof_halo r;
-    halo_properties(g, x, v, N, members + seg[h], (int) cnt[h], mass_particle, r);
+    MemberFetch f{x, v, N, members + seg[h], (int) cnt[h], {0, 0, 0}, {0, 0, 0}};
+    halo_properties(g, f, (int) cnt[h], mass_particle, r);
+#if defined(__CUDA_ARCH__)
+    if ((threadIdx.x & 31u) != 0) return;
+#endif
     out[h] = r;
   }
 };
@@ -220,8 +249,9 @@ struct Task {             // who this task is among the P tasks of the run
 
 inline void check(bool ok, const char *what);   // provided by the back end's translation unit (throws)
 
-// B: alloc<T>(n), zero(p, bytes), run(n, functor[, block]), scan(p, n) (exclusive, in place), sort(k0, k1, v0, v1, n, bits)
-// (stable, ascending, result in k1 / v1), copy(dst, src, bytes), read32 / read64(p), download(host, dev, bytes),
+// B: alloc<T>(n), zero(p, bytes), run(n, functor[, block]), run_warp(n, functor) (one warp per index on the device),
+// max_cells(n) (search cells the memory allows for n particles), scan(p, n) (exclusive, in place), sort(k0, k1, v0, v1,
+// n, bits) (stable, ascending, result in k1 / v1), read32 / read64(p), download(host, dev, bytes),
 // gather2(mine[2], all[2 P]), strip_exchange(x, v, N, n_dom, n_toleft, n_buf), flag_exchange(send, n_buf, recv, n_toleft)
 template <class B>
 void find_halos(B &be, const Store &st, size_t n_dom, const Task &tk, const mgp_fof_config &cfg, std::vector<mgp_fof_halo> &halos) {
@@ -243,8 +273,8 @@ void find_halos(B &be, const Store &st, size_t n_dom, const Task &tk, const mgp_
   const int right = (tk.rank + 1) % tk.P;
   const size_t n_toleft = (size_t) all[2 * (size_t) tk.rank], n_buf = (size_t) all[2 * (size_t) right];
   const float edge_right = (float) ((double) all[2 * (size_t) right + 1] * (cfg.boxsize / (double) tk.nsample));
-  const Geometry g = geometry(cfg, tk.nsample, edge, edge_right, tk.slab_fraction);
   const size_t N = n_dom + n_buf;
+  const Geometry g = geometry(cfg, tk.nsample, edge, edge_right, tk.slab_fraction, std::min(be.max_cells(N), (size_t) 0xffffff00ull));
   check(N < 0xfffffff0ull, "mgp_fof_find: more than 2^32 particles on one rank");
   const size_t ncell = (size_t) g.ncx * (size_t) g.ncy * (size_t) g.ncz;
   check(ncell < 0xfffffff0ull, "mgp_fof_find: more than 2^32 search cells on one rank");
@@ -301,7 +331,7 @@ void find_halos(B &be, const Store &st, size_t n_dom, const Task &tk, const mgp_
 
   // 6. properties: one thread per halo walks its members in the reference's order
   mgp_fof_halo *d_out = be.template alloc<mgp_fof_halo>(n_halos);
-  be.run(n_halos, PropsStep{g, x, v, N, mval1, seg, cnt, 1.0e10 * cfg.mass_part, d_out}, 64);
+  be.run_warp(n_halos, PropsStep{g, x, v, N, mval1, seg, cnt, 1.0e10 * cfg.mass_part, d_out});
   halos.resize(n_halos);
   be.download(halos.data(), d_out, n_halos * sizeof(mgp_fof_halo));
   std::stable_sort(halos.begin(), halos.end(), [](const mgp_fof_halo &a, const mgp_fof_halo &b) { return a.np > b.np; });   // mm_fof.c:459

@@ -12,28 +12,56 @@
 
 namespace mgp {
 
-template <bool WRITE>
+// Slots of the leaving images: the lanes of a warp vote per replicate, one lane adds the warp's number to the replicate's
+// counter and the lanes take consecutive slots behind the value it got back.  (One atomic per image on a few dozen
+// addresses serialises in L2: 20 ns each, measured -- profiles/r02r_fof_lc.md.)  The counting pass adds into a per-CTA copy
+// of the counters in shared memory first (SMEM_COUNT; nrep * 8 bytes of dynamic shared memory).
+template <bool WRITE, bool SMEM_COUNT>
 __global__ void __launch_bounds__(256)
 k_lightcone(size_t n, float4 *__restrict__ pA, const float4 *__restrict__ pB, const float4 *__restrict__ pC,
             const float2 *__restrict__ pE, lc::Params p, unsigned long long *__restrict__ count,
             const unsigned long long *__restrict__ offset, float *__restrict__ rows, int *__restrict__ over_flag) {
+  extern __shared__ unsigned long long s_count[];
+  unsigned long long *cnt = count;
+  if (SMEM_COUNT) {
+    for (int r = threadIdx.x; r < p.nrep; r += blockDim.x) s_count[r] = 0ull;
+    __syncthreads();
+    cnt = s_count;
+  }
+  const unsigned lane = threadIdx.x & 31u;
   bool over = false;
-  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
-    float4 a = pA[i];
-    const float4 b = pB[i], d = pC[i];
-    const float2 e = pE[i];
+  const size_t n_pad = (n + 31) & ~(size_t) 31;            // the lanes of a warp stay together: they vote in every replicate
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n_pad; i += (size_t) gridDim.x * blockDim.x) {
+    const bool valid = i < n;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, d = a;
+    float2 e = make_float2(0.f, 0.f);
+    if (valid) { a = pA[i]; b = pB[i]; d = pC[i]; e = pE[i]; }
     lc::Particle q;
     q.pos[0] = a.x; q.pos[1] = a.y; q.pos[2] = a.z;
     q.vel[0] = b.x; q.vel[1] = b.y; q.vel[2] = b.z;
     q.d[0] = d.x; q.d[1] = d.y; q.d[2] = d.z;
     q.d2[0] = d.w; q.d2[1] = e.x; q.d2[2] = e.y;
-    over |= lc::particle<WRITE>(p, q, offset, rows, [&](int r) { return atomicAdd(&count[r], 1ull); });
-    if (WRITE) {
+    over |= lc::particle<WRITE>(p, q, valid, offset, rows, [&](int r, bool out) -> unsigned long long {
+      const unsigned m = __ballot_sync(0xffffffffu, out);
+      if (m == 0u) return 0ull;
+      const int leader = __ffs(m) - 1;
+      unsigned long long base = 0ull;
+      if ((int) lane == leader) base = atomicAdd(&cnt[r], (unsigned long long) __popc(m));
+      if (!WRITE) return 0ull;                             // the counting pass needs no slot
+      base = __shfl_sync(0xffffffffu, base, leader);
+      return base + (unsigned long long) __popc(m & ((1u << lane) - 1u));
+    });
+    if (WRITE && valid) {
       a.x = q.pos[0]; a.y = q.pos[1]; a.z = q.pos[2];
       pA[i] = a;
     }
   }
   if (over) *over_flag = 1;
+  if (SMEM_COUNT) {
+    __syncthreads();
+    for (int r = threadIdx.x; r < p.nrep; r += blockDim.x)
+      if (s_count[r]) atomicAdd(&count[r], s_count[r]);
+  }
 }
 
 namespace {
@@ -101,8 +129,13 @@ void count_pass(Ctx &c, const lc::Params &p, LcDevice &dv, std::vector<unsigned 
   CK(cudaMemsetAsync(dv.count, 0, (size_t) 2 * nr * sizeof(unsigned long long), c.stream));
   CK(cudaMemsetAsync(c.d_flag, 0, sizeof(int), c.stream));
   if (c.np) {
-    k_lightcone<false><<<grid_for(c.np, 256), 256, 0, c.stream>>>(c.np, c.pA, c.pB, c.pC, (const float2 *) c.pE, p, dv.count,
-                                                               dv.offset, nullptr, c.d_flag);
+    if (p.nrep <= 4096)       // 32 KB of counters per CTA at most
+      k_lightcone<false, true><<<grid_for(c.np, 256), 256, (size_t) nr * sizeof(unsigned long long), c.stream>>>(
+          c.np, c.pA, c.pB, c.pC, (const float2 *) c.pE, p, dv.count, dv.offset, nullptr, c.d_flag);
+    else
+      k_lightcone<false, false><<<grid_for(c.np, 256), 256, 0, c.stream>>>(c.np, c.pA, c.pB, c.pC, (const float2 *) c.pE, p,
+                                                                          dv.count, dv.offset, nullptr, c.d_flag);
+    CK(cudaGetLastError());
     c.launches++;
   }
   CK(cudaMemcpyAsync(cnt.data(), dv.count, (size_t) nr * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
@@ -147,8 +180,9 @@ void lightcone_drift(Ctx &c, const mgp_lightcone_step *ls, uint64_t cap, float *
   CK(cudaMemcpyAsync(dv.offset, off.data(), off.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, c.stream));
   CK(cudaMemsetAsync(dv.count, 0, off.size() * sizeof(unsigned long long), c.stream));
   if (c.np) {
-    k_lightcone<true><<<grid_for(c.np, 256), 256, 0, c.stream>>>(c.np, c.pA, c.pB, c.pC, (const float2 *) c.pE, p, dv.count,
-                                                              dv.offset, dv.rows, c.d_flag);
+    k_lightcone<true, false><<<grid_for(c.np, 256), 256, 0, c.stream>>>(c.np, c.pA, c.pB, c.pC, (const float2 *) c.pE, p,
+                                                                       dv.count, dv.offset, dv.rows, c.d_flag);
+    CK(cudaGetLastError());
     c.launches++;
   }
   std::vector<float> packed((size_t) total * 6);

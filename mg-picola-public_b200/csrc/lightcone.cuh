@@ -122,26 +122,28 @@ LC_HD void advance(const Params &p, Particle &q, const double dp[3]) {
   for (int a = 0; a < 3; a++) q.pos[a] = wrap_f((float) LC_ADD((double) q.pos[a], dp[a]), p.boxf);
 }
 
-// One particle of the loop.  WRITE = false: count the images that leave (count[r]++); WRITE = true: also form their rows
-// at rows[(offset[r] + slot) * 6] and advance the particle.  `bump(r)` returns the slot of a new row of replicate r (an
-// atomic increment on the device, a plain one in the host emulation).  Returns true if Delta_Pos exceeds the boundary.
+// One particle of the loop.  WRITE = false: count the images that leave; WRITE = true: also form their rows at
+// rows[(offset[r] + slot) * 6] and advance the particle.  `bump(r, out)` is called for EVERY replicate (on the device by all
+// lanes of the warp together: one atomic per warp and replicate, the lanes' slots from a ballot; a plain increment in the
+// host emulation) and returns the slot of the new row of replicate r when `out` is set.  `valid` = false: a lane beyond
+// the last particle that only takes part in the ballots.  Returns true if Delta_Pos exceeds the boundary.
 template <bool WRITE, class Bump>
-LC_HD bool particle(const Params &p, Particle &q, const unsigned long long *offset, float *rows, Bump &&bump) {
+LC_HD bool particle(const Params &p, Particle &q, bool valid, const unsigned long long *offset, float *rows, Bump &&bump) {
   double dp[3];
-  const bool over = delta_pos(p, q, dp);
+  const bool over = delta_pos(p, q, dp) && valid;
   for (int r = 0; r < p.nrep; r++) {
     const int i = p.rep[3 * r], j = p.rep[3 * r + 1], k = p.rep[3 * r + 2];
-    double ro2, rn2;
-    if (!leaves(p, q, dp, i, j, k, ro2, rn2)) continue;
-    const unsigned long long slot = bump(r);
-    if (WRITE) {
+    double ro2 = 0.0, rn2 = 0.0;
+    const bool out = valid && leaves(p, q, dp, i, j, k, ro2, rn2);
+    const unsigned long long slot = bump(r, out);
+    if (WRITE && out) {
       float row[6];
       exit_row(p, q, i, j, k, ro2, rn2, row);
       float *o = rows + (size_t) (offset[r] + slot) * 6;
       for (int a = 0; a < 6; a++) o[a] = row[a];
     }
   }
-  if (WRITE) advance(p, q, dp);
+  if (WRITE && valid) advance(p, q, dp);
   return over;
 }
 

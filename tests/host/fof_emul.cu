@@ -44,6 +44,11 @@ struct HostBackend {
   template <class T> T *alloc(size_t n) { void *q = malloc((n ? n : 1) * sizeof(T)); owned.push_back(q); return (T *) q; }
   void zero(void *p, size_t bytes) { memset(p, 0, bytes); }
   template <class F> void run(size_t n, F f, int = 256) { for (size_t i = 0; i < n; i++) f(i); }
+  template <class F> void run_warp(size_t n, F f) { for (size_t i = 0; i < n; i++) f(i); }
+  size_t max_cells(size_t n) {
+    if (const char *e = getenv("MGP_FOF_MAX_CELLS")) return (size_t) strtoull(e, nullptr, 10);
+    return 160 * n + (1u << 20);
+  }
   void scan(unsigned *p, size_t n) { unsigned s = 0; for (size_t i = 0; i < n; i++) { const unsigned t = p[i]; p[i] = s; s += t; } }
   void sort(unsigned *k0, unsigned *k1, unsigned *v0, unsigned *v1, size_t n, int bits) {
     const unsigned mask = bits >= 32 ? 0xffffffffu : ((1u << bits) - 1u);

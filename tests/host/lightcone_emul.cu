@@ -30,14 +30,14 @@ extern "C" int lc_emul(long n, const float *pos, const float *vel, const float *
   bool over = false;
   for (long i = 0; i < n; i++) {
     lc::Particle q = load(i);
-    over |= lc::particle<false>(p, q, off.data(), nullptr, [&](int r) { return cnt[r]++; });
+    over |= lc::particle<false>(p, q, true, off.data(), nullptr, [&](int r, bool out) { return out ? cnt[r]++ : 0ull; });
   }
   unsigned long long total = 0;
   for (int r = 0; r < nrep; r++) { off[r] = total; total += cnt[r]; count[r] = cnt[r]; }
   if (over) return 1;
   for (long i = 0; i < n; i++) {
     lc::Particle q = load(i);
-    lc::particle<true>(p, q, off.data(), rows_out, [&](int r) { return cur[r]++; });
+    lc::particle<true>(p, q, true, off.data(), rows_out, [&](int r, bool out) { return out ? cur[r]++ : 0ull; });
     for (int a = 0; a < 3; a++) newpos[3 * i + a] = q.pos[a];
   }
   for (int r = 0; r < nrep; r++) if (cur[r] != cnt[r]) return 2;

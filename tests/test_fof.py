@@ -129,6 +129,24 @@ def test_gpu_steps_on_emulated_tasks_match_oracle(case, emul, ntask, mode):
         fc.assert_same_halos(em[r], orc[r], exact_vectors=False)
 
 
+@pytest.mark.parametrize("max_cells", [1, 300, 20000])
+def test_gpu_steps_do_not_depend_on_the_search_cells(case, emul, max_cells, monkeypatch):
+    """The search cells are as fine as memory allows (csrc/fof.cuh::geometry); with any budget -- one cell per direction,
+    cells of several linking lengths -- the catalogue is the reference's bit for bit."""
+    c = case
+    monkeypatch.setenv("MGP_FOF_MAX_CELLS", str(max_cells))
+    res = fc.emulated_halos(emul, [dict(pos=c["pos"], vel=c["vel"], D=c["D"], D2=c["D2"], local_p_start=0)], N1D, N1D, c["cfg"],
+                            BOX * c["cfg"]["norm_pos"])
+    fc.assert_same_halos(res[0], c["ref"])
+    tasks = fc.split_tasks(c["pos"], c["vel"], c["D"], c["D2"], 2, N1D, BOX)
+    monkeypatch.delenv("MGP_FOF_MAX_CELLS")
+    fine = fc.emulated_halos(emul, tasks, N1D, N1D, c["cfg"], BOX * c["cfg"]["norm_pos"])
+    monkeypatch.setenv("MGP_FOF_MAX_CELLS", str(max_cells))
+    coarse = fc.emulated_halos(emul, tasks, N1D, N1D, c["cfg"], BOX * c["cfg"]["norm_pos"])
+    for a, b in zip(fine, coarse):
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
 def test_gpu_steps_edge_cases(emul):
     """No halo at all (uniform particles), np_min above every group, a rank without particles in its strip."""
     rng = np.random.default_rng(11)
@@ -166,6 +184,15 @@ def test_cuda_halo_finder_matches_reference(mgp, require_gpu, case):
     h2 = pm.MatchMaker(cfg["norm_pos"], cfg["norm_vel"], BOX * cfg["norm_pos"], cfg["dx_extra"], cfg["b_fof"], cfg["np_min"],
                        cfg["mass_part"], cfg["dDdy"], cfg["dD2dy"])
     assert np.array_equal(h.view(np.uint8), h2.view(np.uint8))
+    # nor on the size of the search cells (as fine as memory allows by default)
+    for max_cells in ("300", "20000"):
+        os.environ["MGP_FOF_MAX_CELLS"] = max_cells
+        try:
+            h3 = pm.MatchMaker(cfg["norm_pos"], cfg["norm_vel"], BOX * cfg["norm_pos"], cfg["dx_extra"], cfg["b_fof"], cfg["np_min"],
+                               cfg["mass_part"], cfg["dDdy"], cfg["dD2dy"])
+        finally:
+            del os.environ["MGP_FOF_MAX_CELLS"]
+        assert np.array_equal(h.view(np.uint8), h3.view(np.uint8))
     pm.close()
 
 

@@ -66,7 +66,7 @@ PY
       timeout 70 python tools/fof_lc_probe.py > gpurun_out/${TAG}_fof_lc_probe.json 2> gpurun_out/${TAG}_fof_lc_probe.err
       tail -c 1500 gpurun_out/${TAG}_fof_lc_probe.json; tail -3 gpurun_out/${TAG}_fof_lc_probe.err
       timeout 50 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/${TAG}_fof_lc_launches.csv \
-        python tools/fof_lc_probe.py --n1d 128 --lc-n1d 64 --reps 1 > gpurun_out/${TAG}_fof_lc_launches.log 2>&1
+        python tools/fof_lc_probe.py --n1d 256 --lc-n1d 128 --reps 1 > gpurun_out/${TAG}_fof_lc_launches.log 2>&1
       tail -2 gpurun_out/${TAG}_fof_lc_launches.log ;;
     smi)
       nvidia-smi --query-gpu=index,name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv | tee gpurun_out/${TAG}_smi.txt
