@@ -420,16 +420,26 @@ class PM:
         self._ck(self.L.mgp_lightcone_count(self.ctx, C.byref(ls), _ptr(cnt)))
         return cnt[:ls.nrep]
 
-    def Drift_Lightcone(self, sc, reps, sumxyz=None, cap=None):
-        """The particle loop of Drift_Lightcone: drifts the particles and returns [rows of replicate r, float32 [count][6]]."""
+    def Drift_Lightcone(self, sc, reps, sumxyz=None, cap=None, pinned=False):
+        """The particle loop of Drift_Lightcone: drifts the particles and returns [rows of replicate r, float32 [count][6]].
+        pinned: receive the rows in a page-locked block (mgp_alloc_host), as the C adapter does."""
         ls, keep = self._lightcone_step(sc, reps, sumxyz)
         if cap is None:
             c0 = self.lightcone_count(sc, reps, sumxyz)
             cap = int(c0.max()) if c0.size else 0
         cnt = np.zeros(max(ls.nrep, 1), np.uint64)
-        block = np.zeros((max(ls.nrep, 1), max(cap, 1), 6), np.float32)
-        self._ck(self.L.mgp_drift_lightcone(self.ctx, C.byref(ls), cap, _ptr(block), _ptr(cnt)))
-        return [block[r, :int(cnt[r])].copy() for r in range(ls.nrep)]
+        shape = (max(ls.nrep, 1), max(cap, 1), 6)
+        host = self.L.mgp_alloc_host(4 * shape[0] * shape[1] * shape[2]) if pinned else None
+        try:
+            if host:
+                block = np.ctypeslib.as_array(C.cast(host, C.POINTER(C.c_float)), shape=shape)
+            else:
+                block = np.empty(shape, np.float32)
+            self._ck(self.L.mgp_drift_lightcone(self.ctx, C.byref(ls), cap, _ptr(block), _ptr(cnt)))
+            return [block[r, :int(cnt[r])].copy() for r in range(ls.nrep)]
+        finally:
+            if host:
+                self.L.mgp_free_host(host)
 
     # ---- P(k) ----
     def set_pofk(self, nbins, bintype, subtract_shotnoise, kmin, kmax):

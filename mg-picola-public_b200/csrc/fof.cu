@@ -75,7 +75,7 @@ struct DeviceBackend {
   }
   template <class F> void run_warp(size_t n, F f) {
     if (!n) return;
-    k_fof_warp_step<F><<<grid_for(n * 32, 128, 64), 128, 0, c.stream>>>(n, f);
+    k_fof_warp_step<F><<<grid_for(n * 32, 32 * fof::FOF_WARPS_PER_CTA, 64), 32 * fof::FOF_WARPS_PER_CTA, 0, c.stream>>>(n, f);
     CK(cudaGetLastError());
     c.launches++;
   }

@@ -159,14 +159,15 @@ FOF_HD unsigned find_root_halving(Load &&load, Store &&store, unsigned i) {
     i = gp;
   }
 }
+// returns the root of the united group as far as this thread knows (an ancestor of both a and b from now on)
 template <class Load, class Store, class Cas>
-FOF_HD void unite(Load &&load, Store &&store, Cas &&cas, unsigned a, unsigned b) {
+FOF_HD unsigned unite(Load &&load, Store &&store, Cas &&cas, unsigned a, unsigned b) {
   for (;;) {
     a = find_root_halving(load, store, a);
     b = find_root_halving(load, store, b);
-    if (a == b) return;
+    if (a == b) return a;
     if (a < b) { const unsigned t = a; a = b; b = t; }
-    if (cas(a, a, b) == a) return;          // a was still a root: hooked.  Otherwise somebody else hooked it: again
+    if (cas(a, a, b) == a) return b;        // a was still a root: hooked.  Otherwise somebody else hooked it: again
   }
 }
 
@@ -202,58 +203,57 @@ FOF_HD void jacobi3(double a[9], double w[3], double v[9]) {
   for (int i = 0; i < 3; i++) w[i] = a[i * 3 + i];
 }
 
-// get_halos, mm_fof.c:468-611, for one halo of np members.  fetch(j, xx, vv) delivers position and velocity of the j-th
-// member in increasing index order (= the reference's order: sorted by x, the buffer particles last); it is called for
-// j = 0 .. np-1 twice.  On the device a whole warp runs this function for one halo, every lane the same arithmetic: the
-// fetcher has the lanes load 32 members at a time (fof_impl.cuh), the sums stay the sequential ones of the reference.
-template <class Fetch>
-FOF_HD void halo_properties(const Geometry &g, Fetch &&fetch, int np, double mass_particle, mgp_fof_halo &h) {
+// ---- get_halos, mm_fof.c:468-611, for one halo, in three pieces.  Every accumulator of the reference (centre-of-mass sums,
+// the 18 sums about the centre) is a sequential sum over the members in increasing index order (= the reference's order:
+// sorted by x, the buffer particles last); the ADDENDS of the second pass do not depend on one another.  The host runs
+// the pieces member by member (halo_properties below); on the device a warp owns a halo, the lanes form the addends of 32
+// members at a time and one lane per accumulator adds them up in order (fof_impl.cuh::PropsStep): the same additions in
+// the same order, so the same bits.
+
+// first pass, one position component: the running mean picks the periodic image (490-511), then the sum.
+// The reference's test is 2 |xx - xs / j| > L.  j |xx - xs / j| = |xx j - xs| to a few ulps, and a member is either near
+// the running mean or a box away from it: only within 2 % of the threshold is the division needed to decide as the
+// reference does.
+FOF_HD void com_add(double &xs, double xx, int j, double L) {
+  if (j > 0) {
+    const double dj = (double) j, Lj = FD_MUL(L, dj);
+    const double d = fabs(FD_SUB(FD_MUL(xx, dj), xs));
+    bool far = d > FD_MUL(0.51, Lj);
+    if (!far && !(d < FD_MUL(0.49, Lj))) far = FD_MUL(2.0, fabs(FD_SUB(xx, FD_DIV(xs, dj)))) > L;
+    if (far) {
+      if (FD_MUL(2.0, xx) > L) xx = FD_SUB(xx, L); else xx = FD_ADD(xx, L);
+    }
+  }
+  xs = FD_ADD(xs, xx);
+}
+
+enum { FOF_NACC = 18 };   // second pass: x_rms^2 [3], v_rms^2 [3], inertia tensor [9], angular momentum [3]
+
+// second pass: the 18 addends of one member (519-555)
+FOF_HD void member_terms(const float xf[3], const float vf[3], const float xavg[3], const float vavg[3], double L, double t[FOF_NACC]) {
+  double dx[3], dv[3];
+  for (int ax = 0; ax < 3; ax++) {
+    double xx = (double) xf[ax];
+    if (FD_MUL(2.0, fabs(FD_SUB(xx, (double) xavg[ax]))) > L) {
+      if (FD_MUL(2.0, xx) > L) xx = FD_SUB(xx, L); else xx = FD_ADD(xx, L);
+    }
+    dx[ax] = FD_SUB(xx, (double) xavg[ax]);
+    dv[ax] = FD_SUB((double) vf[ax], (double) vavg[ax]);
+  }
+  for (int ax = 0; ax < 3; ax++) { t[ax] = FD_MUL(dx[ax], dx[ax]); t[3 + ax] = FD_MUL(dv[ax], dv[ax]); }
+  for (int ax = 0; ax < 3; ax++)
+    for (int a2 = 0; a2 < 3; a2++) t[6 + a2 + 3 * ax] = FD_MUL(dx[ax], dx[a2]);
+  t[15] = FD_SUB(FD_MUL(dx[1], dv[2]), FD_MUL(dx[2], dv[1]));
+  t[16] = FD_SUB(FD_MUL(dx[2], dv[0]), FD_MUL(dx[0], dv[2]));
+  t[17] = FD_SUB(FD_MUL(dx[0], dv[1]), FD_MUL(dx[1], dv[0]));
+}
+
+// the record from the sums (556-611)
+FOF_HD void finish_halo(const Geometry &g, int np, double mass_particle, const float xavg[3], const float vavg[3],
+                        const double acc[FOF_NACC], mgp_fof_halo &h) {
   const double L = g.boxsize;
-  double xs[3] = {0, 0, 0}, vs[3] = {0, 0, 0};
-  for (int j = 0; j < np; j++) {                      // centre of mass; the running mean picks the periodic image (490-511)
-    float xf[3], vf[3];
-    fetch(j, xf, vf);
-    for (int ax = 0; ax < 3; ax++) {
-      double xx = (double) xf[ax];
-      const double vv = (double) vf[ax];
-      if (j > 0) {
-        // the reference's test is 2 |xx - xs / j| > L.  j |xx - xs / j| = |xx j - xs| to a few ulps, and a member is either
-        // near the running mean or a box away from it: only within 2 % of the threshold is the division needed to decide
-        // as the reference does
-        const double dj = (double) j, t2 = FD_MUL(2.0, fabs(FD_SUB(FD_MUL(xx, dj), xs[ax]))), Lj = FD_MUL(L, dj);
-        bool far = t2 > FD_MUL(1.02, Lj);
-        if (!far && !(t2 < FD_MUL(0.98, Lj))) far = FD_MUL(2.0, fabs(FD_SUB(xx, FD_DIV(xs[ax], dj)))) > L;
-        if (far) {
-          if (FD_MUL(2.0, xx) > L) xx = FD_SUB(xx, L); else xx = FD_ADD(xx, L);
-        }
-      }
-      xs[ax] = FD_ADD(xs[ax], xx);
-      vs[ax] = FD_ADD(vs[ax], vv);
-    }
-  }
-  float xavg[3], vavg[3];
-  for (int ax = 0; ax < 3; ax++) { xavg[ax] = (float) FD_DIV(xs[ax], (double) np); vavg[ax] = (float) FD_DIV(vs[ax], (double) np); }
-  double xr[3] = {0, 0, 0}, vr[3] = {0, 0, 0}, lam[3] = {0, 0, 0}, in[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  for (int j = 0; j < np; j++) {                      // quantities relative to the centre of mass (519-555)
-    float xf[3], vf[3];
-    fetch(j, xf, vf);
-    double dx[3], dv[3];
-    for (int ax = 0; ax < 3; ax++) {
-      double xx = (double) xf[ax];
-      if (FD_MUL(2.0, fabs(FD_SUB(xx, (double) xavg[ax]))) > L) {
-        if (FD_MUL(2.0, xx) > L) xx = FD_SUB(xx, L); else xx = FD_ADD(xx, L);
-      }
-      dx[ax] = FD_SUB(xx, (double) xavg[ax]);
-      dv[ax] = FD_SUB((double) vf[ax], (double) vavg[ax]);
-    }
-    for (int ax = 0; ax < 3; ax++) { xr[ax] = FD_ADD(xr[ax], FD_MUL(dx[ax], dx[ax])); vr[ax] = FD_ADD(vr[ax], FD_MUL(dv[ax], dv[ax])); }
-    for (int ax = 0; ax < 3; ax++)
-      for (int a2 = 0; a2 < 3; a2++) in[a2 + 3 * ax] = FD_ADD(in[a2 + 3 * ax], FD_MUL(dx[ax], dx[a2]));
-    lam[0] = FD_ADD(lam[0], FD_SUB(FD_MUL(dx[1], dv[2]), FD_MUL(dx[2], dv[1])));
-    lam[1] = FD_ADD(lam[1], FD_SUB(FD_MUL(dx[2], dv[0]), FD_MUL(dx[0], dv[2])));
-    lam[2] = FD_ADD(lam[2], FD_SUB(FD_MUL(dx[0], dv[1]), FD_MUL(dx[1], dv[0])));
-  }
-  double w[3], e[9];
+  double in[9], w[3], e[9];
+  for (int i = 0; i < 9; i++) in[i] = acc[6 + i];
   jacobi3(in, w, e);
   int o[3] = {0, 1, 2};                               // eigenvalues in descending order (compare_evals, 63-68)
   for (int i = 0; i < 2; i++)
@@ -270,9 +270,9 @@ FOF_HD void halo_properties(const Geometry &g, Fetch &&fetch, int np, double mas
     for (int k = 0; k < 3; k++) { h.ea[k] = (float) e[k * 3 + o[0]]; h.eb[k] = (float) e[k * 3 + o[1]]; h.ec[k] = (float) e[k * 3 + o[2]]; }
   }
   for (int ax = 0; ax < 3; ax++) {
-    h.x_rms[ax] = (float) FD_SQRT(FD_DIV(xr[ax], (double) np));
-    h.v_rms[ax] = (float) FD_SQRT(FD_DIV(vr[ax], (double) np));
-    h.lam[ax] = (float) lam[ax];
+    h.x_rms[ax] = (float) FD_SQRT(FD_DIV(acc[ax], (double) np));
+    h.v_rms[ax] = (float) FD_SQRT(FD_DIV(acc[3 + ax], (double) np));
+    h.lam[ax] = (float) acc[15 + ax];
     float xa = xavg[ax];                              // wrap the centre of mass (598-603)
     if (xa < 0) xa = (float) FD_ADD((double) xa, L);
     else if ((double) xa >= L) xa = (float) FD_SUB((double) xa, L);
@@ -280,6 +280,32 @@ FOF_HD void halo_properties(const Geometry &g, Fetch &&fetch, int np, double mas
     h.v_avg[ax] = vavg[ax];
   }
   h.x_avg[0] = FF_ADD(h.x_avg[0], g.edge);          // 604
+}
+
+// one halo, member by member: members ids[0 .. np) of the particle arrays x[3][stride], v[3][stride]
+FOF_HD void halo_properties(const Geometry &g, const float *x, const float *v, size_t stride, const unsigned *ids, int np,
+                            double mass_particle, mgp_fof_halo &h) {
+  const double L = g.boxsize;
+  double xs[3] = {0, 0, 0}, vs[3] = {0, 0, 0};
+  for (int j = 0; j < np; j++) {
+    const unsigned ip = ids[j];
+    for (int ax = 0; ax < 3; ax++) {
+      com_add(xs[ax], (double) x[ax * stride + ip], j, L);
+      vs[ax] = FD_ADD(vs[ax], (double) v[ax * stride + ip]);
+    }
+  }
+  float xavg[3], vavg[3];
+  for (int ax = 0; ax < 3; ax++) { xavg[ax] = (float) FD_DIV(xs[ax], (double) np); vavg[ax] = (float) FD_DIV(vs[ax], (double) np); }
+  double acc[FOF_NACC];
+  for (int a = 0; a < FOF_NACC; a++) acc[a] = 0.0;
+  for (int j = 0; j < np; j++) {
+    const unsigned ip = ids[j];
+    const float xf[3] = {x[ip], x[stride + ip], x[2 * stride + ip]}, vf[3] = {v[ip], v[stride + ip], v[2 * stride + ip]};
+    double t[FOF_NACC];
+    member_terms(xf, vf, xavg, vavg, L, t);
+    for (int a = 0; a < FOF_NACC; a++) acc[a] = FD_ADD(acc[a], t[a]);
+  }
+  finish_halo(g, np, mass_particle, xavg, vavg, acc, h);
 }
 
 }  // namespace fof

@@ -129,12 +129,12 @@ struct LinkStep {         // every pair of friends, each once: the rest of the o
     auto store = [par](unsigned i, unsigned v) { Atom::store(par + i, v); };
     auto cas = [par](unsigned at, unsigned expect, unsigned desired) { return Atom::cas(par + at, expect, desired); };
     const float4 me = packed[s];
-    const unsigned fme = word(me.w);
+    unsigned anc = word(me.w);      // the last known ancestor of this particle: later unions start their walk there
     const int cx = cell_coord(me.x, g.icx, g.ncx), cy = cell_coord(me.y, g.icy, g.ncy), cz = cell_coord(me.z, g.icz, g.ncz);
     const unsigned own = ((unsigned) cx * (unsigned) g.ncy + (unsigned) cy) * (unsigned) g.ncz + (unsigned) cz;
     for (unsigned t = (unsigned) s + 1u, t1 = start[own + 1]; t < t1; t++) {
       const float4 o = packed[t];
-      if (linked(g, me.x, me.y, me.z, o.x, o.y, o.z)) unite(load, store, cas, fme, word(o.w));
+      if (linked(g, me.x, me.y, me.z, o.x, o.y, o.z)) anc = unite(load, store, cas, anc, word(o.w));
     }
     for (int k = 14; k < 27; k++) {                                   // (ox, oy, oz) after (0, 0, 0) in lexicographic order
       const int ox = k / 9 - 1, oy = (k / 3) % 3 - 1, oz = k % 3 - 1;
@@ -144,7 +144,7 @@ struct LinkStep {         // every pair of friends, each once: the rest of the o
       const unsigned c2 = ((unsigned) x2 * (unsigned) g.ncy + (unsigned) y2) * (unsigned) g.ncz + (unsigned) z2;
       for (unsigned t = start[c2], t1 = start[c2 + 1]; t < t1; t++) {
         const float4 o = packed[t];
-        if (linked(g, me.x, me.y, me.z, o.x, o.y, o.z)) unite(load, store, cas, fme, word(o.w));
+        if (linked(g, me.x, me.y, me.z, o.x, o.y, o.z)) anc = unite(load, store, cas, anc, word(o.w));
       }
     }
   }
@@ -206,37 +206,67 @@ struct SegmentStep {      // where a halo's members start in the list sorted by 
   }
 };
 
-// member j of a halo for halo_properties.  Device: the 32 lanes of the warp that owns the halo each load one member of
-// the current chunk of 32 (the loads of a chunk are in flight together instead of one dependent pair per member) and
-// hand it round by shuffles; every lane must call with the same j.  Host: a plain lookup.
-struct MemberFetch {
-  const float *x, *v; size_t N; const unsigned *ids; int np;
-  float cx[3], cv[3];
-  FOF_HD void operator()(int j, float xf[3], float vf[3]) {
-#if defined(__CUDA_ARCH__)
-    if ((j & 31) == 0) {
-      const int m = j + (int) (threadIdx.x & 31u);
-      if (m < np) {
-        const unsigned ip = ids[m];
-        for (int a = 0; a < 3; a++) { cx[a] = x[a * N + ip]; cv[a] = v[a * N + ip]; }
-      }
-    }
-    for (int a = 0; a < 3; a++) { xf[a] = __shfl_sync(0xffffffffu, cx[a], j & 31); vf[a] = __shfl_sync(0xffffffffu, cv[a], j & 31); }
-#else
-    const unsigned ip = ids[j];
-    for (int a = 0; a < 3; a++) { xf[a] = x[a * N + ip]; vf[a] = v[a * N + ip]; }
-#endif
-  }
-};
+// Halo properties.  Host: one call per halo, member by member.  Device: one WARP per halo (k_fof_warp_step with
+// FOF_WARPS_PER_CTA warps per CTA), 32 members at a time: every lane gathers one member (the loads of a chunk are in flight
+// together), forms its addends and stages them in shared memory; then one lane per accumulator adds the chunk's addends in
+// member order.  What is sequential in the reference -- the chain of additions per accumulator, and in the first pass
+// the image choice against the running mean -- stays sequential (18 and 6 chains side by side); everything else runs
+// across the lanes.
+enum { FOF_WARPS_PER_CTA = 4, FOF_STAGE = FOF_NACC + 1 };
 
-struct PropsStep {        // one warp (device) / one call (host) per halo
+struct PropsStep {
   Geometry g; const float *x, *v; size_t N; const unsigned *members, *seg, *cnt; double mass_particle; mgp_fof_halo *out;
   FOF_HD void operator()(size_t h) const {
+    const unsigned *ids = members + seg[h];
+    const int np = (int) cnt[h];
     mgp_fof_halo r;
-    MemberFetch f{x, v, N, members + seg[h], (int) cnt[h], {0, 0, 0}, {0, 0, 0}};
-    halo_properties(g, f, (int) cnt[h], mass_particle, r);
 #if defined(__CUDA_ARCH__)
-    if ((threadIdx.x & 31u) != 0) return;
+    __shared__ double stage_all[FOF_WARPS_PER_CTA][32 * FOF_STAGE];
+    double *stage = stage_all[threadIdx.x >> 5];
+    const int lane = (int) (threadIdx.x & 31u);
+    const double L = g.boxsize;
+    const unsigned full = 0xffffffffu;
+    // first pass: lanes 0-2 own the position sums, lanes 3-5 the velocity sums
+    double sum = 0.0;
+    for (int base = 0; base < np; base += 32) {
+      const int m = base + lane, n = min(32, np - base);
+      if (m < np) {
+        const unsigned ip = ids[m];
+        for (int a = 0; a < 3; a++) { stage[lane * FOF_STAGE + a] = (double) x[a * N + ip]; stage[lane * FOF_STAGE + 3 + a] = (double) v[a * N + ip]; }
+      }
+      __syncwarp(full);
+      if (lane < 3) {
+        for (int j = 0; j < n; j++) com_add(sum, stage[j * FOF_STAGE + lane], base + j, L);
+      } else if (lane < 6) {
+        for (int j = 0; j < n; j++) sum = FD_ADD(sum, stage[j * FOF_STAGE + lane]);
+      }
+      __syncwarp(full);
+    }
+    const float avg = (float) FD_DIV(sum, (double) np);
+    float xavg[3], vavg[3];
+    for (int a = 0; a < 3; a++) { xavg[a] = __shfl_sync(full, avg, a); vavg[a] = __shfl_sync(full, avg, 3 + a); }
+    // second pass: lane a < 18 owns accumulator a
+    double acc1 = 0.0;
+    for (int base = 0; base < np; base += 32) {
+      const int m = base + lane, n = min(32, np - base);
+      if (m < np) {
+        const unsigned ip = ids[m];
+        const float xf[3] = {x[ip], x[N + ip], x[2 * N + ip]}, vf[3] = {v[ip], v[N + ip], v[2 * N + ip]};
+        double t[FOF_NACC];
+        member_terms(xf, vf, xavg, vavg, L, t);
+        for (int a = 0; a < FOF_NACC; a++) stage[lane * FOF_STAGE + a] = t[a];
+      }
+      __syncwarp(full);
+      if (lane < FOF_NACC)
+        for (int j = 0; j < n; j++) acc1 = FD_ADD(acc1, stage[j * FOF_STAGE + lane]);
+      __syncwarp(full);
+    }
+    double acc[FOF_NACC];
+    for (int a = 0; a < FOF_NACC; a++) acc[a] = __shfl_sync(full, acc1, a);
+    if (lane != 0) return;
+    finish_halo(g, np, mass_particle, xavg, vavg, acc, r);
+#else
+    halo_properties(g, x, v, N, ids, np, mass_particle, r);
 #endif
     out[h] = r;
   }

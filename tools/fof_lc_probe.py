@@ -47,6 +47,10 @@ def clustered(n1d, box, seed, frac=0.3):
     return pos, vel, sizes
 
 
+def nrep_of(case):
+    return int(np.asarray(case["reps"]).reshape(-1, 3).shape[0])
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n1d", type=int, default=256)
@@ -101,14 +105,28 @@ def main():
                 cnt = pm.lightcone_count(s, case["reps"], i["sumxyz"])
                 tc.append(time.perf_counter() - t0)
             total = int(cnt.sum())
+            before = pm.download_particles(("pos",))["pos"]
             t0 = time.perf_counter()
-            rows = pm.Drift_Lightcone(s, case["reps"], i["sumxyz"], cap=int(cnt.max()))
+            rows = pm.Drift_Lightcone(s, case["reps"], i["sumxyz"], cap=int(cnt.max()), pinned=True)
             t_drift = time.perf_counter() - t0
             assert sum(r.shape[0] for r in rows) == total
+            del rows
+            pm.upload_particles(before, i["vel"][k], i["D"][k], i["D2"][k])     # the same step again, library call alone
+            ls, keep = pm._lightcone_step(s, case["reps"], i["sumxyz"])
+            cap = int(cnt.max())
+            host = pm.L.mgp_alloc_host(24 * cap * nrep_of(case))
+            c2 = np.zeros(nrep_of(case), np.uint64)
+            t0 = time.perf_counter()
+            pm._ck(pm.L.mgp_drift_lightcone(pm.ctx, mgp.C.byref(ls), cap, host, c2.ctypes.data))
+            t_call = time.perf_counter() - t0
+            pm.L.mgp_free_host(host)
+            assert int(c2.sum()) == total
             nrep = int(np.asarray(case["reps"]).reshape(-1, 3).shape[0])
             out["lightcone"] = dict(n1d=M, particles=m, replicates=nrep, rows=total, count_ms=[round(1e3 * t, 3) for t in tc],
                                     count_pairs_per_s=m * nrep / min(tc), count_gbs=56.0 * m / min(tc) / 1e9,
-                                    drift_ms_with_count_pass_and_d2h=round(1e3 * t_drift, 3), row_bytes=24 * total)
+                                    drift_ms_python_binding=round(1e3 * t_drift, 3),
+                                    drift_ms_library_call_pinned_block=round(1e3 * t_call, 3), row_bytes=24 * total,
+                                    rows_gbs=24.0 * total / t_call / 1e9)
             print(json.dumps(out["lightcone"]), flush=True)
             pm.close()
     print(json.dumps(out))

@@ -68,6 +68,10 @@ PY
       timeout 50 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/${TAG}_fof_lc_launches.csv \
         python tools/fof_lc_probe.py --n1d 256 --lc-n1d 128 --reps 1 > gpurun_out/${TAG}_fof_lc_launches.log 2>&1
       tail -2 gpurun_out/${TAG}_fof_lc_launches.log ;;
+    fof_ncu)           # ncu --set full of the halo finder's and the lightcone's own kernels
+      timeout 90 ncu --set full --clock-control none --import-source on -k "regex:LinkStep|PropsStep|k_lightcone" -c 7 -f -o gpurun_out/${TAG}_fof_lc \
+        python tools/fof_lc_probe.py --reps 1 > gpurun_out/${TAG}_fof_ncu.log 2>&1
+      tail -2 gpurun_out/${TAG}_fof_ncu.log ;;
     smi)
       nvidia-smi --query-gpu=index,name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv | tee gpurun_out/${TAG}_smi.txt
       nvidia-smi topo -m | head -12 | tee -a gpurun_out/${TAG}_smi.txt; nproc | tee -a gpurun_out/${TAG}_smi.txt; free -g | head -2 | tee -a gpurun_out/${TAG}_smi.txt ;;
