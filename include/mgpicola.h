@@ -337,8 +337,9 @@ int mgp_get_step_power_spectrum_total(mgp_ctx *ctx, double *pofk, double *kmean,
 int mgp_compute_rsd_power_spectrum(mgp_ctx *ctx, double vnorm, double dDdy, double dD2dy, double *out_y, double *out_z);
 
 /* ---- grid access (tests, write_grid_to_file auxPM.c:757-813) ---- */
-/* SimplePofk/main.cpp (the reference's stand-alone P(k) estimator) on the particles the context holds: assignment of raw
- * counts with scheme 1 = NGP, 2 = CIC, 3 = TSC (main.cpp:59-228; x = double(pos_float / boxsize) * ngrid), one transform,
+/* SimplePofk/main.cpp (the reference's stand-alone P(k) estimator) on the particles the context holds: assignment of
+ * counts with scheme 1 = NGP, 2 = CIC, 3 = TSC (main.cpp:59-228; x = double(pos_float / boxsize) * ngrid), normalised to the
+ * density contrast as main() does (513-533: a factor (Nmesh^3 / Npart)^2 on every bin, k = 0 is not binned), one transform,
  * |d_k|^2 / N^6 / window^2 with window = prod sinc(pi k_a / N)^scheme (324-340, 393), bins int(|k| + 0.5), 0 < bin < Nmesh
  * (391), mean per bin, optional shot noise 1 / Npart (420-424).  pofk, nmodes: Nmesh doubles each; the tool prints
  * k = (2 i + 1) pi / Box and pofk[i] Box^3 for 1 <= i <= Nmesh / 2.  tsc_as_published = 1 reproduces the tool's TSC as

@@ -1,6 +1,8 @@
 // The reference's stand-alone P(k) estimator (SimplePofk/main.cpp) on the particles a context holds: NGP / CIC / TSC
-// assignment of raw counts (main.cpp:59-228), one r2c, per-mode window deconvolution and the tool's integer binning
-// (324-424).  Post-processing, not part of a COLA step: simple atomic deposits, one rank only (TSC reaches the plane on
+// assignment of counts (main.cpp:59-228), one r2c, per-mode window deconvolution and the tool's integer binning
+// (324-424).  main() turns the counts into the density contrast before the transform (513-533: divide by the mean count
+// Npart / N^3, subtract 1); the bins exclude k = 0, so here the counts are transformed and the factor (N^3 / Npart)^2
+// goes into the normalisation of |d_k|^2.  Post-processing, not part of a COLA step: simple atomic deposits, one rank only (TSC reaches the plane on
 // the left, for which a slab keeps no ghost).
 #include "common.cuh"
 #include "klayout.cuh"
@@ -57,7 +59,7 @@ k_assign_scheme(size_t n, const float4 *__restrict__ pA, T *__restrict__ grid, i
   }
 }
 
-// per-bin sums of |d_k|^2 / N^6 / window^2 and of the mode count over the FULL complex cube (the tool transforms complex
+// per-bin sums of |d_k|^2 * norm / window^2 (norm = 1 / N^6 of main.cpp:380 times (N^3 / Npart)^2) and of the mode count over the FULL complex cube (the tool transforms complex
 // data): a mode of the half spectrum with 0 < kz < N/2 stands for itself and its conjugate
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -133,7 +135,7 @@ static void simple_pofk_t(Ctx &c, int scheme, int slip, double *pofk_sum, double
   const size_t sm = (size_t) 2 * N * sizeof(double);
   CK(cudaFuncSetAttribute(k_simple_pofk<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
   k_simple_pofk<T><<<grid_for(L.total, 256, 4), 256, sm, c.stream>>>(L, (const typename Cpx<T>::type *) c.grid[gid], d_sinc, scheme,
-                                                                     (1.0 / n3) * (1.0 / n3), d_out);
+                                                                     (1.0 / n3) * (1.0 / n3) * (n3 / (double) c.np) * (n3 / (double) c.np), d_out);
   c.launches++;
   std::vector<double> h((size_t) 2 * N);
   CK(cudaMemcpyAsync(h.data(), d_out, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
@@ -144,13 +146,12 @@ static void simple_pofk_t(Ctx &c, int scheme, int slip, double *pofk_sum, double
 
 void simple_pofk(Ctx &c, int scheme, int subtract_shotnoise, int slip, double *pofk, double *nmodes) {
   REQUIRE(scheme >= 1 && scheme <= 3, MGP_ERR_INVALID, "mgp_simple_pofk: scheme must be 1 (NGP), 2 (CIC) or 3 (TSC)");
+  REQUIRE(c.np > 0, MGP_ERR_STATE, "mgp_simple_pofk: no particles");
   REQUIRE(c.P == 1 && !c.slab, MGP_ERR_INVALID, "mgp_simple_pofk: one rank only (post-processing; TSC needs the plane on the left)");
   REQUIRE((size_t) 2 * c.N * sizeof(double) <= 200 * 1024, MGP_ERR_INVALID, "mgp_simple_pofk: Nmesh too large for the bin table");
   if (c.cfg.scale_dependent) sd_evict_block(c, 0);            // the work grid is force grid X
   c.forces_live = false;
   if (c.gbytes == 4) simple_pofk_t<float>(c, scheme, slip, pofk, nmodes); else simple_pofk_t<double>(c, scheme, slip, pofk, nmodes);
-  const double tot = (double) c.cfg.nsample * (double) c.cfg.nsample * (double) c.cfg.nsample;
-  (void) tot;
   for (int b = 0; b < c.N; b++) {
     if (nmodes[b] > 0) pofk[b] /= nmodes[b];                  // main.cpp:412-416
     if (subtract_shotnoise) pofk[b] -= 1.0 / (double) c.np;   // main.cpp:420-424: 1 / npart_tot

@@ -617,14 +617,16 @@ def rsd_velocity(vel, D, D2, axis, use_cola, dDdy, dD2dy, scale_dependent=False)
 def simple_pofk(pos, ngrid, box, scheme="CIC", subtract_shotnoise=False):
     """SimplePofk/main.cpp restated (the reference's stand-alone P(k) estimator; the only user of NGP and TSC):
     positions as GADGET floats, x = double(pos_float / boxsize) (main.cpp:259-261); assignment add_to_grid_NGP / _CIC /
-    _TSC (59-228) of raw counts (no mean subtraction, no normalisation); complex 3-D transform; per mode
-    |d_k|^2 / N^6 / window^2 with window = prod_a sinc(pi k_a / N) to the power 1 / 2 / 3 (324-340, 393); bin
-    int(|k| + 0.5) for 0 < bin < N (391); mean per bin, optional shot noise 1 / Npart (420-424).
+    _TSC (59-228) of counts; main()'s normalisation to the density contrast (513-533: grid /= N^3 / Npart, the mean
+    of that, grid = grid / mean - 1); complex 3-D transform; per mode |d_k|^2 / N^6 / window^2 with window =
+    prod_a sinc(pi k_a / N) to the power 1 / 2 / 3 (324-340, 393); bin int(|k| + 0.5) for 0 < bin < N (391); mean per
+    bin, optional shot noise 1 / Npart (420-424).
     TSC reproduces the tool as written, including its three `izneighN` where the weight PZ belongs to `izneighP`
     (main.cpp:189, 201, 213: the "010", "110", "210" lines).  Returns (pofk[N], nmodes[N]); the tool prints
     k = (2 i + 1) pi / boxsize and pofk[i] * boxsize^3 for 1 <= i <= N / 2 (436-444).
-    PARITY UNPINNED against a compiled SimplePofk: the tool needs FFTW's complex 3-D plan and OpenMP, which the image does
-    not have; this restatement is what the CUDA path is checked against."""
+    PINNED to the tool itself: oracle/_ref/simplepofk_{NGP,CIC,TSC} = SimplePofk/main.cpp compiled unmodified (g++ -fopenmp,
+    the FFT stand-in's complex plan) run on a GADGET file of these positions (tests/test_simple_pofk.py), to the six digits
+    the tool prints."""
     N = int(ngrid)
     p = np.asarray(pos, dtype=np.float32)
     x = (p.astype(np.float64) / np.float64(box))
@@ -666,6 +668,8 @@ def simple_pofk(pos, ngrid, box, scheme="CIC", subtract_shotnoise=False):
         power = 3
     else:
         raise ValueError(scheme)
+    grid /= float(N) ** 3 / float(len(p))           # main.cpp:515-521 (sic: divided, the mean below undoes it)
+    grid = grid / grid.mean() - 1.0                 # 523-528
     dk = np.fft.fftn(grid)
     k1 = np.arange(N)
     kk = np.where(k1 < N // 2, k1, k1 - N)
@@ -697,8 +701,9 @@ def readic_delta_k(pos01_files, nmesh, nsample, normfac, rescale_by_k2, grid_dty
     that starts at -1, the ghost plane folded onto plane 0 (630-637), r2c, density *= normfac (642-646), sharp-k filter
     above Nsample/2 when Nmesh > Nsample (648-680), and cdelta_cdm = P3D * grid_corr * rescale_fac with the CIC window
     grid_corr = prod_a (sin(pi d_a / N) / (pi d_a / N))^-2 (724-750).  Returns delta_k [N][N][N/2+1]; mode 0 is 0.
-    PARITY UNPINNED against a compiled -DREADICFROMFILE build (it needs particle files of an external code); checked
-    piecewise: the deposit is PtoMesh's (pinned), the transform is pinned, the rest is pointwise."""
+    PINNED to the unmodified reference built with -DREADICFROMFILE -DSCALEDEPENDENT (oracle/_ref/libmgpicola_ref_fofr_ric.so)
+    reading GADGET files written by the test: its cdelta_cdm to 1e-12, with Nmesh = and > Nsample and both settings of
+    input_sigma8_is_for_lcdm (tests/test_readic_oracle.py)."""
     N = int(nmesh)
     W = (float(nmesh) / float(nsample)) ** 3
     dens = np.full((N + 1, N, N), -1.0)

@@ -30,6 +30,8 @@ VARIANT_FLAGS = {
     "fofrnu": dict(scaledependent=True, single=False),
     "lcdm_lc": dict(scaledependent=False, single=False),     # -DLIGHTCONE -DUNFORMATTED, no GADGET_STYLE
     "lcdm_mm": dict(scaledependent=False, single=False),     # -DMATCHMAKER_HALOFINDER
+    "fofr_ric": dict(scaledependent=True, single=False),     # -DREADICFROMFILE (+ SCALEDEPENDENT: delta(k) is kept)
+    "lcdm_ric": dict(scaledependent=False, single=False),    # -DREADICFROMFILE
 }
 
 

@@ -11,6 +11,10 @@
 
 #include <stddef.h>
 
+#ifdef __cplusplus
+extern "C" {
+#endif
+
 typedef double fftw_complex[2];
 typedef float  fftwf_complex[2];
 
@@ -25,5 +29,18 @@ void fftw_execute(const fftw_plan p);
 void fftw_destroy_plan(fftw_plan p);
 void fftwf_execute(const fftwf_plan p);
 void fftwf_destroy_plan(fftwf_plan p);
+
+/* complex 3-D plan, in place (SimplePofk/main.cpp:295-300 is the only user), and the calls around it */
+#define FFTW_FORWARD  (-1)
+#define FFTW_BACKWARD (+1)
+fftw_plan fftw_plan_dft_3d(int n0, int n1, int n2, fftw_complex *in, fftw_complex *out, int sign, unsigned flags);
+void *fftw_malloc(size_t n);
+void fftw_free(void *p);
+int fftw_init_threads(void);
+void fftw_plan_with_nthreads(int nthreads);
+
+#ifdef __cplusplus
+}
+#endif
 
 #endif

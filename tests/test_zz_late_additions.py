@@ -1,0 +1,25 @@
+"""GPU checks written after this round's GPU minutes were spent: first run = the driver's round-end `-m gpu` pass.  They sit
+in the last file of the suite so that a surprise here cannot hide the result of anything that has run green on B200."""
+import numpy as np
+import pytest
+
+from oracle import pm_oracle as po
+from test_gpu_parity import OMEGA, make_particles
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scheme", ["NGP", "CIC", "TSC"])
+def test_simple_pofk_with_npart_different_from_ngrid3(mgp, require_gpu, scheme):
+    """SimplePofk normalises the counts to the density contrast (main.cpp:513-533), so P(k) carries (Ngrid^3 / Npart)^2;
+    the restatement is pinned to the compiled tool for Npart != Ngrid^3 in tests/test_simple_pofk.py."""
+    N, box = 32, 100.0
+    pos, vel, D, D2 = make_particles(N, box, 13, clustered=True)
+    keep = N ** 3 - 9000
+    pm = mgp.PM(N, N, box, omega=OMEGA, grid_bytes=8, sort_particles=0)
+    pm.upload_particles(pos[:keep], vel[:keep], D[:keep], D2[:keep])
+    p, n = pm.simple_pofk(scheme, subtract_shotnoise=True)
+    pr, nr = po.simple_pofk(pos[:keep], N, box, scheme, subtract_shotnoise=True)
+    assert np.array_equal(n, nr)
+    good = nr > 0
+    assert np.abs(p[good] - pr[good]).max() < 1e-10 * np.abs(pr[good]).max()
+    pm.close()
