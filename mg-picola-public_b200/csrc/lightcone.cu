@@ -15,18 +15,16 @@ namespace mgp {
 // Slots of the leaving images: the lanes of a warp vote per replicate, one lane adds the warp's number to the replicate's
 // counter and the lanes take consecutive slots behind the value it got back.  (One atomic per image on a few dozen
 // addresses serialises in L2: 20 ns each, measured -- profiles/r02r_fof_lc.md.)  The counting pass adds into a per-CTA copy
-// of the counters in shared memory first (SMEM_COUNT; nrep * 8 bytes of dynamic shared memory).
+// of the counters in shared memory first (SMEM_COUNT; nrep * 4 bytes of dynamic shared memory: 32-bit counters, a native ATOMS.ADD).
 template <bool WRITE, bool SMEM_COUNT>
 __global__ void __launch_bounds__(256)
 k_lightcone(size_t n, float4 *__restrict__ pA, const float4 *__restrict__ pB, const float4 *__restrict__ pC,
             const float2 *__restrict__ pE, lc::Params p, unsigned long long *__restrict__ count,
             const unsigned long long *__restrict__ offset, float *__restrict__ rows, int *__restrict__ over_flag) {
-  extern __shared__ unsigned long long s_count[];
-  unsigned long long *cnt = count;
-  if (SMEM_COUNT) {
-    for (int r = threadIdx.x; r < p.nrep; r += blockDim.x) s_count[r] = 0ull;
+  extern __shared__ unsigned int s_count[];            // 32-bit: a native shared-memory atomic (a 64-bit add is a CAS loop there);
+  if (SMEM_COUNT) {                                    // a CTA never sees 2^32 particles
+    for (int r = threadIdx.x; r < p.nrep; r += blockDim.x) s_count[r] = 0u;
     __syncthreads();
-    cnt = s_count;
   }
   const unsigned lane = threadIdx.x & 31u;
   bool over = false;
@@ -46,8 +44,12 @@ k_lightcone(size_t n, float4 *__restrict__ pA, const float4 *__restrict__ pB, co
       if (m == 0u) return 0ull;
       const int leader = __ffs(m) - 1;
       unsigned long long base = 0ull;
-      if ((int) lane == leader) base = atomicAdd(&cnt[r], (unsigned long long) __popc(m));
-      if (!WRITE) return 0ull;                             // the counting pass needs no slot
+      if (SMEM_COUNT) {                                    // counting pass: no slot needed
+        if ((int) lane == leader) atomicAdd(&s_count[r], (unsigned) __popc(m));
+        return 0ull;
+      }
+      if ((int) lane == leader) base = atomicAdd(&count[r], (unsigned long long) __popc(m));
+      if (!WRITE) return 0ull;
       base = __shfl_sync(0xffffffffu, base, leader);
       return base + (unsigned long long) __popc(m & ((1u << lane) - 1u));
     });
@@ -60,7 +62,7 @@ k_lightcone(size_t n, float4 *__restrict__ pA, const float4 *__restrict__ pB, co
   if (SMEM_COUNT) {
     __syncthreads();
     for (int r = threadIdx.x; r < p.nrep; r += blockDim.x)
-      if (s_count[r]) atomicAdd(&count[r], s_count[r]);
+      if (s_count[r]) atomicAdd(&count[r], (unsigned long long) s_count[r]);
   }
 }
 
@@ -129,8 +131,8 @@ void count_pass(Ctx &c, const lc::Params &p, LcDevice &dv, std::vector<unsigned 
   CK(cudaMemsetAsync(dv.count, 0, (size_t) 2 * nr * sizeof(unsigned long long), c.stream));
   CK(cudaMemsetAsync(c.d_flag, 0, sizeof(int), c.stream));
   if (c.np) {
-    if (p.nrep <= 4096)       // 32 KB of counters per CTA at most
-      k_lightcone<false, true><<<grid_for(c.np, 256), 256, (size_t) nr * sizeof(unsigned long long), c.stream>>>(
+    if (p.nrep <= 8192)       // 32 KB of counters per CTA at most
+      k_lightcone<false, true><<<grid_for(c.np, 256), 256, (size_t) nr * sizeof(unsigned int), c.stream>>>(
           c.np, c.pA, c.pB, c.pC, (const float2 *) c.pE, p, dv.count, dv.offset, nullptr, c.d_flag);
     else
       k_lightcone<false, false><<<grid_for(c.np, 256), 256, 0, c.stream>>>(c.np, c.pA, c.pB, c.pC, (const float2 *) c.pE, p,
