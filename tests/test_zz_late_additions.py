@@ -1,5 +1,6 @@
-"""GPU checks written after this round's GPU minutes were spent: first run = the driver's round-end `-m gpu` pass.  They sit
-in the last file of the suite so that a surprise here cannot hide the result of anything that has run green on B200."""
+"""GPU checks written when this round's GPU minutes were all but spent: the same comparisons ran green on B200 in
+tools/quick_check.py (profiles/r02v_quick_check.log), but as pytest items their first run is the driver's round-end
+`-m gpu` pass.  They sit in the last file of the suite so that a surprise here cannot hide anything that has run green."""
 import numpy as np
 import pytest
 
