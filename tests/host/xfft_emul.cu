@@ -174,6 +174,8 @@ int main() {
   // row against the 128-byte lines of the owner's buffer)
   CASE_LIB(double2, 9, 8, 8, 257, td);
   CASE_LIB(double2, 10, 8, 8, 513, td);
+  // the strong-scaling run of the bench at 512^3 on 4 ranks (2 and 8 ranks have run on the GPUs)
+  CASE_LIB(double2, 9, 4, 4, 257, td);
   // the wide-tile instances (xfft_wide.cu)
   bad += run_case<double2, 8, tile_lines_wide(8, 16)>(2, 2, 129, 256, td);
   bad += run_case<double2, 9, tile_lines_wide(9, 16)>(8, 8, 17, 256, td);
