@@ -177,6 +177,21 @@ void initialize_parts(void) {
 
 /* ------------------------------------------------------------------ initial conditions (2LPT.c:185-1520) */
 
+/* non-SCALEDEPENDENT builds: main.c:257-309 builds P from ZA / LPT on the host */
+static void fetch_za_lpt(void) {
+#ifndef SCALEDEPENDENT
+  float *za = my_malloc((size_t) NumPart * 3 * sizeof(float)), *lpt = my_malloc((size_t) NumPart * 3 * sizeof(float));
+  ck(mgp_ic_download(g_ctx, za, lpt), "mgp_ic_download");
+  for (int a = 0; a < 3; a++) {
+    ZA[a] = my_malloc(NumPart * sizeof(float));
+    LPT[a] = my_malloc(NumPart * sizeof(float));
+    for (unsigned int q = 0; q < NumPart; q++) { ZA[a][q] = za[3 * (size_t) q + a]; LPT[a][q] = lpt[3 * (size_t) q + a]; }
+  }
+  my_free(za); my_free(lpt);
+#endif
+  g_host_is_newer = 1;
+}
+
 void displacement_fields(void) {
   timer_start(_DisplacementFields);
   const int h = Nmesh / 2;
@@ -201,20 +216,70 @@ void displacement_fields(void) {
   ic.power_by_k2 = power; ic.n_power = nm; ic.seedtable = NULL;
   ck(mgp_ic_generate(g_ctx, &ic), "mgp_ic_generate");
   my_free(power);
-#ifndef SCALEDEPENDENT
-  /* main.c:257-309 builds P from ZA / LPT on the host */
-  float *za = my_malloc((size_t) NumPart * 3 * sizeof(float)), *lpt = my_malloc((size_t) NumPart * 3 * sizeof(float));
-  ck(mgp_ic_download(g_ctx, za, lpt), "mgp_ic_download");
-  for (int a = 0; a < 3; a++) {
-    ZA[a] = my_malloc(NumPart * sizeof(float));
-    LPT[a] = my_malloc(NumPart * sizeof(float));
-    for (unsigned int q = 0; q < NumPart; q++) { ZA[a][q] = za[3 * (size_t) q + a]; LPT[a][q] = lpt[3 * (size_t) q + a]; }
-  }
-  my_free(za); my_free(lpt);
-#endif
-  g_host_is_newer = 1;
+  fetch_za_lpt();
   timer_stop(_DisplacementFields);
 }
+
+#ifdef READICFROMFILE
+/* ------------------------------------------------------------------ initial conditions from particle files
+ * ReadFilesMakeDisplacementField (readICfromfile.c:533-699) with the reference's own file readers (readICfromfile.c is
+ * compiled unmodified, its ReadFilesMakeDisplacementField renamed out of the way by the Makefile): every file's particles
+ * go to mgp_ic_particles_add in place of ProcessParticlesSingleFile, the transform, the normalisation, the sharp-k filter,
+ * AssignDisplacementField and the 2LPT pipeline run in mgp_ic_particles_finish.  GADGET files arrive as the floats the
+ * reference deposits; RAMSES / ASCII positions are doubles there and are rounded to float here. */
+void ReadFilesMakeDisplacementField(void) {
+  timer_start(_ReadParticlesFromFile);
+  int maxpart = 0;
+  if (TypeInputParticleFiles == RAMSESFILE) maxpart = find_maxpart_ramsesfiles(InputParticleFileDir, RamsesOutputNumber, NumInputParticleFiles);
+  else if (TypeInputParticleFiles == ASCIIFILE) maxpart = find_maxpart_asciifiles(InputParticleFileDir, InputParticleFilePrefix, NumInputParticleFiles);
+  else if (TypeInputParticleFiles == GADGETFILE) maxpart = find_maxpart_gadgetfiles(InputParticleFileDir, InputParticleFilePrefix, NumInputParticleFiles);
+  else {
+    printf("Error: unknown file-format [%i]\n", TypeInputParticleFiles);
+    MPI_Abort(MPI_COMM_WORLD, 1);
+    exit(1);
+  }
+  char *buffer = my_malloc(3 * sizeof(double) * (size_t) (maxpart > 0 ? maxpart : 1));
+  float *as_float = NULL;
+  if (TypeInputParticleFiles != GADGETFILE) as_float = my_malloc(3 * sizeof(float) * (size_t) (maxpart > 0 ? maxpart : 1));
+  ck(mgp_ic_particles_begin(g_ctx), "mgp_ic_particles_begin");
+  int npart_read = 0;
+  uint64_t taken = 0;
+  for (int filenum = 1; filenum <= NumInputParticleFiles; filenum++) {
+    int n = 0;
+    if (TypeInputParticleFiles == RAMSESFILE) n = read_ramses_file(InputParticleFileDir, RamsesOutputNumber, filenum, buffer, &npart_read);
+    else if (TypeInputParticleFiles == ASCIIFILE) n = read_ascii_file(InputParticleFileDir, InputParticleFilePrefix, filenum, buffer, &npart_read);
+    else n = read_gadget_file(InputParticleFileDir, InputParticleFilePrefix, filenum - 1, buffer, &npart_read);
+    if (ThisTask == 0) printf("Read so far: %i  Part in current file %i\n", npart_read, n);
+    const float *pos01 = (const float *) buffer;                       /* GADGET: [x1 y1 z1 x2 ...] floats in [0, 1) */
+    if (as_float) {                                                     /* RAMSES, ASCII: [x1 .. xn y1 .. yn z1 .. zn] doubles */
+      const double *d = (const double *) buffer;
+      for (int i = 0; i < n; i++)
+        for (int a = 0; a < 3; a++) as_float[3 * (size_t) i + a] = (float) d[i + (size_t) a * n];
+      pos01 = as_float;
+    }
+    ck(mgp_ic_particles_add(g_ctx, pos01, (uint64_t) n, &taken), "mgp_ic_particles_add");
+  }
+  my_free(buffer);
+  if (as_float) my_free(as_float);
+  /* readICfromfile.c:641-643 and 735-741 */
+  const double normfac = 1.0 / pow((double) Nmesh, 3) * (growth_DLCDM(1.0) / growth_DLCDM(1.0 / (1.0 + Init_Redshift)));
+  const int h = Nmesh / 2;
+  const size_t nm = (size_t) 3 * h * h + 1;
+  double *rescale = my_malloc(sizeof(double) * nm);
+  const double s8 = mg_sigma8_enhancement(1.0);
+  rescale[0] = 1.0;
+  for (size_t m = 1; m < nm; m++) {
+    const double kmag = sqrt((double) m * (2 * PI / Box) * (2 * PI / Box));
+    rescale[m] = sqrt(mg_pofk_ratio(kmag, 1.0));
+    if (!input_sigma8_is_for_lcdm) rescale[m] /= s8;
+  }
+  if (ThisTask == 0) printf("Done precomputing delta(k) from particles, now compute displacement-fields\n\n");
+  ck(mgp_ic_particles_finish(g_ctx, normfac, rescale, nm), "mgp_ic_particles_finish");
+  my_free(rescale);
+  fetch_za_lpt();
+  timer_stop(_ReadParticlesFromFile);
+}
+#endif
 
 /* ------------------------------------------------------------------ host <-> device particle copies */
 

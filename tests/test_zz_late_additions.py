@@ -24,3 +24,77 @@ def test_simple_pofk_with_npart_different_from_ngrid3(mgp, require_gpu, scheme):
     good = nr > 0
     assert np.abs(p[good] - pr[good]).max() < 1e-10 * np.abs(pr[good]).max()
     pm.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant,model", [("lcdm_ric", "lcdm"), ("fofr_ric", "fofr")])
+def test_readic_driver_matches_cpu_reference(require_gpu, tmp_path, variant, model):
+    """-DREADICFROMFILE builds: the reference's driver reading GADGET particle files, with ReadFilesMakeDisplacementField
+    served by mgp_ic_particles_begin / _add / _finish (adapter/auxPM_cuda.c; the file readers stay readICfromfile.c's),
+    against the unmodified reference on the same files and parameter file: every in-step P(k) file and the final snapshot.
+    (The restatement of this path is pinned to the reference on the CPU in tests/test_readic_oracle.py, the library entry
+    points to the restatement in tests/test_readic.py; this is the whole run through the reference's own main().)"""
+    import os
+    import subprocess
+    from test_dropin_driver import _exe, read_gadget, read_pofk
+    N, box, nsteps = 32, 100.0, 5
+    runs = {}
+    for kind in ("cpu", "gpu"):
+        wd = str(tmp_path / kind)
+        pf = readic_case(wd, N, box, variant, model, nsteps)
+        r = subprocess.run([_exe(kind, variant), pf], capture_output=True, text=True, cwd=wd, timeout=900,
+                           env=dict(os.environ, MGP_SD_MERGED="0"))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        runs[kind] = os.path.join(wd, "output")
+    shot = (box / N) ** 3
+    pk_c = sorted(f for f in os.listdir(runs["cpu"]) if f.startswith("pofk_") and f.endswith("_CDM.txt"))
+    pk_g = sorted(f for f in os.listdir(runs["gpu"]) if f.startswith("pofk_") and f.endswith("_CDM.txt"))
+    assert pk_c == pk_g and len(pk_c) >= nsteps
+    for f in pk_c:
+        a, b = read_pofk(os.path.join(runs["cpu"], f)), read_pofk(os.path.join(runs["gpu"], f))
+        assert a.shape == b.shape and np.array_equal(a[:, 0], b[:, 0])
+        assert np.all(np.abs(a[:, 1] - b[:, 1]) <= 2e-5 + 1e-6 * (np.abs(a[:, 1]) + shot)), f
+    snap = [f for f in os.listdir(runs["cpu"]) if f.startswith("bench_z0p000")]
+    pc, vc, ic = read_gadget(os.path.join(runs["cpu"], snap[0]))
+    pg, vg, ig = read_gadget(os.path.join(runs["gpu"], snap[0]))
+    oc, og = np.argsort(ic), np.argsort(ig)
+    assert np.array_equal(ic[oc], ig[og]) and np.array_equal(ic[oc], np.arange(N ** 3, dtype=np.uint64))
+    dp = np.abs(pc[oc].astype(np.float64) - pg[og])
+    dp = np.minimum(dp, box - dp)
+    assert dp.max() < 3e-5 * box / N
+    assert np.abs(vc[oc] - vg[og]).max() < 3e-4 * np.abs(vc).max()
+
+
+def readic_case(wd, N, box, variant, model, nsteps):
+    """Two GADGET files of a perturbed lattice and the parameter file of a READICFROMFILE run in `wd`."""
+    import os
+    import bench
+    import test_readic_oracle as tro
+    os.makedirs(wd, exist_ok=True)
+    pbox = (tro._glass(N, 3) * box).astype(np.float32)
+    half = len(pbox) // 3
+    for i, f in enumerate((pbox[:half], pbox[half:])):
+        tro._write_gadget(os.path.join(wd, "part.%d" % i), f, box)
+    tags = ("ReadParticlesFromFile 1\nNumInputParticleFiles 2\nInputParticleFileDir %s\nInputParticleFilePrefix part\n"
+            "RamsesOutputNumber 1\nTypeInputParticleFiles 3\n" % wd)
+    pf = bench.write_paramfile(wd, N, box, model, nsteps, lcdm_growth=0 if variant == "fofr_ric" else 1, extra=tags)
+    txt = open(pf).read().replace("WhichSpectrum 1", "WhichSpectrum 2")            # see tests/test_readic_oracle.py
+    with open(pf, "w") as f:
+        f.write(txt)
+    return pf
+
+
+def test_readic_reference_drivers_run(tmp_path):
+    """CPU half of the driver test above: the unmodified reference reads the files and runs to z = 0 (both builds)."""
+    import os
+    import subprocess
+    from oracle import ref_lib
+    for variant, model in (("lcdm_ric", "lcdm"), ("fofr_ric", "fofr")):
+        if not os.path.exists(ref_lib.exe_path(variant)):
+            pytest.skip("oracle/_ref READICFROMFILE build missing")
+        wd = str(tmp_path / variant)
+        pf = readic_case(wd, 16, 100.0, variant, model, 3)
+        r = subprocess.run([ref_lib.exe_path(variant), pf], capture_output=True, text=True, cwd=wd, timeout=600)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        out = os.path.join(wd, "output")
+        assert len([f for f in os.listdir(out) if f.startswith("pofk_")]) >= 3 and any(f.startswith("bench_z0p000") for f in os.listdir(out))
