@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "klayout.cuh"
 #include "reduce.cuh"
+#include "ic_modes.cuh"
 
 #include <cmath>
 
@@ -155,56 +156,19 @@ k_ic_delta(KL L, const unsigned *__restrict__ seedtable, const double *__restric
 
 // ------------------------------------------------------------------ k-space kernels of the 2LPT pipeline
 
-// wave vector with the IC code's Nyquist convention: idx < N/2 ? idx : idx - N  (2LPT.c:1229-1245)
-__device__ __forceinline__ void ic_kvec(const KL &L, int i, int j, int k, double box, double kv[3]) {
-  const int N = L.N, h = N / 2;
-  const double PI = 3.14159265358979323846;
-  kv[0] = (i < h ? i : i - N) * 2 * PI / box;
-  kv[1] = (j < h ? j : j - N) * 2 * PI / box;
-  kv[2] = (k < h ? k : k - N) * 2 * PI / box;
-}
-
-// MODE 0: psi_a          = (-kv_a/k^2 * d.im,  kv_a/k^2 * d.re)                        (2LPT.c:417-421)
-// MODE 1: psi_a,a        = (-psi_a.im * kv_a,  psi_a.re * kv_a), a = 0,1,2              (2LPT.c:1252-1268)
-// MODE 2: psi_0,1 psi_0,2 psi_1,2
-// MODE 3: psi2_a         = ( s.im * kv_a / k^2, -s.re * kv_a / k^2)                      (2LPT.c:1348-1355)
-// MODE 4: scale-dependent fields: (-d.im * kv_a/k^2 * G[m], d.re * kv_a/k^2 * G[m])      (2LPT.c:1618-1626)
+// the arithmetic per mode is in ic_modes.cuh (shared with the host emulation); `ext`: delta_k comes from external particles
+// (READICFROMFILE), whose Nyquist planes carry power and follow AssignDisplacementField's wave-vector convention
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256)
 k_ic_kernel(KL L, const typename Cpx<T>::type *__restrict__ src, typename Cpx<T>::type *__restrict__ o0,
             typename Cpx<T>::type *__restrict__ o1, typename Cpx<T>::type *__restrict__ o2, double box,
-            const double *__restrict__ gtab, double norm) {
+            const double *__restrict__ gtab, double norm, int ext) {
   typedef typename Cpx<T>::type C;
   KLOOP(e, L) {
     int i, j, k;
     kl_decode(L, e, i, j, k);
-    double kv[3];
-    ic_kvec(L, i, j, k, box, kv);
-    const double kmag2 = kv[0] * kv[0] + kv[1] * kv[1] + kv[2] * kv[2];
-    const C s = src[e];
     C out[3];
-    if (!(kmag2 > 0.0)) {
-      out[0].x = out[0].y = out[1].x = out[1].y = out[2].x = out[2].y = (T) 0;
-    } else if (MODE == 0) {
-#pragma unroll
-      for (int a = 0; a < 3; a++) { out[a].x = (T) (-kv[a] / kmag2 * (double) s.y); out[a].y = (T) (kv[a] / kmag2 * (double) s.x); }
-    } else if (MODE == 1 || MODE == 2) {
-      T pre[3], pim[3];
-#pragma unroll
-      for (int a = 0; a < 3; a++) { pre[a] = (T) (-kv[a] / kmag2 * (double) s.y); pim[a] = (T) (kv[a] / kmag2 * (double) s.x); }
-      const int A[3] = {0, MODE == 1 ? 1 : 0, MODE == 1 ? 2 : 1}, B[3] = {MODE == 1 ? 0 : 1, MODE == 1 ? 1 : 2, 2};
-#pragma unroll
-      for (int q = 0; q < 3; q++) { out[q].x = (T) (-(double) pim[A[q]] * kv[B[q]]); out[q].y = (T) ((double) pre[A[q]] * kv[B[q]]); }
-    } else if (MODE == 3) {
-#pragma unroll
-      for (int a = 0; a < 3; a++) { out[a].x = (T) ((double) s.y * kv[a] / kmag2); out[a].y = (T) (-(double) s.x * kv[a] / kmag2); }
-    } else {
-      const int N = L.N;
-      const int d0 = i < N / 2 ? i : i - N, d1 = j < N / 2 ? j : j - N, d2 = k < N / 2 ? k : k - N;
-      const double g = norm * gtab[(long long) d0 * d0 + (long long) d1 * d1 + (long long) d2 * d2];
-#pragma unroll
-      for (int a = 0; a < 3; a++) { out[a].x = (T) (-(double) s.y * kv[a] / kmag2 * g); out[a].y = (T) ((double) s.x * kv[a] / kmag2 * g); }
-    }
+    ic_mode<T, C, MODE>(L.N, i, j, k, box, src[e], gtab, norm, ext, out);
     o0[e] = out[0]; o1[e] = out[1]; o2[e] = out[2];
   }
 }
@@ -399,6 +363,7 @@ static void ic_generate_t(Ctx &c, const mgp_ic_config *ic, const double *ext_res
   REQUIRE(nloc <= c.cap, MGP_ERR_BUFFER, "mgp_ic_generate: particle capacity too small");
   const size_t mmax = (size_t) 3 * (N / 2) * (N / 2) + 1;
   const double *table = ext_rescale ? ext_rescale : ic->power_by_k2;
+  const int ext = ext_rescale ? 1 : 0;     // AssignDisplacementField's wave-vector convention on the Nyquist planes (ic_modes.cuh)
   REQUIRE(table != nullptr && (ext_rescale || ic->n_power >= mmax), MGP_ERR_INVALID,
           "mgp_ic_generate: power_by_k2 must hold 3 (Nmesh/2)^2 + 1 entries");
 
@@ -433,8 +398,8 @@ static void ic_generate_t(Ctx &c, const mgp_ic_config *ic, const double *ext_res
   c.launches++;
   // second-order source from the six gradients
   for (int pass = 0; pass < 2; pass++) {
-    if (pass == 0) k_ic_kernel<T, 1><<<gk, 256, 0, c.stream>>>(L, dk, f[0], f[1], f[2], c.cfg.box, nullptr, 1.0);
-    else k_ic_kernel<T, 2><<<gk, 256, 0, c.stream>>>(L, dk, f[0], f[1], f[2], c.cfg.box, nullptr, 1.0);
+    if (pass == 0) k_ic_kernel<T, 1><<<gk, 256, 0, c.stream>>>(L, dk, f[0], f[1], f[2], c.cfg.box, nullptr, 1.0, ext);
+    else k_ic_kernel<T, 2><<<gk, 256, 0, c.stream>>>(L, dk, f[0], f[1], f[2], c.cfg.box, nullptr, 1.0, ext);
     fft_c2r_forces(c);
     k_ic_source<T><<<gr, 256, 0, c.stream>>>(S, fr[0], fr[1], fr[2], c.grid_vals, pass);
     c.launches += 2;
@@ -462,8 +427,8 @@ static void ic_generate_t(Ctx &c, const mgp_ic_config *ic, const double *ext_res
     double means[6];
     const double n3 = (double) N * (double) N * (double) N;
     for (int order = 1; order <= 2; order++) {
-      if (order == 1) k_ic_kernel<T, 0><<<gk, 256, 0, c.stream>>>(L, dk, f[0], f[1], f[2], c.cfg.box, nullptr, 1.0);
-      else k_ic_kernel<T, 3><<<gk, 256, 0, c.stream>>>(L, (const C *) c.grid[0], f[0], f[1], f[2], c.cfg.box, nullptr, 1.0);
+      if (order == 1) k_ic_kernel<T, 0><<<gk, 256, 0, c.stream>>>(L, dk, f[0], f[1], f[2], c.cfg.box, nullptr, 1.0, ext);
+      else k_ic_kernel<T, 3><<<gk, 256, 0, c.stream>>>(L, (const C *) c.grid[0], f[0], f[1], f[2], c.cfg.box, nullptr, 1.0, 0);
       fft_c2r_forces(c);
       halo_fill_forces(c);
       double *res = c.d_red + (size_t) gp * 3;

@@ -92,3 +92,90 @@ def test_readic_restatement_matches_reference(tmp_path, N, ns, sigma8_lcdm):
     assert np.abs(got - ref).max() < 1e-12 * np.abs(ref).max()
     if N > ns:
         assert np.count_nonzero(ref) < ref.size // 2                      # the sharp-k filter removed the modes beyond ns / 2
+
+
+# ---- the displacements behind delta(k): the library's own k-space arithmetic run on the CPU against the reference's ZA / LPT
+
+def _build_ic_emulation(tmpdir):
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        return None
+    so = os.path.join(tmpdir, "libic_emul.so")
+    subprocess.run([nvcc, "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC,-ffp-contract=off", "-gencode", "arch=compute_100a,code=sm_100a",
+                    "-I", os.path.join(ROOT, "mg-picola-public_b200", "csrc"), "-o", so, os.path.join(ROOT, "tests", "host", "ic_emul.cu")],
+                   check=True)
+    return C.CDLL(so)
+
+
+def reference_readic_displacements(wd, N, box):
+    """ZA [n][3], LPT [n][3] of the unmodified reference (non-SCALEDEPENDENT -DREADICFROMFILE build) after
+    ReadFilesMakeDisplacementField on the GADGET files of tests/test_zz_late_additions.py::readic_case, with the particles
+    in [0, 1) and the normalisation the adapter hands to the library.  None without the build."""
+    if not ref_lib.available("lcdm_ric"):
+        return None
+    import test_zz_late_additions as tz
+    pf = tz.readic_case(wd, N, box, "lcdm_ric", "lcdm", 3)
+    R = ref_lib.RefLib("lcdm_ric")
+    L = R.lib
+    with ref_lib._silenced(True):
+        R.init_from_paramfile(pf)
+        L.ReadFilesMakeDisplacementField()
+    n = N ** 3
+    out = []
+    for name in ("ZA", "LPT"):
+        p = (C.c_void_p * 3).in_dll(L, name)
+        out.append(np.stack([np.ctypeslib.as_array(C.cast(p[a], C.POINTER(C.c_float)), shape=(n,)).copy() for a in range(3)], 1))
+    pbox = (_glass(N, 3) * box).astype(np.float32)
+    half = len(pbox) // 3
+    files01 = []
+    for f in (pbox[:half], pbox[half:]):
+        u = (f.astype(np.float64) * (np.float64(1.0) / np.float64(box))).astype(np.float32)
+        files01.append(np.where(u >= np.float32(1.0), (u.astype(np.float64) - 1.0).astype(np.float32), u))
+    L.growth_DLCDM.restype = C.c_double
+    L.growth_DLCDM.argtypes = [C.c_double]
+    zi = R.get("Init_Redshift", C.c_double)
+    normfac = 1.0 / float(N) ** 3 * (L.growth_DLCDM(1.0) / L.growth_DLCDM(1.0 / (1.0 + zi)))
+    return dict(ZA=out[0], LPT=out[1], files01=files01, normfac=normfac)
+
+
+def test_library_kspace_arithmetic_gives_the_reference_displacements(tmp_path):
+    """ic_generate_t's sequence for external particles (csrc/ic.cu) with the kernels' arithmetic (csrc/ic_modes.cuh, run on the
+    CPU) and numpy transforms: delta_k -> six gradients -> second-order source -> ZA and 2LPT displacements at the Lagrangian
+    points, against the ZA / LPT arrays of the unmodified reference.  Nmesh = Nsample, so the Nyquist planes carry power and
+    AssignDisplacementField's wave-vector convention there (+N/2 in psi, -N/2 in the gradients) decides the result: with the
+    convention of the generated initial conditions everywhere the 2LPT field is off by several times its rms."""
+    N, box = 16, 100.0
+    ref = reference_readic_displacements(str(tmp_path), N, box)
+    if ref is None:
+        pytest.skip("oracle/_ref READICFROMFILE build missing")
+    lib = _build_ic_emulation(str(tmp_path))
+    if lib is None:
+        pytest.skip("nvcc not available")
+    NZ = N // 2 + 1
+    lib.ic_mode_f64.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_double] + [C.c_void_p] * 3
+    dk = np.ascontiguousarray(po.readic_delta_k(ref["files01"], N, N, ref["normfac"], np.ones(3 * (N // 2) ** 2 + 1)), np.complex128)
+
+    def mode(m, src, ext):
+        o = [np.zeros((N, N, NZ), np.complex128) for _ in range(3)]
+        assert lib.ic_mode_f64(m, N, box, ext, src.ctypes.data, None, 1.0, *[x.ctypes.data for x in o]) == 0
+        return o
+
+    def c2r(F):                                                         # FFTW's c2r: complex over x and y, then z (unnormalised)
+        t = np.fft.ifft(np.fft.ifft(F, axis=0), axis=1) * N * N
+        return np.fft.irfft(t, n=N, axis=2) * N
+
+    def displacements(ext):
+        g = [c2r(x) for x in mode(1, dk, ext)] + [c2r(x) for x in mode(2, dk, ext)]      # 00 11 22, 01 02 12
+        S = g[0] * (g[1] + g[2]) + g[1] * g[2] - g[3] ** 2 - g[4] ** 2 - g[5] ** 2
+        Sk = np.ascontiguousarray(np.fft.rfftn(S), np.complex128)
+        za = np.stack([c2r(x).reshape(-1) for x in mode(0, dk, ext)], 1)
+        lpt = np.stack([c2r(x).reshape(-1) for x in mode(3, Sk, 0)], 1) * ((-3.0 / 7.0) / float(N) ** 3)
+        return za - za.mean(0), lpt - lpt.mean(0)
+
+    za, lpt = displacements(1)
+    assert np.abs(za - ref["ZA"]).max() < 2e-6 * np.abs(ref["ZA"]).max()
+    assert np.abs(lpt - ref["LPT"]).max() < 2e-6 * np.abs(ref["LPT"]).max()
+    za0, lpt0 = displacements(0)                                        # the convention of the generated ICs is NOT the reference's here
+    assert np.abs(lpt0 - ref["LPT"]).max() > 0.5 * ref["LPT"].std()

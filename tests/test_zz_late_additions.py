@@ -98,3 +98,23 @@ def test_readic_reference_drivers_run(tmp_path):
         assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
         out = os.path.join(wd, "output")
         assert len([f for f in os.listdir(out) if f.startswith("pofk_")]) >= 3 and any(f.startswith("bench_z0p000") for f in os.listdir(out))
+
+
+@pytest.mark.gpu
+def test_readic_displacements_match_reference(mgp, require_gpu, tmp_path):
+    """mgp_ic_particles_* followed by mgp_ic_download against the ZA / LPT arrays of the UNMODIFIED reference
+    (-DREADICFROMFILE build, ReadFilesMakeDisplacementField on the same GADGET files), Nmesh = Nsample so that the Nyquist
+    planes carry power.  The kernels' k-space arithmetic gives these arrays on the CPU
+    (tests/test_readic_oracle.py::test_library_kspace_arithmetic_gives_the_reference_displacements)."""
+    import test_readic_oracle as tro
+    N, box = 16, 100.0
+    ref = tro.reference_readic_displacements(str(tmp_path), N, box)
+    if ref is None:
+        pytest.skip("oracle/_ref READICFROMFILE build missing")
+    pm = mgp.PM(N, N, box, grid_bytes=8)
+    taken = pm.ic_from_particles(ref["files01"], ref["normfac"], np.ones(3 * (N // 2) ** 2 + 1))
+    assert taken == N ** 3
+    za, lpt = pm.ic_download()
+    pm.close()
+    assert np.abs(za - ref["ZA"]).max() < 2e-6 * np.abs(ref["ZA"]).max()
+    assert np.abs(lpt - ref["LPT"]).max() < 2e-6 * np.abs(ref["LPT"]).max()
