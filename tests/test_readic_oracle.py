@@ -92,6 +92,35 @@ def test_readic_restatement_matches_reference(tmp_path, N, ns, sigma8_lcdm):
     assert np.abs(got - ref).max() < 1e-12 * np.abs(ref).max()
     if N > ns:
         assert np.count_nonzero(ref) < ref.size // 2                      # the sharp-k filter removed the modes beyond ns / 2
+    else:
+        _check_second_order_density(R, N, box, str(tmp_path))
+
+
+def _check_second_order_density(R, N, box, tmpdir):
+    """The stored second-order scalar cdelta_cdm2 = -S_k (2LPT.c:1336-1344) of the SCALEDEPENDENT -DREADICFROMFILE build from
+    the reference's own cdelta_cdm through the kernels' gradient arithmetic (csrc/ic_modes.cuh on the CPU), to rounding --
+    with AssignDisplacementField's convention on the Nyquist planes; with the other convention it is off by its own size."""
+    lib = _build_ic_emulation(tmpdir)
+    if lib is None:
+        return
+    NZ = N // 2 + 1
+    d1, d2 = np.ascontiguousarray(R.sd_delta(1), np.complex128), R.sd_delta(2)
+    lib.ic_mode_f64.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_double] + [C.c_void_p] * 3
+
+    def second_order(ext):
+        g = []
+        for m in (1, 2):
+            o = [np.zeros((N, N, NZ), np.complex128) for _ in range(3)]
+            assert lib.ic_mode_f64(m, N, box, ext, d1.ctypes.data, None, 1.0, *[x.ctypes.data for x in o]) == 0
+            for F in o:
+                t = np.fft.ifft(np.fft.ifft(F, axis=0), axis=1) * N * N
+                g.append(np.fft.irfft(t, n=N, axis=2) * N)
+        S = g[0] * (g[1] + g[2]) + g[1] * g[2] - g[3] ** 2 - g[4] ** 2 - g[5] ** 2
+        Sk = -np.fft.rfftn(S)
+        Sk[0, 0, 0] = 0.0
+        return Sk
+    assert np.abs(second_order(1) - d2).max() < 1e-12 * np.abs(d2).max()
+    assert np.abs(second_order(0) - d2).max() > 0.1 * np.abs(d2).max()
 
 
 # ---- the displacements behind delta(k): the library's own k-space arithmetic run on the CPU against the reference's ZA / LPT
@@ -179,39 +208,3 @@ def test_library_kspace_arithmetic_gives_the_reference_displacements(tmp_path):
     assert np.abs(lpt - ref["LPT"]).max() < 2e-6 * np.abs(ref["LPT"]).max()
     za0, lpt0 = displacements(0)                                        # the convention of the generated ICs is NOT the reference's here
     assert np.abs(lpt0 - ref["LPT"]).max() > 0.5 * ref["LPT"].std()
-
-
-def test_library_kspace_arithmetic_gives_the_reference_second_order_density(tmp_path):
-    """SCALEDEPENDENT -DREADICFROMFILE build: the stored second-order scalar cdelta_cdm2 = -S_k (2LPT.c:1336-1344) from the
-    reference's own cdelta_cdm through the kernels' gradient arithmetic, to rounding -- with AssignDisplacementField's
-    convention on the Nyquist planes; with the other convention it is off by its own size."""
-    if not ref_lib.available("fofr_ric"):
-        pytest.skip("oracle/_ref READICFROMFILE build missing")
-    lib = _build_ic_emulation(str(tmp_path))
-    if lib is None:
-        pytest.skip("nvcc not available")
-    import test_zz_late_additions as tz
-    N, box = 16, 100.0
-    NZ = N // 2 + 1
-    pf = tz.readic_case(str(tmp_path / "run"), N, box, "fofr_ric", "fofr", 3)
-    R = ref_lib.RefLib("fofr_ric")
-    with ref_lib._silenced(True):
-        R.init_from_paramfile(pf)
-        R.lib.ReadFilesMakeDisplacementField()
-    d1, d2 = np.ascontiguousarray(R.sd_delta(1), np.complex128), R.sd_delta(2)
-    lib.ic_mode_f64.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_double] + [C.c_void_p] * 3
-
-    def second_order(ext):
-        g = []
-        for m in (1, 2):
-            o = [np.zeros((N, N, NZ), np.complex128) for _ in range(3)]
-            assert lib.ic_mode_f64(m, N, box, ext, d1.ctypes.data, None, 1.0, *[x.ctypes.data for x in o]) == 0
-            for F in o:
-                t = np.fft.ifft(np.fft.ifft(F, axis=0), axis=1) * N * N
-                g.append(np.fft.irfft(t, n=N, axis=2) * N)
-        S = g[0] * (g[1] + g[2]) + g[1] * g[2] - g[3] ** 2 - g[4] ** 2 - g[5] ** 2
-        Sk = -np.fft.rfftn(S)
-        Sk[0, 0, 0] = 0.0
-        return Sk
-    assert np.abs(second_order(1) - d2).max() < 1e-12 * np.abs(d2).max()
-    assert np.abs(second_order(0) - d2).max() > 0.1 * np.abs(d2).max()

@@ -85,11 +85,12 @@ def readic_case(wd, N, box, variant, model, nsteps):
 
 
 def test_readic_reference_drivers_run(tmp_path):
-    """CPU half of the driver test above: the unmodified reference reads the files and runs to z = 0 (both builds)."""
+    """CPU half of the driver test above: the unmodified reference reads the files and runs to z = 0 (the SCALEDEPENDENT
+    build's run through the library interface is tests/test_readic_oracle.py)."""
     import os
     import subprocess
     from oracle import ref_lib
-    for variant, model in (("lcdm_ric", "lcdm"), ("fofr_ric", "fofr")):
+    for variant, model in (("lcdm_ric", "lcdm"),):
         if not os.path.exists(ref_lib.exe_path(variant)):
             pytest.skip("oracle/_ref READICFROMFILE build missing")
         wd = str(tmp_path / variant)
