@@ -36,7 +36,7 @@ def test_readic_driver_matches_cpu_reference(require_gpu, tmp_path, variant, mod
     points to the restatement in tests/test_readic.py; this is the whole run through the reference's own main().)"""
     import os
     import subprocess
-    from test_dropin_driver import _exe, read_gadget, read_pofk
+    from test_dropin_driver import _exe
     N, box, nsteps = 32, 100.0, 5
     runs = {}
     for kind in ("cpu", "gpu"):
@@ -46,23 +46,52 @@ def test_readic_driver_matches_cpu_reference(require_gpu, tmp_path, variant, mod
                            env=dict(os.environ, MGP_SD_MERGED="0"))
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         runs[kind] = os.path.join(wd, "output")
+    _same_runs(runs["cpu"], runs["gpu"], N, box, nsteps)
+
+
+def _same_runs(out_c, out_g, N, box, nsteps, pk_rel=1e-6, tolx=3e-5, tolv=3e-4):
+    """Every in-step P(k) file (print resolution + pk_rel) and the final GADGET snapshot (IDs exact, positions in cells)."""
+    import os
+    from test_dropin_driver import read_gadget, read_pofk
     shot = (box / N) ** 3
-    pk_c = sorted(f for f in os.listdir(runs["cpu"]) if f.startswith("pofk_") and f.endswith("_CDM.txt"))
-    pk_g = sorted(f for f in os.listdir(runs["gpu"]) if f.startswith("pofk_") and f.endswith("_CDM.txt"))
+    pk_c = sorted(f for f in os.listdir(out_c) if f.startswith("pofk_") and f.endswith("_CDM.txt"))
+    pk_g = sorted(f for f in os.listdir(out_g) if f.startswith("pofk_") and f.endswith("_CDM.txt"))
     assert pk_c == pk_g and len(pk_c) >= nsteps
     for f in pk_c:
-        a, b = read_pofk(os.path.join(runs["cpu"], f)), read_pofk(os.path.join(runs["gpu"], f))
+        a, b = read_pofk(os.path.join(out_c, f)), read_pofk(os.path.join(out_g, f))
         assert a.shape == b.shape and np.array_equal(a[:, 0], b[:, 0])
-        assert np.all(np.abs(a[:, 1] - b[:, 1]) <= 2e-5 + 1e-6 * (np.abs(a[:, 1]) + shot)), f
-    snap = [f for f in os.listdir(runs["cpu"]) if f.startswith("bench_z0p000")]
-    pc, vc, ic = read_gadget(os.path.join(runs["cpu"], snap[0]))
-    pg, vg, ig = read_gadget(os.path.join(runs["gpu"], snap[0]))
+        assert np.all(np.abs(a[:, 1] - b[:, 1]) <= 2e-5 + pk_rel * (np.abs(a[:, 1]) + shot)), f
+    snap = [f for f in os.listdir(out_c) if f.startswith("bench_z0p000")]
+    pc, vc, ic = read_gadget(os.path.join(out_c, snap[0]))
+    pg, vg, ig = read_gadget(os.path.join(out_g, snap[0]))
     oc, og = np.argsort(ic), np.argsort(ig)
     assert np.array_equal(ic[oc], ig[og]) and np.array_equal(ic[oc], np.arange(N ** 3, dtype=np.uint64))
     dp = np.abs(pc[oc].astype(np.float64) - pg[og])
     dp = np.minimum(dp, box - dp)
-    assert dp.max() < 3e-5 * box / N
-    assert np.abs(vc[oc] - vg[og]).max() < 3e-4 * np.abs(vc).max()
+    assert dp.max() < tolx * box / N
+    assert np.abs(vc[oc] - vg[og]).max() < tolv * np.abs(vc).max()
+
+
+@pytest.mark.gpu
+def test_driver_without_cola_matches_cpu_reference(require_gpu, tmp_path):
+    """UseCOLA 0: the reference as a plain particle-mesh code (StdDA = 2, logarithmic steps, 2LPT velocities in the initial
+    conditions: main.c:75-85, 284) -- Kick / Drift / snapshot with the UseCOLA factor at zero, every other test runs COLA."""
+    import os
+    import subprocess
+    import bench
+    from test_dropin_driver import _exe
+    N, box, nsteps = 32, 100.0, 6
+    runs = {}
+    for kind in ("cpu", "gpu"):
+        wd = str(tmp_path / kind)
+        pf = bench.write_paramfile(wd, N, box, "fofr", nsteps)
+        txt = open(pf).read().replace("UseCOLA 1", "UseCOLA 0")
+        with open(pf, "w") as f:
+            f.write(txt)
+        r = subprocess.run([_exe(kind, "lcdm"), pf], capture_output=True, text=True, cwd=wd, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        runs[kind] = os.path.join(wd, "output")
+    _same_runs(runs["cpu"], runs["gpu"], N, box, nsteps, pk_rel=1e-8)
 
 
 def readic_case(wd, N, box, variant, model, nsteps):
