@@ -32,6 +32,7 @@ VARIANT_FLAGS = {
     "lcdm_mm": dict(scaledependent=False, single=False),     # -DMATCHMAKER_HALOFINDER
     "fofr_ric": dict(scaledependent=True, single=False),     # -DREADICFROMFILE (+ SCALEDEPENDENT: delta(k) is kept)
     "lcdm_ric": dict(scaledependent=False, single=False),    # -DREADICFROMFILE
+    "jbd": dict(scaledependent=False, single=False),         # -DBRANSDICKE
 }
 
 
