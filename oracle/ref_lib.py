@@ -33,6 +33,7 @@ VARIANT_FLAGS = {
     "fofr_ric": dict(scaledependent=True, single=False),     # -DREADICFROMFILE (+ SCALEDEPENDENT: delta(k) is kept)
     "lcdm_ric": dict(scaledependent=False, single=False),    # -DREADICFROMFILE
     "jbd": dict(scaledependent=False, single=False),         # -DBRANSDICKE
+    "mbeta": dict(scaledependent=True, single=False),        # -DMBETAMODEL -DSCALEDEPENDENT (the symmetron)
 }
 
 

@@ -150,37 +150,49 @@ def test_readic_displacements_match_reference(mgp, require_gpu, tmp_path):
     assert np.abs(lpt - ref["LPT"]).max() < 2e-6 * np.abs(ref["LPT"]).max()
 
 
-def jbd_case(wd, N, box, nsteps):
-    """Parameter file of a Brans-Dicke run (-DBRANSDICKE: user_defined_functions.h:383-399 reads wBD and the physical densities
-    under the tags Omegah2, Omegar2, Omegav2; the Hubble parameter follows from G_eff = 1 today, jbd.c)."""
+MODEL_TAGS = {
+    # -DBRANSDICKE: user_defined_functions.h:383-399 reads wBD and the physical densities under the tags Omegah2, Omegar2,
+    # Omegav2; the Hubble parameter follows from G_eff = 1 today (jbd.c)
+    "jbd": "modified_gravity_active 1\nwBD 50.0\nOmegah2 0.1346\nOmegar2 4.2e-5\nOmegav2 0.3695\ninclude_screening 1\n",
+    # -DMBETAMODEL: the symmetron of paramfiles/example_mbeta.txt (user_defined_functions.h:359-371)
+    "mbeta": "modified_gravity_active 1\nassb_symm 0.5\nbeta_symm 1.0\nrange_symm 1.0\ninclude_screening 1\n",
+}
+
+
+def model_case(wd, variant, N, box, nsteps):
+    """Parameter file of a run of one of the two remaining models of the reference Makefile (85-98)."""
     import bench
-    pf = bench.write_paramfile(wd, N, box, "lcdm", nsteps)
+    pf = bench.write_paramfile(wd, N, box, "lcdm", nsteps, lcdm_growth=0 if variant == "mbeta" else 1)
     txt = open(pf).read()
     for line in ("modified_gravity_active 0\n", "fofr0 %g\nnfofr %g\n" % (bench.FOFR0, bench.NFOFR), "include_screening 0\n"):
         txt = txt.replace(line, "")
-    txt = "modified_gravity_active 1\nwBD 50.0\nOmegah2 0.1346\nOmegar2 4.2e-5\nOmegav2 0.3695\ninclude_screening 1\n" + txt
     with open(pf, "w") as f:
-        f.write(txt)
+        f.write(MODEL_TAGS[variant] + txt)
     return pf
 
 
-def test_brans_dicke_reference_driver_runs(tmp_path):
+@pytest.mark.parametrize("variant,marker", [("jbd", "Multiplying with Geff(a)"), ("mbeta", "Phi_critical")])
+def test_other_models_reference_drivers_run(tmp_path, variant, marker):
     """CPU half of the test below."""
     import os
     import subprocess
     from oracle import ref_lib
-    if not os.path.exists(ref_lib.exe_path("jbd")):
-        pytest.skip("oracle/_ref Brans-Dicke build missing")
+    if not os.path.exists(ref_lib.exe_path(variant)):
+        pytest.skip("oracle/_ref build of this model missing")
     wd = str(tmp_path)
-    r = subprocess.run([ref_lib.exe_path("jbd"), jbd_case(wd, 16, 100.0, 3)], capture_output=True, text=True, cwd=wd, timeout=300)
-    assert r.returncode == 0 and "Multiplying with Geff(a)" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+    r = subprocess.run([ref_lib.exe_path(variant), model_case(wd, variant, 16, 100.0, 3)], capture_output=True, text=True, cwd=wd, timeout=600)
+    assert r.returncode == 0 and marker in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+    assert any(f.startswith("bench_z0p000") for f in os.listdir(os.path.join(wd, "output")))
 
 
 @pytest.mark.gpu
-def test_brans_dicke_driver_matches_cpu_reference(require_gpu, tmp_path):
-    """MODEL = BRANSDICKE (reference Makefile:85-90): the time-dependent G_eff model (ComputeFifthForce_TimeDepGeffModels,
-    mg.h:127-137; MGP_MODEL_GEFF with GeffoverG(a, 0) as the step scalar) and jbd.c's own background through the reference's
-    driver, CUDA library against the unmodified reference."""
+@pytest.mark.parametrize("variant", ["jbd", "mbeta"])
+def test_other_models_driver_matches_cpu_reference(require_gpu, tmp_path, variant):
+    """The two remaining models of the reference Makefile through the reference's driver, CUDA library against the unmodified
+    reference.  MODEL = BRANSDICKE: the time-dependent G_eff (ComputeFifthForce_TimeDepGeffModels, mg.h:127-137; MGP_MODEL_GEFF
+    with GeffoverG(a, 0) as the step scalar) and jbd.c's own background.  MODEL = MBETA: a general (m(a), beta(a)) model, the
+    symmetron, with potential screening (Phi_crit(a) from cosmo.c:125-187, zero before the symmetry breaks) and scale-dependent
+    growth -- the same library path as f(R), other scalars."""
     import os
     import subprocess
     from test_dropin_driver import _exe
@@ -188,7 +200,8 @@ def test_brans_dicke_driver_matches_cpu_reference(require_gpu, tmp_path):
     runs = {}
     for kind in ("cpu", "gpu"):
         wd = str(tmp_path / kind)
-        r = subprocess.run([_exe(kind, "jbd"), jbd_case(wd, N, box, nsteps)], capture_output=True, text=True, cwd=wd, timeout=600)
+        r = subprocess.run([_exe(kind, variant), model_case(wd, variant, N, box, nsteps)], capture_output=True, text=True, cwd=wd,
+                           timeout=900, env=dict(os.environ, MGP_SD_MERGED="0"))
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         runs[kind] = os.path.join(wd, "output")
-    _same_runs(runs["cpu"], runs["gpu"], N, box, nsteps, pk_rel=1e-8)
+    _same_runs(runs["cpu"], runs["gpu"], N, box, nsteps, pk_rel=1e-8 if variant == "jbd" else 1e-6)
