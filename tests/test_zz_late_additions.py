@@ -8,47 +8,6 @@ from oracle import pm_oracle as po
 from test_gpu_parity import OMEGA, make_particles
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("scheme", ["NGP", "CIC", "TSC"])
-def test_simple_pofk_with_npart_different_from_ngrid3(mgp, require_gpu, scheme):
-    """SimplePofk normalises the counts to the density contrast (main.cpp:513-533), so P(k) carries (Ngrid^3 / Npart)^2;
-    the restatement is pinned to the compiled tool for Npart != Ngrid^3 in tests/test_simple_pofk.py."""
-    N, box = 32, 100.0
-    pos, vel, D, D2 = make_particles(N, box, 13, clustered=True)
-    keep = N ** 3 - 9000
-    pm = mgp.PM(N, N, box, omega=OMEGA, grid_bytes=8, sort_particles=0)
-    pm.upload_particles(pos[:keep], vel[:keep], D[:keep], D2[:keep])
-    p, n = pm.simple_pofk(scheme, subtract_shotnoise=True)
-    pr, nr = po.simple_pofk(pos[:keep], N, box, scheme, subtract_shotnoise=True)
-    assert np.array_equal(n, nr)
-    good = nr > 0
-    assert np.abs(p[good] - pr[good]).max() < 1e-10 * np.abs(pr[good]).max()
-    pm.close()
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("variant,model", [("lcdm_ric", "lcdm"), ("fofr_ric", "fofr")])
-def test_readic_driver_matches_cpu_reference(require_gpu, tmp_path, variant, model):
-    """-DREADICFROMFILE builds: the reference's driver reading GADGET particle files, with ReadFilesMakeDisplacementField
-    served by mgp_ic_particles_begin / _add / _finish (adapter/auxPM_cuda.c; the file readers stay readICfromfile.c's),
-    against the unmodified reference on the same files and parameter file: every in-step P(k) file and the final snapshot.
-    (The restatement of this path is pinned to the reference on the CPU in tests/test_readic_oracle.py, the library entry
-    points to the restatement in tests/test_readic.py; this is the whole run through the reference's own main().)"""
-    import os
-    import subprocess
-    from test_dropin_driver import _exe
-    N, box, nsteps = 32, 100.0, 5
-    runs = {}
-    for kind in ("cpu", "gpu"):
-        wd = str(tmp_path / kind)
-        pf = readic_case(wd, N, box, variant, model, nsteps)
-        r = subprocess.run([_exe(kind, variant), pf], capture_output=True, text=True, cwd=wd, timeout=900,
-                           env=dict(os.environ, MGP_SD_MERGED="0"))
-        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-        runs[kind] = os.path.join(wd, "output")
-    _same_runs(runs["cpu"], runs["gpu"], N, box, nsteps)
-
-
 def _same_runs(out_c, out_g, N, box, nsteps, pk_rel=1e-6, tolx=3e-5, tolv=3e-4):
     """Every in-step P(k) file (print resolution + pk_rel) and the final GADGET snapshot (IDs exact, positions in cells)."""
     import os
@@ -70,6 +29,95 @@ def _same_runs(out_c, out_g, N, box, nsteps, pk_rel=1e-6, tolx=3e-5, tolv=3e-4):
     dp = np.minimum(dp, box - dp)
     assert dp.max() < tolx * box / N
     assert np.abs(vc[oc] - vg[og]).max() < tolv * np.abs(vc).max()
+
+
+def readic_case(wd, N, box, variant, model, nsteps):
+    """Two GADGET files of a perturbed lattice and the parameter file of a READICFROMFILE run in `wd`."""
+    import os
+    import bench
+    import test_readic_oracle as tro
+    os.makedirs(wd, exist_ok=True)
+    pbox = (tro._glass(N, 3) * box).astype(np.float32)
+    half = len(pbox) // 3
+    for i, f in enumerate((pbox[:half], pbox[half:])):
+        tro._write_gadget(os.path.join(wd, "part.%d" % i), f, box)
+    tags = ("ReadParticlesFromFile 1\nNumInputParticleFiles 2\nInputParticleFileDir %s\nInputParticleFilePrefix part\n"
+            "RamsesOutputNumber 1\nTypeInputParticleFiles 3\n" % wd)
+    pf = bench.write_paramfile(wd, N, box, model, nsteps, lcdm_growth=0 if variant == "fofr_ric" else 1, extra=tags)
+    txt = open(pf).read().replace("WhichSpectrum 1", "WhichSpectrum 2")            # see tests/test_readic_oracle.py
+    with open(pf, "w") as f:
+        f.write(txt)
+    return pf
+
+
+MODEL_TAGS = {
+    # -DBRANSDICKE: user_defined_functions.h:383-399 reads wBD and the physical densities under the tags Omegah2, Omegar2,
+    # Omegav2; the Hubble parameter follows from G_eff = 1 today (jbd.c)
+    "jbd": "modified_gravity_active 1\nwBD 50.0\nOmegah2 0.1346\nOmegar2 4.2e-5\nOmegav2 0.3695\ninclude_screening 1\n",
+    # -DMBETAMODEL: the symmetron of paramfiles/example_mbeta.txt (user_defined_functions.h:359-371)
+    "mbeta": "modified_gravity_active 1\nassb_symm 0.5\nbeta_symm 1.0\nrange_symm 1.0\ninclude_screening 1\n",
+}
+
+
+def model_case(wd, variant, N, box, nsteps):
+    """Parameter file of a run of one of the two remaining models of the reference Makefile (85-98)."""
+    import bench
+    pf = bench.write_paramfile(wd, N, box, "lcdm", nsteps, lcdm_growth=0 if variant == "mbeta" else 1)
+    txt = open(pf).read()
+    for line in ("modified_gravity_active 0\n", "fofr0 %g\nnfofr %g\n" % (bench.FOFR0, bench.NFOFR), "include_screening 0\n"):
+        txt = txt.replace(line, "")
+    with open(pf, "w") as f:
+        f.write(MODEL_TAGS[variant] + txt)
+    return pf
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scheme", ["NGP", "CIC", "TSC"])
+def test_simple_pofk_with_npart_different_from_ngrid3(mgp, require_gpu, scheme):
+    """SimplePofk normalises the counts to the density contrast (main.cpp:513-533), so P(k) carries (Ngrid^3 / Npart)^2;
+    the restatement is pinned to the compiled tool for Npart != Ngrid^3 in tests/test_simple_pofk.py."""
+    N, box = 32, 100.0
+    pos, vel, D, D2 = make_particles(N, box, 13, clustered=True)
+    keep = N ** 3 - 9000
+    pm = mgp.PM(N, N, box, omega=OMEGA, grid_bytes=8, sort_particles=0)
+    pm.upload_particles(pos[:keep], vel[:keep], D[:keep], D2[:keep])
+    p, n = pm.simple_pofk(scheme, subtract_shotnoise=True)
+    pr, nr = po.simple_pofk(pos[:keep], N, box, scheme, subtract_shotnoise=True)
+    assert np.array_equal(n, nr)
+    good = nr > 0
+    assert np.abs(p[good] - pr[good]).max() < 1e-10 * np.abs(pr[good]).max()
+    pm.close()
+
+
+def test_readic_reference_drivers_run(tmp_path):
+    """CPU half of the driver test above: the unmodified reference reads the files and runs to z = 0 (the SCALEDEPENDENT
+    build's run through the library interface is tests/test_readic_oracle.py)."""
+    import os
+    import subprocess
+    from oracle import ref_lib
+    for variant, model in (("lcdm_ric", "lcdm"),):
+        if not os.path.exists(ref_lib.exe_path(variant)):
+            pytest.skip("oracle/_ref READICFROMFILE build missing")
+        wd = str(tmp_path / variant)
+        pf = readic_case(wd, 16, 100.0, variant, model, 3)
+        r = subprocess.run([ref_lib.exe_path(variant), pf], capture_output=True, text=True, cwd=wd, timeout=600)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        out = os.path.join(wd, "output")
+        assert len([f for f in os.listdir(out) if f.startswith("pofk_")]) >= 3 and any(f.startswith("bench_z0p000") for f in os.listdir(out))
+
+
+@pytest.mark.parametrize("variant,marker", [("jbd", "Multiplying with Geff(a)"), ("mbeta", "Phi_critical")])
+def test_other_models_reference_drivers_run(tmp_path, variant, marker):
+    """CPU half of the test below."""
+    import os
+    import subprocess
+    from oracle import ref_lib
+    if not os.path.exists(ref_lib.exe_path(variant)):
+        pytest.skip("oracle/_ref build of this model missing")
+    wd = str(tmp_path)
+    r = subprocess.run([ref_lib.exe_path(variant), model_case(wd, variant, 16, 100.0, 3)], capture_output=True, text=True, cwd=wd, timeout=600)
+    assert r.returncode == 0 and marker in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+    assert any(f.startswith("bench_z0p000") for f in os.listdir(os.path.join(wd, "output")))
 
 
 @pytest.mark.gpu
@@ -94,42 +142,6 @@ def test_driver_without_cola_matches_cpu_reference(require_gpu, tmp_path):
     _same_runs(runs["cpu"], runs["gpu"], N, box, nsteps, pk_rel=1e-8)
 
 
-def readic_case(wd, N, box, variant, model, nsteps):
-    """Two GADGET files of a perturbed lattice and the parameter file of a READICFROMFILE run in `wd`."""
-    import os
-    import bench
-    import test_readic_oracle as tro
-    os.makedirs(wd, exist_ok=True)
-    pbox = (tro._glass(N, 3) * box).astype(np.float32)
-    half = len(pbox) // 3
-    for i, f in enumerate((pbox[:half], pbox[half:])):
-        tro._write_gadget(os.path.join(wd, "part.%d" % i), f, box)
-    tags = ("ReadParticlesFromFile 1\nNumInputParticleFiles 2\nInputParticleFileDir %s\nInputParticleFilePrefix part\n"
-            "RamsesOutputNumber 1\nTypeInputParticleFiles 3\n" % wd)
-    pf = bench.write_paramfile(wd, N, box, model, nsteps, lcdm_growth=0 if variant == "fofr_ric" else 1, extra=tags)
-    txt = open(pf).read().replace("WhichSpectrum 1", "WhichSpectrum 2")            # see tests/test_readic_oracle.py
-    with open(pf, "w") as f:
-        f.write(txt)
-    return pf
-
-
-def test_readic_reference_drivers_run(tmp_path):
-    """CPU half of the driver test above: the unmodified reference reads the files and runs to z = 0 (the SCALEDEPENDENT
-    build's run through the library interface is tests/test_readic_oracle.py)."""
-    import os
-    import subprocess
-    from oracle import ref_lib
-    for variant, model in (("lcdm_ric", "lcdm"),):
-        if not os.path.exists(ref_lib.exe_path(variant)):
-            pytest.skip("oracle/_ref READICFROMFILE build missing")
-        wd = str(tmp_path / variant)
-        pf = readic_case(wd, 16, 100.0, variant, model, 3)
-        r = subprocess.run([ref_lib.exe_path(variant), pf], capture_output=True, text=True, cwd=wd, timeout=600)
-        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
-        out = os.path.join(wd, "output")
-        assert len([f for f in os.listdir(out) if f.startswith("pofk_")]) >= 3 and any(f.startswith("bench_z0p000") for f in os.listdir(out))
-
-
 @pytest.mark.gpu
 def test_readic_displacements_match_reference(mgp, require_gpu, tmp_path):
     """mgp_ic_particles_* followed by mgp_ic_download against the ZA / LPT arrays of the UNMODIFIED reference
@@ -148,41 +160,6 @@ def test_readic_displacements_match_reference(mgp, require_gpu, tmp_path):
     pm.close()
     assert np.abs(za - ref["ZA"]).max() < 2e-6 * np.abs(ref["ZA"]).max()
     assert np.abs(lpt - ref["LPT"]).max() < 2e-6 * np.abs(ref["LPT"]).max()
-
-
-MODEL_TAGS = {
-    # -DBRANSDICKE: user_defined_functions.h:383-399 reads wBD and the physical densities under the tags Omegah2, Omegar2,
-    # Omegav2; the Hubble parameter follows from G_eff = 1 today (jbd.c)
-    "jbd": "modified_gravity_active 1\nwBD 50.0\nOmegah2 0.1346\nOmegar2 4.2e-5\nOmegav2 0.3695\ninclude_screening 1\n",
-    # -DMBETAMODEL: the symmetron of paramfiles/example_mbeta.txt (user_defined_functions.h:359-371)
-    "mbeta": "modified_gravity_active 1\nassb_symm 0.5\nbeta_symm 1.0\nrange_symm 1.0\ninclude_screening 1\n",
-}
-
-
-def model_case(wd, variant, N, box, nsteps):
-    """Parameter file of a run of one of the two remaining models of the reference Makefile (85-98)."""
-    import bench
-    pf = bench.write_paramfile(wd, N, box, "lcdm", nsteps, lcdm_growth=0 if variant == "mbeta" else 1)
-    txt = open(pf).read()
-    for line in ("modified_gravity_active 0\n", "fofr0 %g\nnfofr %g\n" % (bench.FOFR0, bench.NFOFR), "include_screening 0\n"):
-        txt = txt.replace(line, "")
-    with open(pf, "w") as f:
-        f.write(MODEL_TAGS[variant] + txt)
-    return pf
-
-
-@pytest.mark.parametrize("variant,marker", [("jbd", "Multiplying with Geff(a)"), ("mbeta", "Phi_critical")])
-def test_other_models_reference_drivers_run(tmp_path, variant, marker):
-    """CPU half of the test below."""
-    import os
-    import subprocess
-    from oracle import ref_lib
-    if not os.path.exists(ref_lib.exe_path(variant)):
-        pytest.skip("oracle/_ref build of this model missing")
-    wd = str(tmp_path)
-    r = subprocess.run([ref_lib.exe_path(variant), model_case(wd, variant, 16, 100.0, 3)], capture_output=True, text=True, cwd=wd, timeout=600)
-    assert r.returncode == 0 and marker in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
-    assert any(f.startswith("bench_z0p000") for f in os.listdir(os.path.join(wd, "output")))
 
 
 @pytest.mark.gpu
@@ -205,3 +182,26 @@ def test_other_models_driver_matches_cpu_reference(require_gpu, tmp_path, varian
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         runs[kind] = os.path.join(wd, "output")
     _same_runs(runs["cpu"], runs["gpu"], N, box, nsteps, pk_rel=1e-8 if variant == "jbd" else 1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant,model", [("lcdm_ric", "lcdm"), ("fofr_ric", "fofr")])
+def test_readic_driver_matches_cpu_reference(require_gpu, tmp_path, variant, model):
+    """-DREADICFROMFILE builds: the reference's driver reading GADGET particle files, with ReadFilesMakeDisplacementField
+    served by mgp_ic_particles_begin / _add / _finish (adapter/auxPM_cuda.c; the file readers stay readICfromfile.c's),
+    against the unmodified reference on the same files and parameter file: every in-step P(k) file and the final snapshot.
+    (The restatement of this path is pinned to the reference on the CPU in tests/test_readic_oracle.py, the library entry
+    points to the restatement in tests/test_readic.py; this is the whole run through the reference's own main().)"""
+    import os
+    import subprocess
+    from test_dropin_driver import _exe
+    N, box, nsteps = 32, 100.0, 5
+    runs = {}
+    for kind in ("cpu", "gpu"):
+        wd = str(tmp_path / kind)
+        pf = readic_case(wd, N, box, variant, model, nsteps)
+        r = subprocess.run([_exe(kind, variant), pf], capture_output=True, text=True, cwd=wd, timeout=900,
+                           env=dict(os.environ, MGP_SD_MERGED="0"))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        runs[kind] = os.path.join(wd, "output")
+    _same_runs(runs["cpu"], runs["gpu"], N, box, nsteps)
