@@ -1,6 +1,8 @@
-"""GPU checks written when this round's GPU minutes were all but spent: the same comparisons ran green on B200 in
-tools/quick_check.py (profiles/r02v_quick_check.log), but as pytest items their first run is the driver's round-end
-`-m gpu` pass.  They sit in the last file of the suite so that a surprise here cannot hide anything that has run green."""
+"""GPU checks written when this round's GPU minutes were all but spent; as pytest items their first run is the driver's
+round-end `-m gpu` pass.  They sit in the last file of the suite, most-exercised first, so that a surprise here cannot
+hide anything that has run green.  What already ran: the SimplePofk comparison on B200 in tools/quick_check.py
+(profiles/r02v_quick_check.log); of the others everything that can run on a CPU -- the reference halves of the driver
+runs (below) and the kernels' k-space arithmetic against the reference's arrays (tests/test_readic_oracle.py)."""
 import numpy as np
 import pytest
 
