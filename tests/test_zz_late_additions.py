@@ -22,15 +22,18 @@ def _same_runs(out_c, out_g, N, box, nsteps, pk_rel=1e-6, tolx=3e-5, tolv=3e-4):
         a, b = read_pofk(os.path.join(out_c, f)), read_pofk(os.path.join(out_g, f))
         assert a.shape == b.shape and np.array_equal(a[:, 0], b[:, 0])
         assert np.all(np.abs(a[:, 1] - b[:, 1]) <= 2e-5 + pk_rel * (np.abs(a[:, 1]) + shot)), f
-    snap = [f for f in os.listdir(out_c) if f.startswith("bench_z0p000")]
-    pc, vc, ic = read_gadget(os.path.join(out_c, snap[0]))
-    pg, vg, ig = read_gadget(os.path.join(out_g, snap[0]))
-    oc, og = np.argsort(ic), np.argsort(ig)
-    assert np.array_equal(ic[oc], ig[og]) and np.array_equal(ic[oc], np.arange(N ** 3, dtype=np.uint64))
-    dp = np.abs(pc[oc].astype(np.float64) - pg[og])
-    dp = np.minimum(dp, box - dp)
-    assert dp.max() < tolx * box / N
-    assert np.abs(vc[oc] - vg[og]).max() < tolv * np.abs(vc).max()
+    snaps = sorted(f for f in os.listdir(out_c) if f.startswith("bench_z") and not f.endswith(".txt"))
+    assert snaps and snaps == sorted(f for f in os.listdir(out_g) if f.startswith("bench_z") and not f.endswith(".txt"))
+    for snap in snaps:                                                  # every output redshift
+        pc, vc, ic = read_gadget(os.path.join(out_c, snap))
+        pg, vg, ig = read_gadget(os.path.join(out_g, snap))
+        oc, og = np.argsort(ic), np.argsort(ig)
+        assert np.array_equal(ic[oc], ig[og]) and np.array_equal(ic[oc], np.arange(N ** 3, dtype=np.uint64)), snap
+        dp = np.abs(pc[oc].astype(np.float64) - pg[og])
+        dp = np.minimum(dp, box - dp)
+        assert dp.max() < tolx * box / N, snap
+        assert np.abs(vc[oc] - vg[og]).max() < tolv * np.abs(vc).max(), snap
+    return snaps
 
 
 def readic_case(wd, N, box, variant, model, nsteps):
@@ -207,3 +210,32 @@ def test_readic_driver_matches_cpu_reference(require_gpu, tmp_path, variant, mod
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         runs[kind] = os.path.join(wd, "output")
     _same_runs(runs["cpu"], runs["gpu"], N, box, nsteps)
+
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant,merged", [("lcdm", 0), ("fofr", 0), ("fofr", 1)])
+def test_driver_with_two_outputs_matches_cpu_reference(require_gpu, tmp_path, variant, merged):
+    """Two entries in the output list: after the first snapshot the run goes on, main.c kicks a second time in that step with
+    sumDxyz = 0 and the displacements of the first kick (main.c:562-569), and the SCALEDEPENDENT build replaces the
+    per-particle fields for the output and restores them (main.c:824-832, 1052-1053).  Every other driver test ends at
+    its only output (main.c:545 jumps to `finalize`), so this is the one that runs those lines."""
+    import os
+    import subprocess
+    import bench
+    from test_dropin_driver import _exe
+    N, box = 32, 100.0
+    sd = variant == "fofr"
+    runs = {}
+    for kind in ("cpu", "gpu"):
+        wd = str(tmp_path / kind)
+        pf = bench.write_paramfile(wd, N, box, "fofr", 3, lcdm_growth=0 if sd else 1)
+        with open(os.path.join(wd, "out.dat"), "w") as f:
+            f.write("1.0, 3\n0.0, 3\n")
+        r = subprocess.run([_exe(kind, variant), pf], capture_output=True, text=True, cwd=wd, timeout=900,
+                           env=dict(os.environ, MGP_SD_MERGED=str(merged)))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        runs[kind] = os.path.join(wd, "output")
+    snaps = _same_runs(runs["cpu"], runs["gpu"], N, box, 6, pk_rel=2e-5 if merged else (1e-6 if sd else 1e-8),
+                       tolx=3e-4 if merged else 3e-5, tolv=3e-3 if merged else 3e-4)
+    assert len(snaps) == 2
