@@ -10,11 +10,11 @@ from oracle import pm_oracle as po
 from test_gpu_parity import OMEGA, make_particles
 
 
-def _same_runs(out_c, out_g, N, box, nsteps, pk_rel=1e-6, tolx=3e-5, tolv=3e-4):
+def _same_runs(out_c, out_g, N, box, nsteps, pk_rel=1e-6, tolx=3e-5, tolv=3e-4, nsample=None):
     """Every in-step P(k) file (print resolution + pk_rel) and the final GADGET snapshot (IDs exact, positions in cells)."""
     import os
     from test_dropin_driver import read_gadget, read_pofk
-    shot = (box / N) ** 3
+    shot = (box / (nsample or N)) ** 3
     pk_c = sorted(f for f in os.listdir(out_c) if f.startswith("pofk_") and f.endswith("_CDM.txt"))
     pk_g = sorted(f for f in os.listdir(out_g) if f.startswith("pofk_") and f.endswith("_CDM.txt"))
     assert pk_c == pk_g and len(pk_c) >= nsteps
@@ -28,7 +28,7 @@ def _same_runs(out_c, out_g, N, box, nsteps, pk_rel=1e-6, tolx=3e-5, tolv=3e-4):
         pc, vc, ic = read_gadget(os.path.join(out_c, snap))
         pg, vg, ig = read_gadget(os.path.join(out_g, snap))
         oc, og = np.argsort(ic), np.argsort(ig)
-        assert np.array_equal(ic[oc], ig[og]) and np.array_equal(ic[oc], np.arange(N ** 3, dtype=np.uint64)), snap
+        assert np.array_equal(ic[oc], ig[og]) and np.array_equal(ic[oc], np.arange(ic.size, dtype=np.uint64)), snap
         dp = np.abs(pc[oc].astype(np.float64) - pg[og])
         dp = np.minimum(dp, box - dp)
         assert dp.max() < tolx * box / N, snap
@@ -239,3 +239,29 @@ def test_driver_with_two_outputs_matches_cpu_reference(require_gpu, tmp_path, va
     snaps = _same_runs(runs["cpu"], runs["gpu"], N, box, 6, pk_rel=2e-5 if merged else (1e-6 if sd else 1e-8),
                        tolx=3e-4 if merged else 3e-5, tolv=3e-3 if merged else 3e-4)
     assert len(snaps) == 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["lcdm", "fofr"])
+def test_driver_with_nmesh_twice_nsample_matches_cpu_reference(require_gpu, tmp_path, variant):
+    """Nmesh = 32, Nsample = 16: the mesh finer than the particle lattice (every BASELINE configuration and every other
+    driver test has them equal): initial conditions cut at the particle Nyquist frequency and read out on every second mesh
+    point, W = 8 in the deposit, the particle slabs of initialize_parts (2LPT.c:118-176), the shot noise of P(k)."""
+    import os
+    import subprocess
+    import bench
+    from test_dropin_driver import _exe
+    N, ns, box, nsteps = 32, 16, 100.0, 4
+    sd = variant == "fofr"
+    runs = {}
+    for kind in ("cpu", "gpu"):
+        wd = str(tmp_path / kind)
+        pf = bench.write_paramfile(wd, N, box, "fofr", nsteps, lcdm_growth=0 if sd else 1)
+        txt = open(pf).read().replace("Nsample %d" % N, "Nsample %d" % ns)
+        with open(pf, "w") as f:
+            f.write(txt)
+        r = subprocess.run([_exe(kind, variant), pf], capture_output=True, text=True, cwd=wd, timeout=900,
+                           env=dict(os.environ, MGP_SD_MERGED="0"))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        runs[kind] = os.path.join(wd, "output")
+    _same_runs(runs["cpu"], runs["gpu"], N, box, nsteps, pk_rel=1e-6 if sd else 1e-8, nsample=ns)
